@@ -1,0 +1,296 @@
+/*
+ * otm_b200.h — C-ABI of the B200-native one-to-many-GAN training-step kernels.
+ *
+ * The reference (struan-robertson/one-to-many-gan) has no FFI or plugin boundary:
+ * every GPU op is a PyTorch library call made from src/model/*.py and
+ * src/core/training.py.  This header is the boundary a maintainer would bind instead
+ * (ctypes stub in INTEGRATION.md).  Each entry point names the reference call site it
+ * replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  The CALLER allocates every output
+ *    and workspace (the library never owns device memory).
+ *  - every call only ENQUEUES work on `stream` (no synchronisation, CUDA-graph
+ *    capturable).  One call at a time per stream.
+ *  - return 0 on success, negative otm_status on failure; otm_last_error() returns a
+ *    thread-local message.
+ *  - activations are NHWC "views": channel stride is 1, the n/h/w strides are given in
+ *    ELEMENTS, so an interior view of a halo-padded buffer is a valid tensor.  `halo`
+ *    fields say how many pixels around the view are materialised and readable/writable.
+ *  - dtype: OTM_F32 or OTM_BF16 storage; all arithmetic accumulates in fp32.
+ */
+#ifndef OTM_B200_H
+#define OTM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* otm_stream; /* cudaStream_t */
+
+enum otm_status {
+  OTM_OK = 0,
+  OTM_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  OTM_ERR_CUDA = -2,        /* a CUDA runtime or driver call failed */
+  OTM_ERR_UNSUPPORTED = -3, /* requested path not available for this shape/dtype */
+};
+
+enum otm_dtype { OTM_F32 = 0, OTM_BF16 = 1 };
+enum otm_act { OTM_ACT_NONE = 0, OTM_ACT_RELU = 1, OTM_ACT_LRELU = 2, OTM_ACT_TANH = 3 };
+enum otm_path { OTM_PATH_AUTO = 0, OTM_PATH_SIMT = 1, OTM_PATH_TCGEN05 = 2 };
+
+typedef struct {
+  void* ptr;     /* element (n=0,h=0,w=0,c=0) of the logical view */
+  int32_t dtype; /* otm_dtype */
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw; /* element strides; channel stride is 1 */
+} otm_tensor;
+
+const char* otm_last_error(void);
+int otm_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t otm_launch_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * Convolution (stride 1) as implicit GEMM.
+ * Replaces F.conv2d in EqualisedConv2d.forward (reference src/model/layers.py:82-102)
+ * and the grouped F.conv2d of Conv2dWeightModulate.forward (layers.py:163-168), plus
+ * the cuDNN dgrad/wgrad that autograd runs for both.
+ *
+ *   y[n,h,w,o] = epi( alpha * sum_{r,s,i} x[n, h+r-pad, w+s-pad, i] * wpack[nb][o][r][s][i] )
+ *   epi(v) = act( v * row_scale[n,o] + bias[o] ) + residual[n,h,w,o]
+ *
+ * x positions outside [-x_halo, H+x_halo) x [-x_halo, W+x_halo) read as zero; positions
+ * inside the halo read the materialised halo (e.g. a reflect halo written by a producer).
+ * Output size: y.h = x.h + 2*pad - kh + 1 (same for w).  If y_halo > 0 the epilogue also
+ * writes the REFLECT halo of that width around y (nn.ReflectionPad2d of the consumer,
+ * reference blocks.py:21,25,49,54; builder.py:162,202).
+ * dgrad = the same call on dy with a flipped/transposed pack and pad' = k-1-pad.
+ * --------------------------------------------------------------------------------- */
+typedef struct {
+  otm_tensor x;
+  int32_t x_halo;
+  const void* wpack;      /* [wbatch][Cout][kh][kw][Cin], dtype == x.dtype */
+  int64_t w_batch_stride; /* elements between per-sample packs; 0 = shared weights */
+  int32_t kh, kw, pad;
+  otm_tensor y;
+  int32_t y_halo;
+  float alpha;
+  const float* row_scale; /* [n, Cout] or NULL */
+  const float* bias;      /* [Cout] or NULL */
+  int32_t act;            /* otm_act */
+  otm_tensor residual;    /* ptr NULL = none */
+  int32_t path;           /* otm_path */
+} otm_conv_fwd_args;
+int otm_conv_fwd(const otm_conv_fwd_args* a, otm_stream stream);
+/* 1 if the tcgen05 path would be used for these arguments, 0 if SIMT */
+int otm_conv_fwd_uses_tcgen05(const otm_conv_fwd_args* a);
+
+/* wgrad:  dw[o][i][r][s] (fp32, torch parameter layout [Cout,Cin,kh,kw], ACCUMULATED into)
+ *   += alpha * sum_{n,h,w} rs[n,o] * cs[n,i] * dy[n,h,w,o] * x[n, h+r-pad, w+s-pad, i]
+ * rs / cs (per-sample demodulation / modulation factors, reference layers.py:148-161)
+ * may be NULL.  x obeys the same halo/zero rule as the forward. */
+typedef struct {
+  otm_tensor x;
+  int32_t x_halo;
+  otm_tensor dy;
+  int32_t kh, kw, pad;
+  float* dw;
+  float alpha;
+  const float* rs; /* [n, Cout] or NULL */
+  const float* cs; /* [n, Cin] or NULL */
+  int32_t path;
+} otm_conv_wgrad_args;
+int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream);
+int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a);
+
+/* Weight staging.  Replaces EqualisedWeight.forward (layers.py:23-24) and the per-sample
+ * `weights * s` materialisation (layers.py:152-161).
+ *   transpose == 0: out[b][o][r][s][i]           = alpha * w[o][i][r][s] * cs[b,i] * rs[b,o]
+ *   transpose == 1: out[b][i][kh-1-r][kw-1-s][o] = same value          (dgrad pack)
+ * cs / rs may be NULL (factor 1); nb = number of per-sample packs (1 = shared). */
+typedef struct {
+  const float* w; /* [Cout, Cin, kh, kw] */
+  int32_t cout, cin, kh, kw;
+  float alpha;
+  const float* cs; /* [nb, Cin] or NULL */
+  const float* rs; /* [nb, Cout] or NULL */
+  int32_t nb;
+  int32_t transpose;
+  void* out;
+  int32_t out_dtype;
+} otm_weight_pack_args;
+int otm_weight_pack(const otm_weight_pack_args* a, otm_stream stream);
+
+/* q[o,i] = sum_k (alpha*w[o,i,k])^2   (layers.py:156-158, dense form SURVEY App. B.2) */
+int otm_weight_sqsum(const float* w, int32_t cout, int32_t cin, int32_t taps, float alpha,
+                     float* q, otm_stream stream);
+/* sigma_inv[b,o] = rsqrt(sum_i s[b,i]^2 q[o,i] + eps) */
+int otm_demod(const float* s, const float* q, int32_t nb, int32_t cout, int32_t cin, float eps,
+              float* sigma_inv, otm_stream stream);
+/* Backward of the modulation coefficients given P[b,o] = sum_hw dy*y and
+ * Q[b,i] = sum_hw dxt*x:
+ *   dd[b,o] = -0.5 * sigma_inv^2 * P ;  ds[b,i] = Q[b,i] + 2 s[b,i] sum_o dd[b,o] q[o,i]
+ *   dw[o,i,k] += 2 * alpha^2 * w[o,i,k] * sum_b dd[b,o] s[b,i]^2 */
+typedef struct {
+  const float* w;
+  int32_t cout, cin, taps;
+  float alpha;
+  const float* s;
+  const float* sigma_inv;
+  const float* q;
+  const float* P;
+  const float* Q;
+  int32_t nb;
+  float* ds; /* [nb, Cin] written */
+  float* dw; /* [Cout,Cin,taps] accumulated */
+} otm_mod_bwd_args;
+int otm_mod_bwd(const otm_mod_bwd_args* a, otm_stream stream);
+
+/* ---------------------------------------------------------------------------------
+ * Instance norm / activation / padding passes (HBM-bound).
+ * Replace nn.InstanceNorm2d (eps 1e-5, biased variance), ReLU / LeakyReLU(0.2) / Tanh,
+ * nn.ReflectionPad2d and the residual adds of reference blocks.py:20-33 and
+ * builder.py:161-176,268-284.
+ * --------------------------------------------------------------------------------- */
+/* stats[n,c,0..1] = (mean, rstd) over h*w of x.  ws: fp32 workspace [n*c*2], zeroed here. */
+int otm_instnorm_stats(const otm_tensor* x, float eps, float* ws, float* stats,
+                       otm_stream stream);
+/* y = act((x - mean) * rstd) + residual, optional reflect halo of width y_halo around y.
+ * stats NULL = no normalisation. */
+typedef struct {
+  otm_tensor x;
+  const float* stats;
+  int32_t act;
+  otm_tensor residual; /* ptr NULL = none */
+  otm_tensor y;
+  int32_t y_halo;
+} otm_norm_act_args;
+int otm_norm_act(const otm_norm_act_args* a, otm_stream stream);
+
+/* Backward of otm_norm_act.  g is the gradient w.r.t. y; when g_halo > 0 it is the
+ * gradient w.r.t. the reflect-padded y (size +2*g_halo) and is folded back on load.
+ *   ga  = fold(g) [+ g2]                (optional second gradient source, interior size)
+ *   gn  = ga * act'(.)                   gres = ga (written if gres.ptr != NULL)
+ *   gx  = rstd * (gn - mean_hw(gn) - yhat * mean_hw(gn*yhat))       (stats != NULL)
+ * sums: fp32 workspace [n*c*2]. */
+typedef struct {
+  otm_tensor g;
+  int32_t g_halo;
+  otm_tensor g2; /* ptr NULL = none */
+  otm_tensor x;  /* forward input (pre-norm) */
+  const float* stats;
+  int32_t act;
+  otm_tensor gx;
+  otm_tensor gres; /* ptr NULL = none */
+  float* sums;
+} otm_norm_act_bwd_args;
+int otm_norm_act_bwd(const otm_norm_act_bwd_args* a, otm_stream stream);
+
+/* ---------------------------------------------------------------------------------
+ * Resampling stencils.  Replace Smooth / UpSample / DownSample
+ * (reference layers.py:191-247): replicate-pad 3x3 binomial blur, bilinear x2
+ * (align_corners=False) and bilinear to (H//2, W//2) with scale H/(H//2).
+ * otm_down fuses the producer's normalise+activation in front of the stencil.
+ * --------------------------------------------------------------------------------- */
+typedef struct {
+  otm_tensor x;
+  const float* stats; /* NULL = none */
+  int32_t act;
+  otm_tensor y; /* [n, H/2, W/2, c] */
+  int32_t y_halo;
+} otm_down_args;
+int otm_down(const otm_down_args* a, otm_stream stream);
+/* ga[n,H,W,c] = transpose(stencil)(g);  g_halo folds a reflect-padded g first. */
+int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_stream stream);
+int otm_up(const otm_tensor* x, const otm_tensor* y, int32_t y_halo, otm_stream stream);
+int otm_up_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* gx, otm_stream stream);
+
+/* ---------------------------------------------------------------------------------
+ * Modulated-conv side passes (HBM-bound).  SURVEY App. B.2.
+ * --------------------------------------------------------------------------------- */
+/* out side:  gy = fold(g)[+g2] * act'(out) ;  P[n,o] += sum_hw gy * (out - res)
+ * (out is the saved conv output AFTER activation/residual; act in {NONE, RELU}) */
+typedef struct {
+  otm_tensor g;
+  int32_t g_halo;
+  otm_tensor g2;
+  otm_tensor out;
+  otm_tensor res; /* ptr NULL = none */
+  int32_t act;
+  otm_tensor gy; /* ptr NULL = do not materialise (act NONE, no fold, no g2) */
+  float* P;      /* [n, c] zeroed here then accumulated */
+} otm_mod_out_args;
+int otm_mod_out(const otm_mod_out_args* a, otm_stream stream);
+/* in side:  gxt = fold(g_padded) ; Q[n,i] = sum_hw gxt * x ; gx = s[n,i] * gxt [+ gadd] */
+typedef struct {
+  otm_tensor g;
+  int32_t g_halo;
+  otm_tensor x;
+  const float* s; /* [n, c] */
+  otm_tensor gadd; /* ptr NULL = none */
+  otm_tensor gx;
+  float* Q; /* [n, c] zeroed here then accumulated */
+} otm_mod_in_args;
+int otm_mod_in(const otm_mod_in_args* a, otm_stream stream);
+
+/* per-channel sum over n,h,w of fold(g): bias gradients (dy -> db[c]); out zeroed here */
+int otm_channel_sum(const otm_tensor* g, float* out, otm_stream stream);
+/* global average pool fwd/bwd (StyleExtractor head, builder.py:314) */
+int otm_avgpool(const otm_tensor* x, float* out /*[n,c] fp32*/, otm_stream stream);
+int otm_avgpool_bwd(const float* g /*[n,c]*/, const otm_tensor* gx, otm_stream stream);
+
+/* ---------------------------------------------------------------------------------
+ * Losses (reference src/core/training.py:111-117,178-190,202-204; src/model/loss.py).
+ * Every call writes its scalar(s) to `out` (fp32, device) and, when grad.ptr != NULL,
+ * the backward seed d(scale*loss)/dx in the same pass.
+ * --------------------------------------------------------------------------------- */
+/* out[0] = mean((x - target)^2); out[1] = mean(sign(2x-1));  grad = scale*2(x-target)/N */
+int otm_loss_lsgan(const otm_tensor* x, float target, float scale, float* out,
+                   const otm_tensor* grad, otm_stream stream);
+/* out[0] = mean|a-b| ; grad = scale*sign(a-b)/N (w.r.t. a) */
+int otm_loss_l1(const otm_tensor* a, const otm_tensor* b, float scale, float* out,
+                const otm_tensor* grad, otm_stream stream);
+/* moments: out[0] = sum x, out[1] = sum x^2 over the whole tensor (kl_loss_func, loss.py:82-92) */
+int otm_moments(const otm_tensor* x, float* out, otm_stream stream);
+/* grad[...] (+)= coef[0] + coef[1]*x   (device-side coefficients; KL backward) */
+int otm_affine_grad(const otm_tensor* x, const float* coef, const otm_tensor* grad,
+                    int32_t accumulate, otm_stream stream);
+/* path_loss_func (loss.py:98-111) for one feature pair:
+ *   out[0] += weight * mean(((f1-f2)/h[n])^2) ; g1 = scale*weight*2(f1-f2)/(h^2 N), g2 = -g1 */
+int otm_loss_path(const otm_tensor* f1, const otm_tensor* f2, const float* h, float weight,
+                  float scale, float* out, const otm_tensor* g1, const otm_tensor* g2,
+                  otm_stream stream);
+
+/* ---------------------------------------------------------------------------------
+ * Optimiser and data.
+ * --------------------------------------------------------------------------------- */
+/* torch.optim.Adam defaults (reference train.py:94-116) over a flat fp32 arena.
+ * `step` is read from the device (int32) so the call is graph-replayable; grad is
+ * multiplied by grad_scale first (1/world for DDP). */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* m;
+  float* v;
+  int64_t n;
+  float lr, beta1, beta2, eps, grad_scale;
+  const int32_t* step; /* device pointer to the 1-based step count */
+} otm_adam_args;
+int otm_adam(const otm_adam_args* a, otm_stream stream);
+
+/* Synthetic U(-1,1) batch (replaces src/data/datasets.py + DataLoader, train.py:120-169)
+ * Philox4x32-10 keyed by (seed, stream_id), counter = offset + element index. */
+int otm_synth_uniform(float* out, int64_t n, uint64_t seed, uint64_t stream_id,
+                      uint64_t offset, otm_stream stream);
+
+/* generic helpers */
+int otm_cast(const otm_tensor* x, const otm_tensor* y, otm_stream stream); /* dtype/stride copy */
+int otm_add_inplace(const otm_tensor* dst, const otm_tensor* src, otm_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTM_B200_H */

@@ -1,0 +1,696 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+// Forward and dgrad (same kernel, dgrad = flipped/transposed weight pack):
+//   GEMM  M = 128 output pixels (a TH x TW rectangle of one image), N = BN output channels,
+//         K = kh*kw*Cin walked as (filter tap, 64-channel chunk).
+//   A operand: one 4-D TMA box {64 ch, TW, TH, 1} per (tap, chunk) straight out of the NHWC
+//         activation (halo included in the tensor map; TMA zero-fills out-of-bounds = the
+//         conv's zero padding) -> 128 rows x 128 B, SWIZZLE_128B = UMMA K-major canonical.
+//   B operand: 2-D TMA box {64 k, BN rows} of the packed weights [Cout][kh][kw][Cin].
+//   D: fp32 accumulator in TMEM (BN columns x 128 lanes), read back with tcgen05.ld by four
+//      epilogue warps which apply alpha, demodulation row-scale, bias, activation, residual
+//      and write bf16 NHWC (plus the reflect halo the consumer conv needs).
+// Wgrad:
+//   GEMM  M = 128 (Cout or Cin), N = BN (the other), K = output pixels of one sample chunk.
+//   Both operands are MN-major (channels contiguous, pixel = K strided): the same TMA boxes
+//   ({64 ch, 8, 8, 1} = 64 pixels x 128 B) read through MN-major SWIZZLE_128B descriptors.
+//   Split-K over (sample, pixel chunk); the epilogue applies the per-sample modulation
+//   factors rs[n,o]*cs[n,i] and reduces into the fp32 weight gradient with red.global.add.
+//
+// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected lane),
+// warp2 = TMEM allocator, warps4-7 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace otm {
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------
+// forward / dgrad kernel
+// ---------------------------------------------------------------------------
+struct TcFwdP {
+  View y, res;
+  const float* row_scale;
+  const float* bias;
+  float alpha;
+  int act, y_halo;
+  int cin, cout, kh, kw;
+  int coord_off;  // x_halo - pad : added to (h0 + r), (w0 + s) to index the halo'd tensor map
+  int TW, TH, tiles_w;
+  int w_rows_per_sample;  // cout if per-sample packs else 0
+};
+
+constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
+
+template <int BN>
+__device__ __forceinline__ void epilogue_store16(const TcFwdP& p, int n, int oh, int ow, int o,
+                                                 float (&v)[16]) {
+  if (p.row_scale) {
+    const float4* rs = reinterpret_cast<const float4*>(p.row_scale + (long long)n * p.cout + o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 t = rs[q];
+      v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+    }
+  }
+  if (p.bias) {
+    const float4* bs = reinterpret_cast<const float4*>(p.bias + o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 t = bs[q];
+      v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = act_fwd(v[i], p.act);
+  if (p.res.ptr) {
+    const __nv_bfloat16* rp = vptr<__nv_bfloat16>(p.res, n, oh, ow, o);
+    float r0[8], r1[8];
+    load_vec<__nv_bfloat16, 8>(rp, r0);
+    load_vec<__nv_bfloat16, 8>(rp + 8, r1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] += r0[i]; v[8 + i] += r1[i]; }
+  }
+  float lo[8], hi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+  int hs[3], ws[3];
+  int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
+  int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
+  for (int a = 0; a < nh; ++a)
+    for (int b = 0; b < nw; ++b) {
+      __nv_bfloat16* yp = vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o);
+      store_vec<__nv_bfloat16, 8>(yp, lo);
+      store_vec<__nv_bfloat16, 8>(yp + 8, hi);
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   TcFwdP p) {
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* accum_full = bars + 2 * STAGES;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n = blockIdx.z;
+  const int tile = blockIdx.x;
+  const int h0 = (tile / p.tiles_w) * p.TH, w0 = (tile % p.tiles_w) * p.TW;
+  const int o0 = blockIdx.y * BN;
+  const int cin_chunks = p.cin / 64;
+  const int num_k = p.kh * p.kw * cin_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<BN>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    const int wrow = n * p.w_rows_per_sample + o0;
+    for (int it = 0; it < num_k; ++it) {
+      const int stage = it % STAGES;
+      const uint32_t parity = ((it / STAGES) & 1) ^ 1;
+      mbar_wait(smem_u32(&empty[stage]), parity);
+      if (lane == 0) {
+        const int tap = it / cin_chunks, cc = it - tap * cin_chunks;
+        const int r = tap / p.kw, s = tap - r * p.kw;
+        const uint32_t bar = smem_u32(&full[stage]);
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        mbar_expect_tx(bar, STAGE_BYTES);
+        tma_load_4d(sa, &tmA, bar, cc * 64, w0 + s + p.coord_off, h0 + r + p.coord_off, n);
+        tma_load_2d(sa + A_STAGE_BYTES, &tmB, bar, tap * p.cin + cc * 64, wrow);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    for (int it = 0; it < num_k; ++it) {
+      const int stage = it % STAGES;
+      const uint32_t parity = (it / STAGES) & 1;
+      mbar_wait(smem_u32(&full[stage]), parity);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t da = make_desc(sa, 16, 1024);
+        const uint64_t db = make_desc(sa + A_STAGE_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 4 x (K=16 bf16 = 32 B) per 128-B swizzled row
+          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                    (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(smem_u32(&empty[stage]));
+        if (it == num_k - 1) umma_commit(smem_u32(accum_full));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int wq = warp - 4;
+    mbar_wait(smem_u32(accum_full), 0);
+    tc_fence_after();
+    const int m = wq * 32 + lane;
+    const int oh = h0 + m / p.TW, ow = w0 + m % p.TW;
+    const bool valid = (oh < p.y.h) && (ow < p.y.w);
+#pragma unroll 1
+    for (int j = 0; j < BN / 16; ++j) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+        epilogue_store16<BN>(p, n, oh, ow, o0 + j * 16, v);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// wgrad kernel
+// ---------------------------------------------------------------------------
+struct TcWgP {
+  float* dw;
+  const float* rs;
+  const float* cs;
+  float alpha;
+  int cin, cout, kh, kw;
+  int a_is_x;        // 1: M side = x (Cin), N side = dy (Cout); 0: M = dy, N = x
+  int x_coord_off;   // x_halo - pad
+  int tiles_w, tiles_total, splits;
+  int n_tiles_n;     // number of N tiles (grid.y = m_tiles * n_tiles_n)
+};
+
+constexpr int WG_CHUNK_BYTES = 64 * 128;  // 64 pixels x 64 channels bf16
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmB, TcWgP p) {
+  constexpr int A_BYTES = 2 * WG_CHUNK_BYTES;
+  constexpr int B_BYTES = (BN / 64) * WG_CHUNK_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* accum_full = bars + 2 * STAGES;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int tap = blockIdx.x;
+  const int r = tap / p.kw, s = tap - r * p.kw;
+  const int mt = blockIdx.y / p.n_tiles_n, nt = blockIdx.y % p.n_tiles_n;
+  const int m0 = mt * 128, n0 = nt * BN;
+  const int n = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int t_beg = (int)((long long)p.tiles_total * split / p.splits);
+  const int t_end = (int)((long long)p.tiles_total * (split + 1) / p.splits);
+  const int num_k = t_end - t_beg;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int st = 0; st < STAGES; ++st) {
+      mbar_init(smem_u32(&full[st]), 1);
+      mbar_init(smem_u32(&empty[st]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<BN>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      const int sh_a = p.a_is_x ? (r + p.x_coord_off) : 0, sw_a = p.a_is_x ? (s + p.x_coord_off) : 0;
+      const int sh_b = p.a_is_x ? 0 : (r + p.x_coord_off), sw_b = p.a_is_x ? 0 : (s + p.x_coord_off);
+      for (int it = 0; it < num_k; ++it) {
+        const int stage = it % STAGES;
+        const uint32_t parity = ((it / STAGES) & 1) ^ 1;
+        mbar_wait(smem_u32(&empty[stage]), parity);
+        if (lane == 0) {
+          const int t = t_beg + it;
+          const int h0 = (t / p.tiles_w) * 8, w0 = (t % p.tiles_w) * 8;
+          const uint32_t bar = smem_u32(&full[stage]);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            tma_load_4d(sa + c * WG_CHUNK_BYTES, &tmA, bar, m0 + c * 64, w0 + sw_a, h0 + sh_a, n);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_4d(sa + A_BYTES + c * WG_CHUNK_BYTES, &tmB, bar, n0 + c * 64, w0 + sw_b,
+                        h0 + sh_b, n);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+      for (int it = 0; it < num_k; ++it) {
+        const int stage = it % STAGES;
+        const uint32_t parity = (it / STAGES) & 1;
+        mbar_wait(smem_u32(&full[stage]), parity);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          // MN-major SW128: LBO = stride between 64-channel chunks, SBO = 8 pixel rows (1024 B)
+          const uint64_t da = make_desc(sa, WG_CHUNK_BYTES, 1024);
+          const uint64_t db = make_desc(sa + A_BYTES, WG_CHUNK_BYTES, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 16 pixels (K) = 2048 B per step
+            umma_bf16(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc,
+                      (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&empty[stage]));
+          if (it == num_k - 1) umma_commit(smem_u32(accum_full));
+        }
+        __syncwarp();
+      }
+    } else if (warp >= 4) {
+      const int wq = warp - 4;
+      mbar_wait(smem_u32(accum_full), 0);
+      tc_fence_after();
+      const int m = m0 + wq * 32 + lane;
+      const int taps = p.kh * p.kw;
+      // row factor
+      float rowf = p.alpha;
+      if (p.a_is_x) { if (p.cs) rowf *= p.cs[(long long)n * p.cin + m]; }
+      else { if (p.rs) rowf *= p.rs[(long long)n * p.cout + m]; }
+#pragma unroll 1
+      for (int j = 0; j < BN / 16; ++j) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int nn = n0 + j * 16 + i;
+          float colf = 1.f;
+          int o, ci;
+          if (p.a_is_x) { ci = m; o = nn; if (p.rs) colf = p.rs[(long long)n * p.cout + o]; }
+          else { o = m; ci = nn; if (p.cs) colf = p.cs[(long long)n * p.cin + ci]; }
+          atomicAdd(p.dw + ((long long)o * p.cin + ci) * taps + tap, v[i] * rowf * colf);
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 4-D map over an NHWC bf16 view including `halo` pixels on every side
+static int make_act_map(CUtensorMap* map, const otm_tensor& t, int halo, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(OTM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  char* base = (char*)t.ptr - (long long)halo * (t.sh + t.sw) * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)t.c, (cuuint64_t)(t.w + 2 * halo), (cuuint64_t)(t.h + 2 * halo),
+                        (cuuint64_t)t.n};
+  cuuint64_t strides[3] = {(cuuint64_t)t.sw * 2, (cuuint64_t)t.sh * 2, (cuuint64_t)t.sn * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(OTM_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d (c=%d w=%d h=%d n=%d)", (int)r,
+                t.c, t.w, t.h, t.n);
+  return OTM_OK;
+}
+
+static int make_weight_map(CUtensorMap* map, const void* w, long long rows, long long ktot,
+                           int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(OTM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OTM_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return OTM_OK;
+}
+
+static bool act_tma_ok(const otm_tensor& t) {
+  return t.dtype == OTM_BF16 && t.c % 64 == 0 && t.sw % 8 == 0 && t.sh % 8 == 0 && t.sn % 8 == 0 &&
+         ((uintptr_t)t.ptr % 16 == 0);
+}
+
+bool conv_fwd_tc_eligible(const otm_conv_fwd_args* a) {
+  if (!act_tma_ok(a->x) || a->y.dtype != OTM_BF16) return false;
+  if (a->y.c % 64 != 0 || a->y.sw % 8 || a->y.sh % 8 || a->y.sn % 8) return false;
+  if ((uintptr_t)a->y.ptr % 16 || (uintptr_t)a->wpack % 16) return false;
+  if (a->w_batch_stride != 0 && a->w_batch_stride != (long long)a->y.c * a->kh * a->kw * a->x.c)
+    return false;
+  if (a->residual.ptr && (a->residual.dtype != OTM_BF16 || a->residual.sw % 8 ||
+                          a->residual.sh % 8 || a->residual.sn % 8 ||
+                          (uintptr_t)a->residual.ptr % 16))
+    return false;
+  return true;
+}
+
+template <int BN, int STAGES>
+static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcFwdP& p, dim3 grid,
+                      cudaStream_t st) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + 1024 + 256;
+  auto kern = conv_tc_fwd_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<grid, 256, smem, st>>>(tmA, tmB, p);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
+int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
+  const int Ho = a->y.h, Wo = a->y.w, cout = a->y.c, cin = a->x.c;
+  // pixel tile shape: 128 = TW x TH, minimise the number of tiles (ties -> squarer)
+  int best_tw = 16, best_tiles = 1 << 30;
+  const int cand[5] = {16, 32, 8, 64, 128};
+  for (int i = 0; i < 5; ++i) {
+    int tw = cand[i], th = 128 / tw;
+    int tiles = ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+    if (tiles < best_tiles) { best_tiles = tiles; best_tw = tw; }
+  }
+  const int TW = best_tw, TH = 128 / TW;
+  int BN = 128;
+  if (cout % 128 != 0) BN = 64;
+  else if (cout % 256 == 0 && (long long)best_tiles * a->y.n * (cout / 256) >= 2 * num_sms()) BN = 256;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_act_map(&tmA, a->x, a->x_halo, TW, TH);
+  if (rc) return rc;
+  const long long ktot = (long long)a->kh * a->kw * cin;
+  const long long rows = (a->w_batch_stride ? (long long)a->x.n : 1) * cout;
+  rc = make_weight_map(&tmB, a->wpack, rows, ktot, BN);
+  if (rc) return rc;
+
+  TcFwdP p;
+  p.y = make_view(a->y);
+  p.res = a->residual.ptr ? make_view(a->residual) : null_view();
+  p.row_scale = a->row_scale; p.bias = a->bias; p.alpha = a->alpha; p.act = a->act;
+  p.y_halo = a->y_halo; p.cin = cin; p.cout = cout; p.kh = a->kh; p.kw = a->kw;
+  p.coord_off = a->x_halo - a->pad;
+  p.TW = TW; p.TH = TH; p.tiles_w = (Wo + TW - 1) / TW;
+  p.w_rows_per_sample = a->w_batch_stride ? cout : 0;
+  dim3 grid(best_tiles, cout / BN, a->y.n);
+  if (BN == 64) return launch_fwd<64, 6>(tmA, tmB, p, grid, st);
+  if (BN == 128) return launch_fwd<128, 6>(tmA, tmB, p, grid, st);
+  return launch_fwd<256, 4>(tmA, tmB, p, grid, st);
+}
+
+bool conv_wgrad_tc_eligible(const otm_conv_wgrad_args* a) {
+  if (!act_tma_ok(a->x) || !act_tma_ok(a->dy)) return false;
+  const int cin = a->x.c, cout = a->dy.c;
+  if (cout % 128 != 0 && cin % 128 != 0) return false;
+  return true;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcWgP& p, dim3 grid,
+                        cudaStream_t st) {
+  constexpr int smem = STAGES * (2 * WG_CHUNK_BYTES + (BN / 64) * WG_CHUNK_BYTES) + 1024 + 256;
+  auto kern = conv_tc_wgrad_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<grid, 256, smem, st>>>(tmA, tmB, p);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
+int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
+  const int cin = a->x.c, cout = a->dy.c;
+  TcWgP p;
+  p.dw = a->dw; p.rs = a->rs; p.cs = a->cs; p.alpha = a->alpha;
+  p.cin = cin; p.cout = cout; p.kh = a->kh; p.kw = a->kw;
+  p.a_is_x = (cout % 128 != 0) ? 1 : 0;
+  p.x_coord_off = a->x_halo - a->pad;
+  const int M = p.a_is_x ? cin : cout, N = p.a_is_x ? cout : cin;
+  int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  const int Ho = a->dy.h, Wo = a->dy.w;
+  p.tiles_w = (Wo + 7) / 8;
+  p.tiles_total = p.tiles_w * ((Ho + 7) / 8);
+  const int taps = a->kh * a->kw;
+  const int m_tiles = M / 128;
+  p.n_tiles_n = N / BN;
+  long long base = (long long)taps * m_tiles * p.n_tiles_n * a->dy.n;
+  int splits = (int)((2LL * num_sms() + base - 1) / base);
+  int max_splits = (p.tiles_total + 15) / 16;  // keep >= 16 K-stages per CTA when possible
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  OTM_REQUIRE((long long)a->dy.n * splits <= 65535, "wgrad_tc: grid.z too large");
+
+  CUtensorMap tmX, tmDy;
+  int rc = make_act_map(&tmX, a->x, a->x_halo, 8, 8);
+  if (rc) return rc;
+  rc = make_act_map(&tmDy, a->dy, 0, 8, 8);
+  if (rc) return rc;
+  const CUtensorMap& tmA = p.a_is_x ? tmX : tmDy;
+  const CUtensorMap& tmB = p.a_is_x ? tmDy : tmX;
+  dim3 grid(taps, m_tiles * p.n_tiles_n, a->dy.n * splits);
+  if (BN == 64) return launch_wgrad<64, 6>(tmA, tmB, p, grid, st);
+  if (BN == 128) return launch_wgrad<128, 6>(tmA, tmB, p, grid, st);
+  return launch_wgrad<256, 4>(tmA, tmB, p, grid, st);
+}
+
+int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st);
+int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st);
+
+static int validate_fwd(const otm_conv_fwd_args* a) {
+  OTM_REQUIRE(a && a->x.ptr && a->y.ptr && a->wpack, "conv_fwd: null argument");
+  OTM_REQUIRE(a->kh >= 1 && a->kw >= 1 && a->pad >= 0 && a->x_halo >= 0 && a->y_halo >= 0,
+              "conv_fwd: bad geometry");
+  OTM_REQUIRE(a->y.h == a->x.h + 2 * a->pad - a->kh + 1 && a->y.w == a->x.w + 2 * a->pad - a->kw + 1,
+              "conv_fwd: output %dx%d does not match input %dx%d k=%dx%d pad=%d", a->y.h, a->y.w,
+              a->x.h, a->x.w, a->kh, a->kw, a->pad);
+  OTM_REQUIRE(a->y.n == a->x.n, "conv_fwd: batch mismatch");
+  OTM_REQUIRE(a->x_halo <= a->pad, "conv_fwd: x_halo (%d) larger than pad (%d)", a->x_halo, a->pad);
+  OTM_REQUIRE(a->y_halo == 0 || (a->y_halo < a->y.h && a->y_halo < a->y.w),
+              "conv_fwd: reflect halo too large");
+  if (a->residual.ptr)
+    OTM_REQUIRE(a->residual.n == a->y.n && a->residual.h == a->y.h && a->residual.w == a->y.w &&
+                    a->residual.c == a->y.c && a->residual.dtype == a->y.dtype,
+                "conv_fwd: residual mismatch");
+  return OTM_OK;
+}
+
+}  // namespace otm
+
+using namespace otm;
+
+extern "C" {
+
+int otm_conv_fwd_uses_tcgen05(const otm_conv_fwd_args* a) {
+  if (!a || a->path == OTM_PATH_SIMT) return 0;
+  return conv_fwd_tc_eligible(a) ? 1 : 0;
+}
+
+int otm_conv_fwd(const otm_conv_fwd_args* a, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = validate_fwd(a);
+  if (rc) return rc;
+  const bool tc = conv_fwd_tc_eligible(a);
+  if (a->path == OTM_PATH_TCGEN05 && !tc)
+    return fail(OTM_ERR_UNSUPPORTED, "conv_fwd: tcgen05 path not available for this shape/dtype");
+  if (tc && a->path != OTM_PATH_SIMT) return conv_fwd_tc(a, st);
+  return conv_fwd_simt(a, st);
+}
+
+int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a) {
+  if (!a || a->path == OTM_PATH_SIMT) return 0;
+  return conv_wgrad_tc_eligible(a) ? 1 : 0;
+}
+
+int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(a && a->x.ptr && a->dy.ptr && a->dw, "conv_wgrad: null argument");
+  OTM_REQUIRE(a->dy.h == a->x.h + 2 * a->pad - a->kh + 1 && a->dy.w == a->x.w + 2 * a->pad - a->kw + 1 &&
+                  a->dy.n == a->x.n,
+              "conv_wgrad: dy %dx%d does not match x %dx%d k=%d pad=%d", a->dy.h, a->dy.w, a->x.h,
+              a->x.w, a->kh, a->pad);
+  OTM_REQUIRE(a->x.dtype == a->dy.dtype, "conv_wgrad: dtype mismatch");
+  OTM_REQUIRE(a->x_halo <= a->pad, "conv_wgrad: x_halo larger than pad");
+  const bool tc = conv_wgrad_tc_eligible(a);
+  if (a->path == OTM_PATH_TCGEN05 && !tc)
+    return fail(OTM_ERR_UNSUPPORTED, "conv_wgrad: tcgen05 path not available for this shape/dtype");
+  if (tc && a->path != OTM_PATH_SIMT) return conv_wgrad_tc(a, st);
+  return conv_wgrad_simt(a, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,829 @@
+// HBM-bound passes: instance-norm statistics/apply, activations, reflect halos, the
+// blur/bilinear resampling stencils and the modulated-conv side reductions.
+// All kernels use channel-vector (8-wide, 128-bit for bf16) NHWC access when the
+// tensors allow it and fall back to scalar access for C==1 images.
+#include "common.cuh"
+
+namespace otm {
+
+thread_local char g_err[512] = {0};
+std::atomic<int64_t> g_launches{0};
+
+static inline int ew_grid(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------
+// generic element-wise driver: F::operator()(n,h,w,c0)
+// ---------------------------------------------------------------------------
+template <int V, typename F>
+__global__ void __launch_bounds__(256) ew_kernel(F f, int N, int H, int W, int C) {
+  const int CV = C / V;
+  const long long total = (long long)N * H * W * CV;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    long long p = idx / CV;
+    int w = (int)(p % W);
+    p /= W;
+    int h = (int)(p % H);
+    int n = (int)(p / H);
+    f(n, h, w, cv * V);
+  }
+}
+
+template <int V, typename F>
+static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
+  long long total = (long long)N * H * W * (C / V);
+  if (total == 0) return OTM_OK;
+  ew_kernel<V, F><<<ew_grid(total, 256), 256, 0, st>>>(f, N, H, W, C);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// generic per-(n,c) reduction driver.
+//   F::NQ quantities; F::operator()(n,h,w,c0, acc[NQ][V]) accumulates (and may write
+//   element-wise outputs); F::out_index(n,c,q) gives the atomicAdd target.
+// grid = (pixel chunks, 1, N), 256 threads = lanes (channel vectors) x rows (pixels).
+// ---------------------------------------------------------------------------
+template <int V, typename F>
+__global__ void __launch_bounds__(256) nc_reduce_kernel(F f, int H, int W, int C, int lanes,
+                                                        int pix_per_cta, float* out) {
+  constexpr int NQ = F::NQ;
+  __shared__ float red[256 * NQ * V];
+  const int CV = C / V;
+  const int rows = 256 / lanes;
+  const int lane = threadIdx.x % lanes;
+  const int row = threadIdx.x / lanes;
+  const int n = blockIdx.z;
+  const int HW = H * W;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  for (int cv0 = 0; cv0 < CV; cv0 += lanes) {
+    const int cv = cv0 + lane;
+    float acc[NQ][V];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+    if (cv < CV) {
+      for (int p = p0 + row; p < p1; p += rows) {
+        int h = p / W, w = p - h * W;
+        f(n, h, w, cv * V, acc);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int i = 0; i < V; ++i) red[(q * V + i) * 256 + threadIdx.x] = acc[q][i];
+    __syncthreads();
+    // tree over rows (rows is a power of two)
+    for (int s = rows / 2; s > 0; s >>= 1) {
+      if (row < s) {
+#pragma unroll
+        for (int q = 0; q < NQ * V; ++q)
+          red[q * 256 + threadIdx.x] += red[q * 256 + threadIdx.x + s * lanes];
+      }
+      __syncthreads();
+    }
+    if (row == 0 && cv < CV) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          atomicAdd(out + f.out_index(n, cv * V + i, q), red[(q * V + i) * 256 + threadIdx.x]);
+    }
+    __syncthreads();
+  }
+}
+
+template <int V, typename F>
+static int launch_nc_reduce(F f, int N, int H, int W, int C, float* out, cudaStream_t st) {
+  if (N == 0 || H * W == 0) return OTM_OK;
+  int CV = C / V;
+  int lanes = 1;
+  while (lanes * 2 <= CV && lanes * 2 <= 256) lanes *= 2;
+  int HW = H * W;
+  int rows = 256 / lanes;
+  // aim for ~4 CTAs per SM overall, but at least `rows*4` pixels per CTA
+  int want_chunks = (num_sms() * 4 + N - 1) / N;
+  int pix = (HW + want_chunks - 1) / want_chunks;
+  int min_pix = rows * 4;
+  if (pix < min_pix) pix = min_pix;
+  int chunks = (HW + pix - 1) / pix;
+  dim3 grid(chunks, 1, N);
+  nc_reduce_kernel<V, F><<<grid, 256, 0, st>>>(f, H, W, C, lanes, pix, out);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// instance-norm statistics
+// ---------------------------------------------------------------------------
+template <typename T, int V>
+struct StatsF {
+  static constexpr int NQ = 2;
+  View x;
+  int C;
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[2][V]) const {
+    float v[V];
+    load_vec<T, V>(vptr<T>(x, n, h, w, c), v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      acc[0][i] += v[i];
+      acc[1][i] += v[i] * v[i];
+    }
+  }
+  __device__ int out_index(int n, int c, int q) const { return (n * C + c) * 2 + q; }
+};
+
+__global__ void stats_finalize_kernel(const float* ws, float* stats, int count, float inv_n,
+                                      float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = ws[2 * i], ss = ws[2 * i + 1];
+  float mean = s * inv_n;
+  float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+  stats[2 * i] = mean;
+  stats[2 * i + 1] = rsqrtf(var + eps);
+}
+
+// ---------------------------------------------------------------------------
+// norm + act (+ residual) (+ reflect halo)
+// ---------------------------------------------------------------------------
+template <typename T, int V>
+struct NormActF {
+  View x, res, y;
+  const float* stats;
+  int act, halo, C;
+  __device__ void operator()(int n, int h, int w, int c) const {
+    float v[V];
+    load_vec<T, V>(vptr<T>(x, n, h, w, c), v);
+    if (stats) {
+      const float* st = stats + ((long long)n * C + c) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = (v[i] - st[2 * i]) * st[2 * i + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = act_fwd(v[i], act);
+    if (res.ptr) {
+      float r[V];
+      load_vec<T, V>(vptr<T>(res, n, h, w, c), r);
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] += r[i];
+    }
+    store_halo<T, V>(y, halo, n, h, w, c, v);
+  }
+};
+
+// backward: shared recompute of (ga, gn, pre)
+template <typename T, int V>
+struct NormActBwdBase {
+  View g, g2, x;
+  const float* stats;
+  int act, g_halo, C;
+  __device__ void compute(int n, int h, int w, int c, float (&ga)[V], float (&gn)[V],
+                          float (&pre)[V]) const {
+    load_fold<T, V>(g, g_halo, n, h, w, c, ga);
+    if (g2.ptr) {
+      float t[V];
+      load_vec<T, V>(vptr<T>(g2, n, h, w, c), t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) ga[i] += t[i];
+    }
+    load_vec<T, V>(vptr<T>(x, n, h, w, c), pre);
+    if (stats) {
+      const float* st = stats + ((long long)n * C + c) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) pre[i] = (pre[i] - st[2 * i]) * st[2 * i + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) gn[i] = ga[i] * act_bwd(pre[i], act);
+  }
+};
+
+template <typename T, int V>
+struct NormActBwdReduceF : NormActBwdBase<T, V> {
+  static constexpr int NQ = 2;
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[2][V]) const {
+    float ga[V], gn[V], pre[V];
+    this->compute(n, h, w, c, ga, gn, pre);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      acc[0][i] += gn[i];
+      acc[1][i] += gn[i] * pre[i];
+    }
+  }
+  __device__ int out_index(int n, int c, int q) const { return (n * this->C + c) * 2 + q; }
+};
+
+template <typename T, int V>
+struct NormActBwdApplyF : NormActBwdBase<T, V> {
+  View gx, gres;
+  const float* sums;
+  float inv_hw;
+  __device__ void operator()(int n, int h, int w, int c) const {
+    float ga[V], gn[V], pre[V];
+    this->compute(n, h, w, c, ga, gn, pre);
+    if (gres.ptr) store_vec<T, V>(vptr_mut<T>(gres, n, h, w, c), ga);
+    if (this->stats) {
+      const float* st = this->stats + ((long long)n * this->C + c) * 2;
+      const float* sm = sums + ((long long)n * this->C + c) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        gn[i] = st[2 * i + 1] * (gn[i] - sm[2 * i] * inv_hw - pre[i] * sm[2 * i + 1] * inv_hw);
+    }
+    store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), gn);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// resampling: shared 1-D tap generators
+// ---------------------------------------------------------------------------
+// DownSample = blur then bilinear to n_out = n_in/2 (align_corners=False, scale n_in/n_out).
+// For output index j: up to 4 source positions base-1+k (clamped) with merged weights.
+__device__ __forceinline__ void down_taps(int j, int n_in, float scale, int (&pos)[4],
+                                          float (&wt)[4]) {
+  float src = fmaxf((j + 0.5f) * scale - 0.5f, 0.f);
+  int i0 = min((int)floorf(src), n_in - 1);
+  int i1 = min(i0 + 1, n_in - 1);
+  float lam = src - (float)i0;
+  const float wa = 1.f - lam;
+  const float l0 = (i1 == i0) ? lam : 0.f;  // degenerate edge: both taps on the same row
+  const float l1 = (i1 == i0) ? 0.f : lam;
+  wt[0] = 0.25f * (wa + l0);
+  wt[1] = 0.5f * (wa + l0) + 0.25f * l1;
+  wt[2] = 0.25f * (wa + l0) + 0.5f * l1;
+  wt[3] = 0.25f * l1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pos[k] = min(max(i0 - 1 + k, 0), n_in - 1);
+}
+
+// UpSample = bilinear x2 then blur.  For output j in [0, 2n): positions base+k, k<4.
+__device__ __forceinline__ void up_taps(int j, int n_in, int (&pos)[4], float (&wt)[4]) {
+  const int n_out = 2 * n_in;
+  wt[0] = wt[1] = wt[2] = wt[3] = 0.f;
+  int jm = max(j - 1, 0);
+  float srcm = fmaxf((jm + 0.5f) * 0.5f - 0.5f, 0.f);
+  int base = (int)floorf(srcm);
+#pragma unroll
+  for (int d = -1; d <= 1; ++d) {
+    int jj = min(max(j + d, 0), n_out - 1);
+    float kd = (d == 0) ? 0.5f : 0.25f;
+    float src = fmaxf((jj + 0.5f) * 0.5f - 0.5f, 0.f);
+    int i0 = min((int)floorf(src), n_in - 1);
+    int i1 = min(i0 + 1, n_in - 1);
+    float lam = src - (float)i0;
+    const int a = i0 - base, b = i1 - base;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      wt[k] += (k == a ? kd * (1.f - lam) : 0.f) + (k == b ? kd * lam : 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pos[k] = min(base + k, n_in - 1);
+}
+
+template <typename T, int V>
+struct DownF {
+  View x, y;
+  const float* stats;
+  int act, halo, C;
+  float sch, scw;
+  __device__ void operator()(int n, int ho, int wo, int c) const {
+    int ph[4], pw[4];
+    float wh[4], ww[4];
+    down_taps(ho, x.h, sch, ph, wh);
+    down_taps(wo, x.w, scw, pw, ww);
+    float mean[V], rstd[V];
+    if (stats) {
+      const float* st = stats + ((long long)n * C + c) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { mean[i] = st[2 * i]; rstd[i] = st[2 * i + 1]; }
+    }
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (wh[a] == 0.f) continue;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float wgt = wh[a] * ww[b];
+        if (wgt == 0.f) continue;
+        float v[V];
+        load_vec<T, V>(vptr<T>(x, n, ph[a], pw[b], c), v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float t = stats ? (v[i] - mean[i]) * rstd[i] : v[i];
+          acc[i] += wgt * act_fwd(t, act);
+        }
+      }
+    }
+    store_halo<T, V>(y, halo, n, ho, wo, c, acc);
+  }
+};
+
+// gather form of the transpose: for input index i, list (j, weight) of outputs touching it
+template <int MAXC>
+__device__ __forceinline__ int down_bwd_taps(int i, int n_in, int n_out, float scale,
+                                             int (&js)[MAXC], float (&wj)[MAXC]) {
+  int cnt = 0;
+  int lo = max(0, (int)floorf((i - 2.5f) / scale) - 1);
+  int hi = min(n_out - 1, (int)ceilf((i + 1.5f) / scale) + 1);
+  for (int j = lo; j <= hi; ++j) {
+    int pos[4];
+    float wt[4];
+    down_taps(j, n_in, scale, pos, wt);
+    float w = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (pos[k] == i) w += wt[k];
+    if (w != 0.f && cnt < MAXC) { js[cnt] = j; wj[cnt] = w; ++cnt; }
+  }
+  return cnt;
+}
+
+template <int MAXC>
+__device__ __forceinline__ int up_bwd_taps(int i, int n_in, int (&js)[MAXC], float (&wj)[MAXC]) {
+  int cnt = 0;
+  const int n_out = 2 * n_in;
+  int lo = max(0, 2 * i - 4), hi = min(n_out - 1, 2 * i + 5);
+  for (int j = lo; j <= hi; ++j) {
+    int pos[4];
+    float wt[4];
+    up_taps(j, n_in, pos, wt);
+    float w = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (pos[k] == i) w += wt[k];
+    if (w != 0.f && cnt < MAXC) { js[cnt] = j; wj[cnt] = w; ++cnt; }
+  }
+  return cnt;
+}
+
+template <typename T, int V>
+struct DownBwdF {
+  View g, ga;
+  int g_halo;
+  float sch, scw;
+  __device__ void operator()(int n, int h, int w, int c) const {
+    int jh[8], jw[8];
+    float wh[8], ww[8];
+    int nh = down_bwd_taps<8>(h, ga.h, g.h, sch, jh, wh);
+    int nw = down_bwd_taps<8>(w, ga.w, g.w, scw, jw, ww);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        float v[V];
+        load_fold<T, V>(g, g_halo, n, jh[a], jw[b], c, v);
+        float wgt = wh[a] * ww[b];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += wgt * v[i];
+      }
+    store_vec<T, V>(vptr_mut<T>(ga, n, h, w, c), acc);
+  }
+};
+
+template <typename T, int V>
+struct UpF {
+  View x, y;
+  int halo;
+  __device__ void operator()(int n, int ho, int wo, int c) const {
+    int ph[4], pw[4];
+    float wh[4], ww[4];
+    up_taps(ho, x.h, ph, wh);
+    up_taps(wo, x.w, pw, ww);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (wh[a] == 0.f) continue;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float wgt = wh[a] * ww[b];
+        if (wgt == 0.f) continue;
+        float v[V];
+        load_vec<T, V>(vptr<T>(x, n, ph[a], pw[b], c), v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += wgt * v[i];
+      }
+    }
+    store_halo<T, V>(y, halo, n, ho, wo, c, acc);
+  }
+};
+
+template <typename T, int V>
+struct UpBwdF {
+  View g, gx;
+  int g_halo;
+  __device__ void operator()(int n, int h, int w, int c) const {
+    int jh[10], jw[10];
+    float wh[10], ww[10];
+    int nh = up_bwd_taps<10>(h, gx.h, jh, wh);
+    int nw = up_bwd_taps<10>(w, gx.w, jw, ww);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        float v[V];
+        load_fold<T, V>(g, g_halo, n, jh[a], jw[b], c, v);
+        float wgt = wh[a] * ww[b];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += wgt * v[i];
+      }
+    store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), acc);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// modulated-conv side passes
+// ---------------------------------------------------------------------------
+template <typename T, int V>
+struct ModOutF {
+  static constexpr int NQ = 1;
+  View g, g2, out, res, gy;
+  int g_halo, act, C;
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V]) const {
+    float ga[V], o[V];
+    load_fold<T, V>(g, g_halo, n, h, w, c, ga);
+    if (g2.ptr) {
+      float t[V];
+      load_vec<T, V>(vptr<T>(g2, n, h, w, c), t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) ga[i] += t[i];
+    }
+    load_vec<T, V>(vptr<T>(out, n, h, w, c), o);
+    if (act == OTM_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) ga[i] = o[i] > 0.f ? ga[i] : 0.f;
+    }
+    if (res.ptr) {
+      float r[V];
+      load_vec<T, V>(vptr<T>(res, n, h, w, c), r);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] -= r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[0][i] += ga[i] * o[i];
+    if (gy.ptr) store_vec<T, V>(vptr_mut<T>(gy, n, h, w, c), ga);
+  }
+  __device__ int out_index(int n, int c, int) const { return n * C + c; }
+};
+
+template <typename T, int V>
+struct ModInF {
+  static constexpr int NQ = 1;
+  View g, x, gadd, gx;
+  const float* s;
+  int g_halo, C;
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V]) const {
+    float gt[V], xv[V];
+    load_fold<T, V>(g, g_halo, n, h, w, c, gt);
+    load_vec<T, V>(vptr<T>(x, n, h, w, c), xv);
+    const float* sp = s + (long long)n * C + c;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      acc[0][i] += gt[i] * xv[i];
+      gt[i] *= sp[i];
+    }
+    if (gadd.ptr) {
+      float t[V];
+      load_vec<T, V>(vptr<T>(gadd, n, h, w, c), t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) gt[i] += t[i];
+    }
+    store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), gt);
+  }
+  __device__ int out_index(int n, int c, int) const { return n * C + c; }
+};
+
+template <typename T, int V>
+struct ChannelSumF {
+  static constexpr int NQ = 1;
+  View g;
+  float scale;
+  int per_sample, C;
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V]) const {
+    float v[V];
+    load_vec<T, V>(vptr<T>(g, n, h, w, c), v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[0][i] += v[i] * scale;
+  }
+  __device__ int out_index(int n, int c, int) const { return per_sample ? n * C + c : c; }
+};
+
+template <typename T, int V>
+struct AvgPoolBwdF {
+  View gx;
+  const float* g;
+  float inv_hw;
+  int C;
+  __device__ void operator()(int n, int h, int w, int c) const {
+    float v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = g[(long long)n * C + c + i] * inv_hw;
+    store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), v);
+  }
+};
+
+template <typename TX, typename TY>
+struct CastF {
+  View x, y;
+  __device__ void operator()(int n, int h, int w, int c) const {
+    *vptr_mut<TY>(y, n, h, w, c) = from_f<TY>(to_f(*vptr<TX>(x, n, h, w, c)));
+  }
+};
+
+template <typename T, int V>
+struct AddF {
+  View dst, src;
+  __device__ void operator()(int n, int h, int w, int c) const {
+    float a[V], b[V];
+    load_vec<T, V>(vptr<T>(dst, n, h, w, c), a);
+    load_vec<T, V>(vptr<T>(src, n, h, w, c), b);
+#pragma unroll
+    for (int i = 0; i < V; ++i) a[i] += b[i];
+    store_vec<T, V>(vptr_mut<T>(dst, n, h, w, c), a);
+  }
+};
+
+static bool same_shape(const otm_tensor& a, const otm_tensor& b) {
+  return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
+}
+
+}  // namespace otm
+
+using namespace otm;
+
+// dispatch on (dtype, vector width) and run BODY with T and V defined
+#define OTM_DISPATCH_TV(dt, vecok, ...)                                      \
+  do {                                                                       \
+    if ((dt) == OTM_BF16) {                                                  \
+      using T = __nv_bfloat16;                                               \
+      if (vecok) { constexpr int V = 8; __VA_ARGS__; }                       \
+      else { constexpr int V = 1; __VA_ARGS__; }                             \
+    } else {                                                                 \
+      using T = float;                                                       \
+      if (vecok) { constexpr int V = 8; __VA_ARGS__; }                       \
+      else { constexpr int V = 1; __VA_ARGS__; }                             \
+    }                                                                        \
+  } while (0)
+
+extern "C" {
+
+const char* otm_last_error(void) { return g_err; }
+int otm_version(void) { return 1; }
+int64_t otm_launch_count(void) { return g_launches.load(); }
+
+int otm_instnorm_stats(const otm_tensor* x, float eps, float* ws, float* stats,
+                       otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(x && x->ptr && ws && stats, "instnorm_stats: null argument");
+  int count = x->n * x->c;
+  OTM_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * count, st));
+  bool vok = vec_ok(*x, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(x->dtype, vok, {
+    StatsF<T, V> f{make_view(*x), x->c};
+    rc = launch_nc_reduce<V>(f, x->n, x->h, x->w, x->c, ws, st);
+  });
+  if (rc) return rc;
+  stats_finalize_kernel<<<(count + 255) / 256, 256, 0, st>>>(ws, stats, count,
+                                                             1.f / (float)(x->h * x->w), eps);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
+int otm_norm_act(const otm_norm_act_args* a, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(a && a->x.ptr && a->y.ptr, "norm_act: null tensor");
+  OTM_REQUIRE(same_shape(a->x, a->y), "norm_act: x/y shape mismatch");
+  OTM_REQUIRE(a->x.dtype == a->y.dtype, "norm_act: dtype mismatch");
+  OTM_REQUIRE(a->y_halo >= 0 && a->y_halo < a->y.h && a->y_halo < a->y.w,
+              "norm_act: reflect halo %d too large for %dx%d", a->y_halo, a->y.h, a->y.w);
+  if (a->residual.ptr) {
+    OTM_REQUIRE(same_shape(a->x, a->residual) && a->residual.dtype == a->x.dtype,
+                "norm_act: residual mismatch");
+  }
+  bool vok = vec_ok(a->x, 8) && vec_ok(a->y, 8) && vec_ok(a->residual, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(a->x.dtype, vok, {
+    NormActF<T, V> f{make_view(a->x), a->residual.ptr ? make_view(a->residual) : null_view(),
+                     make_view(a->y), a->stats, a->act, a->y_halo, a->x.c};
+    rc = launch_ew<V>(f, a->x.n, a->x.h, a->x.w, a->x.c, st);
+  });
+  return rc;
+}
+
+int otm_norm_act_bwd(const otm_norm_act_bwd_args* a, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(a && a->g.ptr && a->x.ptr && a->gx.ptr, "norm_act_bwd: null tensor");
+  OTM_REQUIRE(same_shape(a->g, a->x) && same_shape(a->gx, a->x), "norm_act_bwd: shape mismatch");
+  OTM_REQUIRE(a->g.dtype == a->x.dtype && a->gx.dtype == a->x.dtype, "norm_act_bwd: dtype");
+  OTM_REQUIRE(!a->stats || a->sums, "norm_act_bwd: sums workspace required with stats");
+  bool vok = vec_ok(a->g, 8) && vec_ok(a->x, 8) && vec_ok(a->gx, 8) && vec_ok(a->g2, 8) &&
+             vec_ok(a->gres, 8);
+  int rc = OTM_OK;
+  const int C = a->x.c;
+  OTM_DISPATCH_TV(a->x.dtype, vok, {
+    if (a->stats) {
+      OTM_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * a->x.n * C, st));
+      NormActBwdReduceF<T, V> r;
+      r.g = make_view(a->g); r.g2 = a->g2.ptr ? make_view(a->g2) : null_view();
+      r.x = make_view(a->x); r.stats = a->stats; r.act = a->act; r.g_halo = a->g_halo; r.C = C;
+      rc = launch_nc_reduce<V>(r, a->x.n, a->x.h, a->x.w, C, a->sums, st);
+    }
+    if (rc == OTM_OK) {
+      NormActBwdApplyF<T, V> f;
+      f.g = make_view(a->g); f.g2 = a->g2.ptr ? make_view(a->g2) : null_view();
+      f.x = make_view(a->x); f.stats = a->stats; f.act = a->act; f.g_halo = a->g_halo; f.C = C;
+      f.gx = make_view(a->gx); f.gres = a->gres.ptr ? make_view(a->gres) : null_view();
+      f.sums = a->sums; f.inv_hw = 1.f / (float)(a->x.h * a->x.w);
+      rc = launch_ew<V>(f, a->x.n, a->x.h, a->x.w, C, st);
+    }
+  });
+  return rc;
+}
+
+int otm_down(const otm_down_args* a, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(a && a->x.ptr && a->y.ptr, "down: null tensor");
+  OTM_REQUIRE(a->y.h == a->x.h / 2 && a->y.w == a->x.w / 2 && a->y.n == a->x.n &&
+                  a->y.c == a->x.c && a->y.h > 0 && a->y.w > 0,
+              "down: y must be [n, H/2, W/2, c]");
+  OTM_REQUIRE(a->x.dtype == a->y.dtype, "down: dtype mismatch");
+  OTM_REQUIRE(a->y_halo >= 0 && (a->y_halo == 0 || (a->y_halo < a->y.h && a->y_halo < a->y.w)),
+              "down: halo too large");
+  bool vok = vec_ok(a->x, 8) && vec_ok(a->y, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(a->x.dtype, vok, {
+    DownF<T, V> f{make_view(a->x), make_view(a->y), a->stats, a->act, a->y_halo, a->x.c,
+                  (float)a->x.h / (float)a->y.h, (float)a->x.w / (float)a->y.w};
+    rc = launch_ew<V>(f, a->y.n, a->y.h, a->y.w, a->y.c, st);
+  });
+  return rc;
+}
+
+int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(g && ga && g->ptr && ga->ptr, "down_bwd: null tensor");
+  OTM_REQUIRE(g->h == ga->h / 2 && g->w == ga->w / 2 && g->n == ga->n && g->c == ga->c,
+              "down_bwd: shape mismatch");
+  OTM_REQUIRE(g->dtype == ga->dtype, "down_bwd: dtype mismatch");
+  bool vok = vec_ok(*g, 8) && vec_ok(*ga, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(g->dtype, vok, {
+    DownBwdF<T, V> f{make_view(*g), make_view(*ga), g_halo, (float)ga->h / (float)g->h,
+                     (float)ga->w / (float)g->w};
+    rc = launch_ew<V>(f, ga->n, ga->h, ga->w, ga->c, st);
+  });
+  return rc;
+}
+
+int otm_up(const otm_tensor* x, const otm_tensor* y, int32_t y_halo, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(x && y && x->ptr && y->ptr, "up: null tensor");
+  OTM_REQUIRE(y->h == 2 * x->h && y->w == 2 * x->w && y->n == x->n && y->c == x->c,
+              "up: y must be [n, 2H, 2W, c]");
+  OTM_REQUIRE(x->dtype == y->dtype, "up: dtype mismatch");
+  bool vok = vec_ok(*x, 8) && vec_ok(*y, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(x->dtype, vok, {
+    UpF<T, V> f{make_view(*x), make_view(*y), y_halo};
+    rc = launch_ew<V>(f, y->n, y->h, y->w, y->c, st);
+  });
+  return rc;
+}
+
+int otm_up_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* gx, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(g && gx && g->ptr && gx->ptr, "up_bwd: null tensor");
+  OTM_REQUIRE(g->h == 2 * gx->h && g->w == 2 * gx->w && g->n == gx->n && g->c == gx->c,
+              "up_bwd: shape mismatch");
+  OTM_REQUIRE(g->dtype == gx->dtype, "up_bwd: dtype mismatch");
+  bool vok = vec_ok(*g, 8) && vec_ok(*gx, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(g->dtype, vok, {
+    UpBwdF<T, V> f{make_view(*g), make_view(*gx), g_halo};
+    rc = launch_ew<V>(f, gx->n, gx->h, gx->w, gx->c, st);
+  });
+  return rc;
+}
+
+int otm_mod_out(const otm_mod_out_args* a, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(a && a->g.ptr && a->out.ptr && a->P, "mod_out: null argument");
+  OTM_REQUIRE(same_shape(a->g, a->out), "mod_out: shape mismatch");
+  OTM_REQUIRE(a->act == OTM_ACT_NONE || a->act == OTM_ACT_RELU, "mod_out: act must be none/relu");
+  const int C = a->out.c;
+  OTM_CHECK_CUDA(cudaMemsetAsync(a->P, 0, sizeof(float) * a->out.n * C, st));
+  bool vok = vec_ok(a->g, 8) && vec_ok(a->out, 8) && vec_ok(a->g2, 8) && vec_ok(a->res, 8) &&
+             vec_ok(a->gy, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(a->out.dtype, vok, {
+    ModOutF<T, V> f{make_view(a->g),
+                    a->g2.ptr ? make_view(a->g2) : null_view(),
+                    make_view(a->out),
+                    a->res.ptr ? make_view(a->res) : null_view(),
+                    a->gy.ptr ? make_view(a->gy) : null_view(),
+                    a->g_halo, a->act, C};
+    rc = launch_nc_reduce<V>(f, a->out.n, a->out.h, a->out.w, C, a->P, st);
+  });
+  return rc;
+}
+
+int otm_mod_in(const otm_mod_in_args* a, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(a && a->g.ptr && a->x.ptr && a->gx.ptr && a->Q && a->s, "mod_in: null argument");
+  OTM_REQUIRE(same_shape(a->g, a->x) && same_shape(a->gx, a->x), "mod_in: shape mismatch");
+  const int C = a->x.c;
+  OTM_CHECK_CUDA(cudaMemsetAsync(a->Q, 0, sizeof(float) * a->x.n * C, st));
+  bool vok = vec_ok(a->g, 8) && vec_ok(a->x, 8) && vec_ok(a->gadd, 8) && vec_ok(a->gx, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(a->x.dtype, vok, {
+    ModInF<T, V> f{make_view(a->g), make_view(a->x),
+                   a->gadd.ptr ? make_view(a->gadd) : null_view(), make_view(a->gx),
+                   a->s, a->g_halo, C};
+    rc = launch_nc_reduce<V>(f, a->x.n, a->x.h, a->x.w, C, a->Q, st);
+  });
+  return rc;
+}
+
+int otm_channel_sum(const otm_tensor* g, float* out, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(g && g->ptr && out, "channel_sum: null argument");
+  OTM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * g->c, st));
+  bool vok = vec_ok(*g, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(g->dtype, vok, {
+    ChannelSumF<T, V> f{make_view(*g), 1.f, 0, g->c};
+    rc = launch_nc_reduce<V>(f, g->n, g->h, g->w, g->c, out, st);
+  });
+  return rc;
+}
+
+int otm_avgpool(const otm_tensor* x, float* out, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(x && x->ptr && out, "avgpool: null argument");
+  OTM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * x->n * x->c, st));
+  bool vok = vec_ok(*x, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(x->dtype, vok, {
+    ChannelSumF<T, V> f{make_view(*x), 1.f / (float)(x->h * x->w), 1, x->c};
+    rc = launch_nc_reduce<V>(f, x->n, x->h, x->w, x->c, out, st);
+  });
+  return rc;
+}
+
+int otm_avgpool_bwd(const float* g, const otm_tensor* gx, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(g && gx && gx->ptr, "avgpool_bwd: null argument");
+  bool vok = vec_ok(*gx, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(gx->dtype, vok, {
+    AvgPoolBwdF<T, V> f{make_view(*gx), g, 1.f / (float)(gx->h * gx->w), gx->c};
+    rc = launch_ew<V>(f, gx->n, gx->h, gx->w, gx->c, st);
+  });
+  return rc;
+}
+
+int otm_cast(const otm_tensor* x, const otm_tensor* y, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(x && y && x->ptr && y->ptr && same_shape(*x, *y), "cast: bad arguments");
+  View xv = make_view(*x), yv = make_view(*y);
+  int rc;
+  if (x->dtype == OTM_F32 && y->dtype == OTM_F32)
+    rc = launch_ew<1>(CastF<float, float>{xv, yv}, x->n, x->h, x->w, x->c, st);
+  else if (x->dtype == OTM_F32)
+    rc = launch_ew<1>(CastF<float, __nv_bfloat16>{xv, yv}, x->n, x->h, x->w, x->c, st);
+  else if (y->dtype == OTM_F32)
+    rc = launch_ew<1>(CastF<__nv_bfloat16, float>{xv, yv}, x->n, x->h, x->w, x->c, st);
+  else
+    rc = launch_ew<1>(CastF<__nv_bfloat16, __nv_bfloat16>{xv, yv}, x->n, x->h, x->w, x->c, st);
+  return rc;
+}
+
+int otm_add_inplace(const otm_tensor* dst, const otm_tensor* src, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(dst && src && dst->ptr && src->ptr && same_shape(*dst, *src) &&
+                  dst->dtype == src->dtype,
+              "add_inplace: bad arguments");
+  bool vok = vec_ok(*dst, 8) && vec_ok(*src, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(dst->dtype, vok, {
+    AddF<T, V> f{make_view(*dst), make_view(*src)};
+    rc = launch_ew<V>(f, dst->n, dst->h, dst->w, dst->c, st);
+  });
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+"""Thin Python wrappers over the C-ABI: allocate outputs with torch (plumbing), describe the
+tensors, call the kernel on the current CUDA stream.  No arithmetic happens here."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, PATH_AUTO, PATH_SIMT, PATH_TC  # noqa: F401
+
+_byref = C.byref
+
+
+def alloc(n: int, c: int, h: int, w: int, dtype, device, halo: int = 0, zero: bool = False):
+    """NHWC buffer with `halo` extra pixels on every side; returns the INTERIOR view as a
+    logically-NCHW tensor (channel stride 1)."""
+    mk = torch.zeros if zero else torch.empty
+    buf = mk((n, h + 2 * halo, w + 2 * halo, c), dtype=dtype, device=device)
+    if halo:
+        buf = buf[:, halo : halo + h, halo : halo + w, :]
+    return buf.permute(0, 3, 1, 2)
+
+
+def padded_view(t: torch.Tensor, halo: int) -> torch.Tensor:
+    """The halo-inclusive view [n,c,h+2p,w+2p] of an interior view produced by alloc()."""
+    if halo == 0:
+        return t
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    off = t.storage_offset() - halo * (sh + sw)
+    if off < 0:
+        raise ValueError("tensor has no materialised halo")
+    return t.as_strided((n, c, h + 2 * halo, w + 2 * halo), (sn, sc, sh, sw), off)
+
+
+def conv_fwd(x, wpack, cout, kh, kw, pad, *, x_halo=0, y_halo=0, alpha=1.0, row_scale=None,
+             bias=None, act=ACT_NONE, residual=None, out_dtype=None, per_sample=False,
+             path=PATH_AUTO, out=None):
+    n, cin, h, w = x.shape
+    ho, wo = h + 2 * pad - kh + 1, w + 2 * pad - kw + 1
+    if out is None:
+        out = alloc(n, cout, ho, wo, out_dtype or x.dtype, x.device, y_halo)
+    a = L.ConvFwdArgs()
+    a.x = L.tdesc(x)
+    a.x_halo = x_halo
+    a.wpack = L.ptr(wpack)
+    a.w_batch_stride = cout * kh * kw * cin if per_sample else 0
+    a.kh, a.kw, a.pad = kh, kw, pad
+    a.y = L.tdesc(out)
+    a.y_halo = y_halo
+    a.alpha = alpha
+    a.row_scale = L.ptr(row_scale)
+    a.bias = L.ptr(bias)
+    a.act = act
+    a.residual = L.tdesc(residual)
+    a.path = path
+    L.check(L.lib.otm_conv_fwd(_byref(a), L.stream_ptr()), "otm_conv_fwd")
+    return out
+
+
+def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None, path=PATH_AUTO):
+    a = L.ConvWgradArgs()
+    a.x = L.tdesc(x)
+    a.x_halo = x_halo
+    a.dy = L.tdesc(dy)
+    a.kh, a.kw, a.pad = kh, kw, pad
+    a.dw = L.ptr(dw)
+    a.alpha = alpha
+    a.rs = L.ptr(rs)
+    a.cs = L.ptr(cs)
+    a.path = path
+    L.check(L.lib.otm_conv_wgrad(_byref(a), L.stream_ptr()), "otm_conv_wgrad")
+    return dw
+
+
+def weight_pack(w, alpha, dtype, *, cs=None, rs=None, nb=1, transpose=False):
+    cout, cin, kh, kw = w.shape
+    out = torch.empty((nb, cin if transpose else cout, kh, kw, cout if transpose else cin),
+                      dtype=dtype, device=w.device)
+    a = L.WeightPackArgs()
+    a.w = L.ptr(w)
+    a.cout, a.cin, a.kh, a.kw = cout, cin, kh, kw
+    a.alpha = alpha
+    a.cs = L.ptr(cs)
+    a.rs = L.ptr(rs)
+    a.nb = nb
+    a.transpose = int(transpose)
+    a.out = L.ptr(out)
+    a.out_dtype = L.dtype_code(out)
+    L.check(L.lib.otm_weight_pack(_byref(a), L.stream_ptr()), "otm_weight_pack")
+    return out
+
+
+def weight_sqsum(w, alpha):
+    cout, cin, kh, kw = w.shape
+    q = torch.empty((cout, cin), dtype=torch.float32, device=w.device)
+    L.check(L.lib.otm_weight_sqsum(L.ptr(w), cout, cin, kh * kw, alpha, L.ptr(q), L.stream_ptr()),
+            "otm_weight_sqsum")
+    return q
+
+
+def demod(s, q, eps=1e-8):
+    nb, cin = s.shape
+    cout = q.shape[0]
+    out = torch.empty((nb, cout), dtype=torch.float32, device=s.device)
+    L.check(L.lib.otm_demod(L.ptr(s), L.ptr(q), nb, cout, cin, eps, L.ptr(out), L.stream_ptr()),
+            "otm_demod")
+    return out
+
+
+def mod_bwd(w, alpha, s, sigma_inv, q, P, Q, dw):
+    cout, cin, kh, kw = w.shape
+    ds = torch.empty_like(s)
+    a = L.ModBwdArgs()
+    a.w = L.ptr(w)
+    a.cout, a.cin, a.taps = cout, cin, kh * kw
+    a.alpha = alpha
+    a.s, a.sigma_inv, a.q, a.P, a.Q = L.ptr(s), L.ptr(sigma_inv), L.ptr(q), L.ptr(P), L.ptr(Q)
+    a.nb = s.shape[0]
+    a.ds = L.ptr(ds)
+    a.dw = L.ptr(dw)
+    L.check(L.lib.otm_mod_bwd(_byref(a), L.stream_ptr()), "otm_mod_bwd")
+    return ds
+
+
+def instnorm_stats(x, eps=1e-5):
+    n, c = x.shape[:2]
+    ws = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+    stats = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+    d = L.tdesc(x)
+    L.check(L.lib.otm_instnorm_stats(_byref(d), eps, L.ptr(ws), L.ptr(stats), L.stream_ptr()),
+            "otm_instnorm_stats")
+    return stats
+
+
+def norm_act(x, stats=None, act=ACT_NONE, residual=None, y_halo=0, out=None):
+    n, c, h, w = x.shape
+    if out is None:
+        out = alloc(n, c, h, w, x.dtype, x.device, y_halo)
+    a = L.NormActArgs()
+    a.x = L.tdesc(x)
+    a.stats = L.ptr(stats)
+    a.act = act
+    a.residual = L.tdesc(residual)
+    a.y = L.tdesc(out)
+    a.y_halo = y_halo
+    L.check(L.lib.otm_norm_act(_byref(a), L.stream_ptr()), "otm_norm_act")
+    return out
+
+
+def norm_act_bwd(g, x, stats=None, act=ACT_NONE, *, g_halo=0, g2=None, want_gres=False):
+    """g: gradient w.r.t. the forward output; if g_halo>0 it is the INTERIOR view of the
+    gradient w.r.t. the reflect-padded output."""
+    n, c, h, w = x.shape
+    gx = alloc(n, c, h, w, x.dtype, x.device)
+    gres = alloc(n, c, h, w, x.dtype, x.device) if want_gres else None
+    sums = torch.empty((n, c, 2), dtype=torch.float32, device=x.device) if stats is not None else None
+    a = L.NormActBwdArgs()
+    a.g = L.tdesc(g)
+    a.g_halo = g_halo
+    a.g2 = L.tdesc(g2)
+    a.x = L.tdesc(x)
+    a.stats = L.ptr(stats)
+    a.act = act
+    a.gx = L.tdesc(gx)
+    a.gres = L.tdesc(gres)
+    a.sums = L.ptr(sums)
+    L.check(L.lib.otm_norm_act_bwd(_byref(a), L.stream_ptr()), "otm_norm_act_bwd")
+    return (gx, gres) if want_gres else gx
+
+
+def down(x, stats=None, act=ACT_NONE, y_halo=0):
+    n, c, h, w = x.shape
+    out = alloc(n, c, h // 2, w // 2, x.dtype, x.device, y_halo)
+    a = L.DownArgs()
+    a.x = L.tdesc(x)
+    a.stats = L.ptr(stats)
+    a.act = act
+    a.y = L.tdesc(out)
+    a.y_halo = y_halo
+    L.check(L.lib.otm_down(_byref(a), L.stream_ptr()), "otm_down")
+    return out
+
+
+def down_bwd(g, in_hw, g_halo=0):
+    n, c = g.shape[:2]
+    ga = alloc(n, c, in_hw[0], in_hw[1], g.dtype, g.device)
+    dg, dga = L.tdesc(g), L.tdesc(ga)
+    L.check(L.lib.otm_down_bwd(_byref(dg), g_halo, _byref(dga), L.stream_ptr()), "otm_down_bwd")
+    return ga
+
+
+def up(x, y_halo=0):
+    n, c, h, w = x.shape
+    out = alloc(n, c, 2 * h, 2 * w, x.dtype, x.device, y_halo)
+    dx, dy = L.tdesc(x), L.tdesc(out)
+    L.check(L.lib.otm_up(_byref(dx), _byref(dy), y_halo, L.stream_ptr()), "otm_up")
+    return out
+
+
+def up_bwd(g, g_halo=0):
+    n, c, h, w = g.shape
+    gx = alloc(n, c, h // 2, w // 2, g.dtype, g.device)
+    dg, dgx = L.tdesc(g), L.tdesc(gx)
+    L.check(L.lib.otm_up_bwd(_byref(dg), g_halo, _byref(dgx), L.stream_ptr()), "otm_up_bwd")
+    return gx
+
+
+def mod_out(g, out, *, g_halo=0, g2=None, res=None, act=ACT_NONE, materialise=True):
+    n, c, h, w = out.shape
+    gy = alloc(n, c, h, w, out.dtype, out.device) if materialise else None
+    P = torch.empty((n, c), dtype=torch.float32, device=out.device)
+    a = L.ModOutArgs()
+    a.g = L.tdesc(g)
+    a.g_halo = g_halo
+    a.g2 = L.tdesc(g2)
+    a.out = L.tdesc(out)
+    a.res = L.tdesc(res)
+    a.act = act
+    a.gy = L.tdesc(gy)
+    a.P = L.ptr(P)
+    L.check(L.lib.otm_mod_out(_byref(a), L.stream_ptr()), "otm_mod_out")
+    return gy, P
+
+
+def mod_in(g, x, s, *, g_halo=0, gadd=None):
+    n, c, h, w = x.shape
+    gx = alloc(n, c, h, w, x.dtype, x.device)
+    Q = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    a = L.ModInArgs()
+    a.g = L.tdesc(g)
+    a.g_halo = g_halo
+    a.x = L.tdesc(x)
+    a.s = L.ptr(s)
+    a.gadd = L.tdesc(gadd)
+    a.gx = L.tdesc(gx)
+    a.Q = L.ptr(Q)
+    L.check(L.lib.otm_mod_in(_byref(a), L.stream_ptr()), "otm_mod_in")
+    return gx, Q
+
+
+def channel_sum(g):
+    out = torch.empty((g.shape[1],), dtype=torch.float32, device=g.device)
+    d = L.tdesc(g)
+    L.check(L.lib.otm_channel_sum(_byref(d), L.ptr(out), L.stream_ptr()), "otm_channel_sum")
+    return out
+
+
+def avgpool(x):
+    out = torch.empty(x.shape[:2], dtype=torch.float32, device=x.device)
+    d = L.tdesc(x)
+    L.check(L.lib.otm_avgpool(_byref(d), L.ptr(out), L.stream_ptr()), "otm_avgpool")
+    return out
+
+
+def avgpool_bwd(g, shape, dtype):
+    n, c, h, w = shape
+    gx = alloc(n, c, h, w, dtype, g.device)
+    d = L.tdesc(gx)
+    L.check(L.lib.otm_avgpool_bwd(L.ptr(g), _byref(d), L.stream_ptr()), "otm_avgpool_bwd")
+    return gx
+
+
+def loss_lsgan(x, target, scale=1.0, want_grad=True):
+    out = torch.empty((2,), dtype=torch.float32, device=x.device)
+    grad = alloc(*_nchw(x), x.dtype, x.device) if want_grad else None
+    dx, dg = L.tdesc(x), L.tdesc(grad)
+    L.check(L.lib.otm_loss_lsgan(_byref(dx), target, scale, L.ptr(out), _byref(dg), L.stream_ptr()),
+            "otm_loss_lsgan")
+    return out, grad
+
+
+def _nchw(x):
+    n, c, h, w = x.shape
+    return n, c, h, w
+
+
+def loss_l1(a, b, scale=1.0, want_grad=True):
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    grad = alloc(*_nchw(a), a.dtype, a.device) if want_grad else None
+    da, db, dg = L.tdesc(a), L.tdesc(b), L.tdesc(grad)
+    L.check(L.lib.otm_loss_l1(_byref(da), _byref(db), scale, L.ptr(out), _byref(dg), L.stream_ptr()),
+            "otm_loss_l1")
+    return out, grad
+
+
+def moments(x):
+    out = torch.empty((2,), dtype=torch.float32, device=x.device)
+    d = L.tdesc(x)
+    L.check(L.lib.otm_moments(_byref(d), L.ptr(out), L.stream_ptr()), "otm_moments")
+    return out
+
+
+def affine_grad(x, coef, grad=None):
+    accumulate = grad is not None
+    if grad is None:
+        grad = alloc(*_nchw(x), x.dtype, x.device)
+    dx, dg = L.tdesc(x), L.tdesc(grad)
+    L.check(L.lib.otm_affine_grad(_byref(dx), L.ptr(coef), _byref(dg), int(accumulate), L.stream_ptr()),
+            "otm_affine_grad")
+    return grad
+
+
+def loss_path(f1, f2, h, weight, scale, out, want_grad=True):
+    g1 = alloc(*_nchw(f1), f1.dtype, f1.device) if want_grad else None
+    g2 = alloc(*_nchw(f1), f1.dtype, f1.device) if want_grad else None
+    d1, d2, dg1, dg2 = L.tdesc(f1), L.tdesc(f2), L.tdesc(g1), L.tdesc(g2)
+    L.check(L.lib.otm_loss_path(_byref(d1), _byref(d2), L.ptr(h), weight, scale, L.ptr(out),
+                                _byref(dg1), _byref(dg2), L.stream_ptr()), "otm_loss_path")
+    return g1, g2
+
+
+def adam(param, grad, m, v, step_dev, lr, beta1, beta2, eps=1e-8, grad_scale=1.0):
+    a = L.AdamArgs()
+    a.param, a.grad, a.m, a.v = L.ptr(param), L.ptr(grad), L.ptr(m), L.ptr(v)
+    a.n = param.numel()
+    a.lr, a.beta1, a.beta2, a.eps, a.grad_scale = lr, beta1, beta2, eps, grad_scale
+    a.step = L.ptr(step_dev)
+    L.check(L.lib.otm_adam(_byref(a), L.stream_ptr()), "otm_adam")
+
+
+def synth_uniform(out, seed, stream_id, offset=0):
+    L.check(L.lib.otm_synth_uniform(L.ptr(out), out.numel(), seed, stream_id, offset, L.stream_ptr()),
+            "otm_synth_uniform")
+    return out
+
+
+def cast(x, dtype, out=None):
+    if out is None:
+        out = alloc(*_nchw(x), dtype, x.device)
+    dx, dy = L.tdesc(x), L.tdesc(out)
+    L.check(L.lib.otm_cast(_byref(dx), _byref(dy), L.stream_ptr()), "otm_cast")
+    return out
+
+
+def add_(dst, src):
+    dd, ds = L.tdesc(dst), L.tdesc(src)
+    L.check(L.lib.otm_add_inplace(_byref(dd), _byref(ds), L.stream_ptr()), "otm_add_inplace")
+    return dst
+
+
+def launch_count() -> int:
+    return int(L.lib.otm_launch_count())
