@@ -196,7 +196,12 @@ struct NormActBwdBase {
 #pragma unroll
       for (int i = 0; i < V; ++i) ga[i] += t[i];
     }
-    load_vec<T, V>(vptr<T>(x, n, h, w, c), pre);
+    if (x.ptr) {
+      load_vec<T, V>(vptr<T>(x, n, h, w, c), pre);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) pre[i] = 0.f;
+    }
     if (stats) {
       const float* st = stats + ((long long)n * C + c) * 2;
 #pragma unroll
@@ -626,29 +631,35 @@ int otm_norm_act(const otm_norm_act_args* a, otm_stream stream) {
 
 int otm_norm_act_bwd(const otm_norm_act_bwd_args* a, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  OTM_REQUIRE(a && a->g.ptr && a->x.ptr && a->gx.ptr, "norm_act_bwd: null tensor");
-  OTM_REQUIRE(same_shape(a->g, a->x) && same_shape(a->gx, a->x), "norm_act_bwd: shape mismatch");
-  OTM_REQUIRE(a->g.dtype == a->x.dtype && a->gx.dtype == a->x.dtype, "norm_act_bwd: dtype");
+  OTM_REQUIRE(a && a->g.ptr && a->gx.ptr, "norm_act_bwd: null tensor");
+  // x (the forward input) may be omitted for a pure fold/add pass (no norm, no activation)
+  OTM_REQUIRE(a->x.ptr || (a->act == OTM_ACT_NONE && !a->stats), "norm_act_bwd: x required");
+  OTM_REQUIRE(same_shape(a->g, a->gx) && (!a->x.ptr || same_shape(a->gx, a->x)),
+              "norm_act_bwd: shape mismatch");
+  OTM_REQUIRE(a->g.dtype == a->gx.dtype && (!a->x.ptr || a->gx.dtype == a->x.dtype),
+              "norm_act_bwd: dtype");
   OTM_REQUIRE(!a->stats || a->sums, "norm_act_bwd: sums workspace required with stats");
   bool vok = vec_ok(a->g, 8) && vec_ok(a->x, 8) && vec_ok(a->gx, 8) && vec_ok(a->g2, 8) &&
              vec_ok(a->gres, 8);
   int rc = OTM_OK;
-  const int C = a->x.c;
-  OTM_DISPATCH_TV(a->x.dtype, vok, {
+  const otm_tensor& sh = a->gx;
+  const int C = sh.c;
+  OTM_DISPATCH_TV(sh.dtype, vok, {
     if (a->stats) {
-      OTM_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * a->x.n * C, st));
+      OTM_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * sh.n * C, st));
       NormActBwdReduceF<T, V> r;
       r.g = make_view(a->g); r.g2 = a->g2.ptr ? make_view(a->g2) : null_view();
       r.x = make_view(a->x); r.stats = a->stats; r.act = a->act; r.g_halo = a->g_halo; r.C = C;
-      rc = launch_nc_reduce<V>(r, a->x.n, a->x.h, a->x.w, C, a->sums, st);
+      rc = launch_nc_reduce<V>(r, sh.n, sh.h, sh.w, C, a->sums, st);
     }
     if (rc == OTM_OK) {
       NormActBwdApplyF<T, V> f;
       f.g = make_view(a->g); f.g2 = a->g2.ptr ? make_view(a->g2) : null_view();
-      f.x = make_view(a->x); f.stats = a->stats; f.act = a->act; f.g_halo = a->g_halo; f.C = C;
+      f.x = a->x.ptr ? make_view(a->x) : null_view();
+      f.stats = a->stats; f.act = a->act; f.g_halo = a->g_halo; f.C = C;
       f.gx = make_view(a->gx); f.gres = a->gres.ptr ? make_view(a->gres) : null_view();
-      f.sums = a->sums; f.inv_hw = 1.f / (float)(a->x.h * a->x.w);
-      rc = launch_ew<V>(f, a->x.n, a->x.h, a->x.w, C, st);
+      f.sums = a->sums; f.inv_hw = 1.f / (float)(sh.h * sh.w);
+      rc = launch_ew<V>(f, sh.n, sh.h, sh.w, C, st);
     }
   });
   return rc;

@@ -153,10 +153,10 @@ def norm_act(x, stats=None, act=ACT_NONE, residual=None, y_halo=0, out=None):
 def norm_act_bwd(g, x, stats=None, act=ACT_NONE, *, g_halo=0, g2=None, want_gres=False):
     """g: gradient w.r.t. the forward output; if g_halo>0 it is the INTERIOR view of the
     gradient w.r.t. the reflect-padded output."""
-    n, c, h, w = x.shape
-    gx = alloc(n, c, h, w, x.dtype, x.device)
-    gres = alloc(n, c, h, w, x.dtype, x.device) if want_gres else None
-    sums = torch.empty((n, c, 2), dtype=torch.float32, device=x.device) if stats is not None else None
+    n, c, h, w = g.shape
+    gx = alloc(n, c, h, w, g.dtype, g.device)
+    gres = alloc(n, c, h, w, g.dtype, g.device) if want_gres else None
+    sums = torch.empty((n, c, 2), dtype=torch.float32, device=g.device) if stats is not None else None
     a = L.NormActBwdArgs()
     a.g = L.tdesc(g)
     a.g_halo = g_halo
@@ -303,9 +303,10 @@ def affine_grad(x, coef, grad=None):
     return grad
 
 
-def loss_path(f1, f2, h, weight, scale, out, want_grad=True):
-    g1 = alloc(*_nchw(f1), f1.dtype, f1.device) if want_grad else None
-    g2 = alloc(*_nchw(f1), f1.dtype, f1.device) if want_grad else None
+def loss_path(f1, f2, h, weight, scale, out, want_grad=True, g1=None, g2=None):
+    if want_grad and g1 is None:
+        g1 = alloc(*_nchw(f1), f1.dtype, f1.device)
+        g2 = alloc(*_nchw(f1), f1.dtype, f1.device)
     d1, d2, dg1, dg2 = L.tdesc(f1), L.tdesc(f2), L.tdesc(g1), L.tdesc(g2)
     L.check(L.lib.otm_loss_path(_byref(d1), _byref(d2), L.ptr(h), weight, scale, L.ptr(out),
                                 _byref(dg1), _byref(dg2), L.stream_ptr()), "otm_loss_path")

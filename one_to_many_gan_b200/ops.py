@@ -1,0 +1,470 @@
+"""Fused stages of the training step as torch.autograd.Functions over the C-ABI kernels.
+
+Each Function is one *block* of the reference network with a hand-scheduled backward
+(SURVEY.md App. B): the convolutions run as implicit GEMMs (tcgen05 for the dense bf16
+layers, FFMA in fp32 parity mode), everything between two convolutions is one HBM pass.
+Tensors are logically NCHW / physically NHWC; a tensor "with halo p" is the interior view
+of a buffer whose p-pixel reflect border has been materialised by its producer, so the
+consumer convolution reads nn.ReflectionPad2d(p) for free.
+
+Block-boundary gradients are always the true (interior-shaped) gradients; gradients of
+halo-padded intermediates stay padded inside a block and are folded on load by the next
+pass."""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import kernels as K
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = K.ACT_NONE, K.ACT_RELU, K.ACT_LRELU, K.ACT_TANH
+
+# ---------------------------------------------------------------------------
+# weight staging cache: packs are rebuilt when the parameter changes
+# ---------------------------------------------------------------------------
+_EPOCH = 0
+_PACKS: dict = {}
+
+
+def invalidate_packs() -> None:
+    """Called by the optimiser after it has updated the flat parameter arenas in place."""
+    global _EPOCH
+    _EPOCH += 1
+    _PACKS.clear()
+
+
+def eq_scale(weight: torch.Tensor) -> float:
+    """EqualisedWeight constant c = 1/sqrt(fan_in) (reference layers.py:19)."""
+    return 1.0 / math.sqrt(weight[0].numel())
+
+
+def _pack(weight: torch.Tensor, dtype, transpose: bool):
+    key = (weight.data_ptr(), weight._version, _EPOCH, dtype, transpose)
+    p = _PACKS.get(key)
+    if p is None:
+        p = K.weight_pack(weight.detach(), eq_scale(weight), dtype, transpose=transpose)
+        _PACKS[key] = p
+    return p
+
+
+def _sqsum(weight: torch.Tensor):
+    key = (weight.data_ptr(), weight._version, _EPOCH, "q")
+    q = _PACKS.get(key)
+    if q is None:
+        q = K.weight_sqsum(weight.detach(), eq_scale(weight))
+        _PACKS[key] = q
+    return q
+
+
+def nhwc(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    """API-boundary normalisation (plumbing): channel-stride-1 storage in `dtype`."""
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    ok = (w == 1 or sw > 0) and (h == 1 or sh > 0) and (n == 1 or sn > 0)
+    if c != 1:
+        ok = ok and sc == 1
+    if not ok:
+        t = t.contiguous(memory_format=torch.channels_last)
+        if c != 1 and t.stride(1) != 1:  # degenerate spatial dims: force NHWC strides
+            t = t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    return t
+
+
+def halo_of(t: torch.Tensor) -> int:
+    """Width of the reflect halo materialised around `t` by its producer (0 if unknown)."""
+    return getattr(t, "_otm_halo", 0)
+
+
+def with_halo(t: torch.Tensor, p: int) -> torch.Tensor:
+    t._otm_halo = p
+    return t
+
+
+def _g(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    return nhwc(t, like.dtype)
+
+
+# ---------------------------------------------------------------------------
+# plain convolution (+bias, + sign-preserving activation)
+# ---------------------------------------------------------------------------
+class ConvFn(torch.autograd.Function):
+    """EqualisedConv2d (reference layers.py:82-102) with the following activation fused when
+    it is ReLU/LeakyReLU.  x may carry a reflect halo (x_halo) = the ReflectionPad2d in front
+    of the conv; `pad` is the total logical padding (halo + zero padding)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype):
+        cout = weight.shape[0]
+        wp = _pack(weight, x.dtype, False)
+        y = K.conv_fwd(x, wp, cout, k, k, pad, x_halo=x_halo, y_halo=y_halo,
+                       bias=bias.detach() if bias is not None else None, act=act,
+                       out_dtype=out_dtype)
+        ctx.cfg = (k, pad, x_halo, act)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, y = ctx.saved_tensors
+        k, pad, x_halo, act = ctx.cfg
+        cin = weight.shape[1]
+        g = nhwc(g)
+        if act != ACT_NONE:  # relu / lrelu: derivative from the sign of the output
+            g = K.norm_act_bwd(g, y, None, act)
+        gw = gb = gx = None
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros_like(weight)
+            gq = g if g.dtype == x.dtype else K.cast(g, x.dtype)
+            K.conv_wgrad(x, gq, gw, k, k, pad, x_halo=x_halo, alpha=eq_scale(weight))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = K.channel_sum(g)
+        if ctx.needs_input_grad[0]:
+            wpt = _pack(weight, g.dtype, True)
+            gxp = K.conv_fwd(g, wpt, cin, k, k, k - 1 - pad + x_halo, out_dtype=x.dtype)
+            if x_halo:
+                h, w = x.shape[2:]
+                gint = gxp[:, :, x_halo : x_halo + h, x_halo : x_halo + w]
+                gx = K.norm_act_bwd(gint, None, None, ACT_NONE, g_halo=x_halo)
+            else:
+                gx = gxp
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+def conv(x, weight, bias, k, pad, *, x_halo=0, y_halo=0, act=ACT_NONE, out_dtype=None):
+    return ConvFn.apply(x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype or x.dtype)
+
+
+# ---------------------------------------------------------------------------
+# instance norm + activation (+ residual) (+ reflect halo)
+# ---------------------------------------------------------------------------
+class NormActFn(torch.autograd.Function):
+    """nn.InstanceNorm2d -> activation -> (+ residual) -> ReflectionPad2d(y_halo) in one pass
+    (reference blocks.py:20-33, builder.py:161-165)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, norm, act, y_halo):
+        stats = K.instnorm_stats(x) if norm else None
+        y = K.norm_act(x, stats, act, residual=residual, y_halo=y_halo)
+        ctx.act = act
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, stats = ctx.saved_tensors
+        g = _g(g, x)
+        want_res = ctx.has_res and ctx.needs_input_grad[1]
+        r = K.norm_act_bwd(g, x, stats, ctx.act, want_gres=want_res)
+        gx, gres = (r if want_res else (r, None))
+        return gx, gres, None, None, None
+
+
+def norm_act(x, *, norm=True, act=ACT_NONE, residual=None, y_halo=0):
+    return NormActFn.apply(x, residual, norm, act, y_halo)
+
+
+class DownFn(torch.autograd.Function):
+    """(InstanceNorm -> activation ->) DownSample (reference layers.py:232-247) in one pass."""
+
+    @staticmethod
+    def forward(ctx, x, norm, act, y_halo):
+        stats = K.instnorm_stats(x) if norm else None
+        y = K.down(x, stats, act, y_halo)
+        ctx.act = act
+        ctx.save_for_backward(x, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, stats = ctx.saved_tensors
+        g = _g(g, x)
+        ga = K.down_bwd(g, x.shape[2:])
+        if stats is None and ctx.act == ACT_NONE:
+            return ga, None, None, None
+        return K.norm_act_bwd(ga, x, stats, ctx.act), None, None, None
+
+
+def down(x, *, norm=False, act=ACT_NONE, y_halo=0):
+    return DownFn.apply(x, norm, act, y_halo)
+
+
+class UpFn(torch.autograd.Function):
+    """UpSample: bilinear x2 + blur (reference layers.py:217-229)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.up(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.up_bwd(nhwc(g))
+
+
+def up(x):
+    return UpFn.apply(x)
+
+
+class ResBlockFn(torch.autograd.Function):
+    """ResnetBlock (reference blocks.py:9-33): x + IN(conv(refl(ReLU(IN(conv(refl(x))))))).
+    x carries a reflect halo of 1."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, y_halo):
+        f = w1.shape[0]
+        raw1 = K.conv_fwd(x, _pack(w1, x.dtype, False), f, 3, 3, 1, x_halo=1)
+        st1 = K.instnorm_stats(raw1)
+        t = K.norm_act(raw1, st1, ACT_RELU, y_halo=1)
+        raw2 = K.conv_fwd(t, _pack(w2, x.dtype, False), f, 3, 3, 1, x_halo=1)
+        st2 = K.instnorm_stats(raw2)
+        out = K.norm_act(raw2, st2, ACT_NONE, residual=x, y_halo=y_halo)
+        ctx.save_for_backward(x, w1, w2, raw1, st1, t, raw2, st2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w1, w2, raw1, st1, t, raw2, st2 = ctx.saved_tensors
+        g = _g(g, x)
+        n, f, h, w = x.shape
+        g_raw2 = K.norm_act_bwd(g, raw2, st2, ACT_NONE)
+        gw1 = gw2 = None
+        if ctx.needs_input_grad[2]:
+            gw2 = torch.zeros_like(w2)
+            K.conv_wgrad(t, g_raw2, gw2, 3, 3, 1, x_halo=1, alpha=eq_scale(w2))
+        gt_p = K.conv_fwd(g_raw2, _pack(w2, g.dtype, True), f, 3, 3, 2)
+        g_raw1 = K.norm_act_bwd(gt_p[:, :, 1 : 1 + h, 1 : 1 + w], raw1, st1, ACT_RELU, g_halo=1)
+        if ctx.needs_input_grad[1]:
+            gw1 = torch.zeros_like(w1)
+            K.conv_wgrad(x, g_raw1, gw1, 3, 3, 1, x_halo=1, alpha=eq_scale(w1))
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx_p = K.conv_fwd(g_raw1, _pack(w1, g.dtype, True), f, 3, 3, 2)
+            gx = K.norm_act_bwd(gx_p[:, :, 1 : 1 + h, 1 : 1 + w], None, None, ACT_NONE, g_halo=1, g2=g)
+        return gx, gw1, gw2, None
+
+
+def res_block(x, w1, w2, *, y_halo):
+    return ResBlockFn.apply(x, w1, w2, y_halo)
+
+
+# ---------------------------------------------------------------------------
+# modulated convolutions (reference layers.py:111-182, dense form SURVEY App. B.2)
+# ---------------------------------------------------------------------------
+def _modconv_fwd(x, s, weight, pad, x_halo, act, residual, y_halo):
+    """y = act(sigma_inv[b,o] * conv(x, cW * s[b,i])) (+ residual).  Returns (y, sigma_inv)."""
+    n = x.shape[0]
+    cout = weight.shape[0]
+    c = eq_scale(weight)
+    sig = K.demod(s, _sqsum(weight))
+    wp = K.weight_pack(weight.detach(), c, x.dtype, cs=s, nb=n)
+    y = K.conv_fwd(x, wp, cout, 3, 3, pad, x_halo=x_halo, y_halo=y_halo, row_scale=sig, act=act,
+                   residual=residual, per_sample=True)
+    return y, sig
+
+
+def _modconv_bwd(gy, P, x, s, sig, weight, pad, x_halo, gadd, need_x):
+    """gy: gradient w.r.t. the pre-activation conv output; P[b,o] = sum_hw gy*y.
+    Returns (gx, ds, dw)."""
+    n, cin, h, w = x.shape
+    c = eq_scale(weight)
+    dw = torch.zeros_like(weight)
+    K.conv_wgrad(x, gy, dw, 3, 3, pad, x_halo=x_halo, alpha=c, rs=sig, cs=s)
+    # dgrad with the un-modulated, demodulated weights: gxt = d L / d (s*x)
+    wpt = K.weight_pack(weight.detach(), c, gy.dtype, rs=sig, nb=n, transpose=True)
+    gxt_p = K.conv_fwd(gy, wpt, cin, 3, 3, 2 - pad + x_halo, per_sample=True)
+    gint = gxt_p[:, :, x_halo : x_halo + h, x_halo : x_halo + w] if x_halo else gxt_p
+    gx, Q = K.mod_in(gint, x, s, g_halo=x_halo, gadd=gadd)
+    ds = K.mod_bwd(weight.detach(), c, s, sig, _sqsum(weight), P, Q, dw)
+    return (gx if need_x else None), ds, dw
+
+
+class ModConvFn(torch.autograd.Function):
+    """Conv2dWeightModulate (+ ReLU) with zero padding 1 (the up-sampling stages,
+    reference builder.py:190-197)."""
+
+    @staticmethod
+    def forward(ctx, x, s, weight, act, y_halo, pad):
+        s = s.contiguous().float()
+        y, sig = _modconv_fwd(x, s, weight, pad, 0, act, None, y_halo)
+        ctx.act, ctx.pad = act, pad
+        ctx.save_for_backward(x, s, weight, sig, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s, weight, sig, y = ctx.saved_tensors
+        g = _g(g, y)
+        gy, P = K.mod_out(g, y, act=ctx.act, materialise=ctx.act != ACT_NONE)
+        if gy is None:
+            gy = g
+        gx, ds, dw = _modconv_bwd(gy, P, x, s, sig, weight, ctx.pad, 0, None,
+                                  ctx.needs_input_grad[0])
+        return gx, ds, dw, None, None, None
+
+
+def mod_conv(x, s, weight, *, act=ACT_RELU, y_halo=0, pad=1):
+    return ModConvFn.apply(x, s, weight, act, y_halo, pad)
+
+
+class ModResBlockFn(torch.autograd.Function):
+    """ModulatedResnetBlock (reference blocks.py:36-68):
+    x + modconv2(refl(ReLU(modconv1(refl(x), w))), w); x carries a reflect halo of 1."""
+
+    @staticmethod
+    def forward(ctx, x, s1, s2, w1, w2, y_halo):
+        s1 = s1.contiguous().float()
+        s2 = s2.contiguous().float()
+        h, sig1 = _modconv_fwd(x, s1, w1, 1, 1, ACT_RELU, None, 1)
+        out, sig2 = _modconv_fwd(h, s2, w2, 1, 1, ACT_NONE, x, y_halo)
+        ctx.save_for_backward(x, s1, s2, w1, w2, h, sig1, sig2, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s1, s2, w1, w2, h, sig1, sig2, out = ctx.saved_tensors
+        g = _g(g, x)
+        # conv2: y2 = out - x, no activation
+        _, P2 = K.mod_out(g, out, res=x, materialise=False)
+        gh, ds2, dw2 = _modconv_bwd(g, P2, h, s2, sig2, w2, 1, 1, None, True)
+        # conv1: ReLU
+        gy1, P1 = K.mod_out(gh, h, act=ACT_RELU)
+        gx, ds1, dw1 = _modconv_bwd(gy1, P1, x, s1, sig1, w1, 1, 1, g, ctx.needs_input_grad[0])
+        return gx, ds1, ds2, dw1, dw2, None
+
+
+def mod_res_block(x, s1, s2, w1, w2, *, y_halo):
+    return ModResBlockFn.apply(x, s1, s2, w1, w2, y_halo)
+
+
+# ---------------------------------------------------------------------------
+# global average pool (StyleExtractor head)
+# ---------------------------------------------------------------------------
+class AvgPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape, ctx.dtype = tuple(x.shape), x.dtype
+        return K.avgpool(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.avgpool_bwd(g.contiguous().float(), ctx.shape, ctx.dtype)
+
+
+def avgpool(x):
+    return AvgPoolFn.apply(x)
+
+
+# ---------------------------------------------------------------------------
+# losses: forward writes the scalar and the backward seed in the same pass
+# ---------------------------------------------------------------------------
+# The training step sums its loss terms with unit coefficients (each term's lambda is folded
+# into the kernel that writes the backward seed), so the upstream gradient is exactly 1 and
+# the seeds can be returned as they are.  Set to False to use the loss functions generically.
+UNIT_LOSS_GRADS = False
+
+
+def _scaled(seed, g):
+    """seed was computed for an upstream gradient of 1; rescale if autograd hands us another."""
+    if UNIT_LOSS_GRADS or seed is None:
+        return seed
+    return seed * g.to(seed.dtype)
+
+
+class LsganFn(torch.autograd.Function):
+    """mean((scores - target)^2) and mean(sign(2 s - 1)) (reference training.py:86,111-117)."""
+
+    @staticmethod
+    def forward(ctx, scores, target, weight):
+        out, seed = K.loss_lsgan(scores, target, weight, want_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(seed)
+        conf = out[1:2].clone()
+        ctx.mark_non_differentiable(conf)
+        return out[0:1] * weight, conf
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (seed,) = ctx.saved_tensors
+        return _scaled(seed, g), None, None
+
+
+def lsgan(scores, target, weight=1.0):
+    """Returns (weight * loss, confidence) as 1-element tensors."""
+    return LsganFn.apply(nhwc(scores), float(target), float(weight))
+
+
+class L1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, weight):
+        out, seed = K.loss_l1(a, b, weight, want_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(seed)
+        return out * weight
+
+    @staticmethod
+    def backward(ctx, g):
+        (seed,) = ctx.saved_tensors
+        return _scaled(seed, g), None, None
+
+
+def l1(a, b, weight=1.0):
+    return L1Fn.apply(nhwc(a), nhwc(b, a.dtype), float(weight))
+
+
+class KlFn(torch.autograd.Function):
+    """kl_loss_func (reference loss.py:82-92): mean^2 + (biased var - 1)^2 over all elements."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        mom = K.moments(x)
+        n = float(x.numel())
+        m = mom[0] / n
+        v = mom[1] / n - m * m
+        # d kl / dx_i = c0 + c1 x_i
+        c1 = 4.0 * (v - 1.0) / n * weight
+        c0 = (2.0 * m / n) * weight - c1 * m
+        ctx.save_for_backward(x, torch.stack([c0, c1]))
+        return (m * m + (v - 1.0) ** 2).reshape(1) * weight
+
+    @staticmethod
+    def backward(ctx, g):
+        x, coef = ctx.saved_tensors
+        return K.affine_grad(x, (coef * g.reshape(())).contiguous()), None
+
+
+def kl(x, weight=1.0):
+    return KlFn.apply(x, float(weight))
+
+
+class PathFn(torch.autograd.Function):
+    """path_loss_func (reference loss.py:98-111).  Each feature tensor holds the two
+    extractions of the same latent stacked along the batch: [f1 ; f2] of shape [2B, ...]."""
+
+    @staticmethod
+    def forward(ctx, h, weight, *feats):
+        L = len(feats)
+        b = feats[0].shape[0] // 2
+        out = torch.zeros(1, dtype=torch.float32, device=h.device)
+        seeds = []
+        for idx, f in enumerate(feats):
+            g = None
+            if ctx.needs_input_grad[2 + idx]:
+                n, c, hh, ww = f.shape
+                g = K.alloc(n, c, hh, ww, f.dtype, f.device)
+            K.loss_path(f[:b], f[b:], h, 1.0 / L, weight, out, want_grad=g is not None,
+                        g1=None if g is None else g[:b], g2=None if g is None else g[b:])
+            seeds.append(g)
+        ctx.save_for_backward(*seeds)
+        return out * weight
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None, *[_scaled(s, g) for s in ctx.saved_tensors])
+
+
+def path(feats, h, weight=1.0):
+    """feats: list of [2B,C,H,W] tensors ([f1 ; f2] stacked); h: [B] finite-difference steps."""
+    return PathFn.apply(h.contiguous().float(), float(weight), *feats)

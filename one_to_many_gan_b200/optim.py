@@ -1,0 +1,112 @@
+"""Adam over flat fp32 arenas (one kernel per optimiser step) + data-parallel gradient
+all-reduce of the same arena over NCCL.
+
+Replaces torch.optim.Adam as used by reference train.py:94-116 (defaults: eps 1e-8, no weight
+decay, no amsgrad).  Parameters, gradients and both moments of one network live in four
+contiguous buffers; `param.data` / `param.grad` are views into them, so autograd accumulates
+straight into the all-reduce bucket and the update is a single 128-bit-vectorised pass."""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+from . import ops
+
+_ALIGN = 64  # elements; keeps every tensor 256-byte aligned inside the arena
+
+
+class FlatAdam:
+    def __init__(self, params, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, *,
+                 process_group=None, data_parallel: bool | None = None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatAdam got an empty parameter list")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdam needs CUDA parameters (no CPU fallback)")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.offsets = []
+        total = 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = total
+        self.param_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.steps = 0
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.param_arena[off : off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+        self._attach_grads()
+        self.group = process_group
+        if data_parallel is None:
+            data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.data_parallel = data_parallel
+        self.world = dist.get_world_size(process_group) if data_parallel else 1
+        self._pending = None
+        ops.invalidate_packs()
+
+    def _attach_grads(self):
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.grad_arena[off : off + p.numel()].view_as(p)
+
+    def zero_grad(self, set_to_none: bool = False):
+        """One memset over the arena; gradients stay views of it (set_to_none is accepted for
+        signature compatibility and ignored)."""
+        self.grad_arena.zero_()
+        if any(p.grad is None or p.grad.data_ptr() != self.grad_arena.data_ptr() + 4 * off
+               for p, off in zip(self.params, self.offsets)):
+            self._attach_grads()
+
+    def all_reduce_async(self):
+        """Sum-all-reduce the gradient arena (NCCL over NVLink); averaged inside the Adam kernel."""
+        if self.data_parallel and self._pending is None:
+            self._pending = dist.all_reduce(self.grad_arena, op=dist.ReduceOp.SUM, group=self.group,
+                                            async_op=True)
+
+    def step(self):
+        if self.data_parallel:
+            self.all_reduce_async()
+            self._pending.wait()
+            self._pending = None
+        self.steps += 1
+        self.step_dev += 1
+        K.adam(self.param_arena, self.grad_arena, self.exp_avg, self.exp_avg_sq, self.step_dev,
+               self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
+        ops.invalidate_packs()
+
+    # torch.optim.Adam-compatible checkpoint layout (reference evaluation.py:248-263)
+    def state_dict(self):
+        state = {}
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            n = p.numel()
+            state[i] = {
+                "step": torch.tensor(float(self.steps)),
+                "exp_avg": self.exp_avg[off : off + n].view_as(p).clone(),
+                "exp_avg_sq": self.exp_avg_sq[off : off + n].view_as(p).clone(),
+            }
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        with torch.no_grad():
+            for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+                st = sd["state"].get(i)
+                if st is None:
+                    continue
+                n = p.numel()
+                self.exp_avg[off : off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off : off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                self.steps = int(st["step"])
+            self.step_dev.fill_(self.steps)
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])

@@ -1,0 +1,280 @@
+"""The two halves of one training iteration, with the signatures and return values of the
+reference's src/core/training.py (`discriminator_step` :71-128, `generator_step` :136-257),
+executing on the B200 kernels.
+
+What is kept: the order of host RNG draws, every loss definition and weight,
+the ImageBuffer / ADAp host logic, the (float, tuple-of-floats) return values.
+What is scheduled differently (same mathematics):
+  * the generator forward inside the D step runs without building an autograd graph (the
+    reference builds one and discards it, training.py:98);
+  * fake and real images go through the discriminator as ONE 2B batch, the three image
+    decodes (reconstruction, identity, translation) as ONE 3B batch and the two path-length
+    extractions as ONE 2B batch (InstanceNorm and the style modulation are per-sample, so the
+    results are identical);
+  * discriminator weight gradients are not computed in the G step (the reference computes and
+    then zeroes them, training.py:245 vs :88);
+  * every loss weight is folded into the kernel that writes its backward seed, and the 3+7
+    logged scalars come back in one device->host copy instead of ten."""
+
+from __future__ import annotations
+
+import random
+from collections.abc import Iterator
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .builder import Discriminator, Generator, MappingNetwork, StyleExtractor
+
+
+class ImageBuffer:
+    """History pool of generated images (reference training.py:22-65)."""
+
+    def __init__(self, buffer_size: int):
+        self.buffer_size = buffer_size
+        if self.buffer_size < 1:
+            raise ValueError
+        self.num_imgs = 0
+        self.images: list[torch.Tensor] = []
+
+    def __call__(self, images: torch.Tensor):
+        out = []
+        for image in images:
+            image = torch.unsqueeze(image.detach(), 0)
+            if self.num_imgs < self.buffer_size:
+                self.num_imgs += 1
+                self.images.append(image)
+                out.append(image)
+            else:
+                if random.uniform(0, 1) > 0.5:
+                    k = random.randint(0, self.buffer_size - 1)
+                    out.append(self.images[k].clone())
+                    self.images[k] = image
+                else:
+                    out.append(image)
+        return torch.cat(out, 0)
+
+
+class ADAp:
+    """Adaptive-augmentation probability controller (reference loss.py:11-52, host side)."""
+
+    def __init__(self, ada_e: float, ada_adjustment_size: float, batch_size: int,
+                 discriminator_overfitting_target: float):
+        self.n_batches = ada_e // batch_size
+        self.ada_adjustment = ada_adjustment_size * ada_e
+        self.overfitting_target = discriminator_overfitting_target
+        self.p = torch.zeros(())
+        self.curr_batch = 0
+        self.mean_real_scores: list[torch.Tensor] = []
+
+    def update_p(self, mean_score: torch.Tensor):
+        if self.curr_batch == self.n_batches:
+            self.mean_real_scores.append(mean_score)
+            mean_sign = torch.mean(torch.stack(self.mean_real_scores)).cpu()
+            if mean_sign < self.overfitting_target:
+                self.p -= self.ada_adjustment
+            elif mean_sign > self.overfitting_target:
+                self.p += self.ada_adjustment
+            self.curr_batch = 0
+            self.mean_real_scores = []
+            self.p = F.relu(self.p, inplace=True)
+        self.curr_batch += 1
+        self.mean_real_scores.append(mean_score)
+
+    def __call__(self) -> float:
+        return self.p.item()
+
+
+class IdentityAugment(torch.nn.Module):
+    """Stand-in with the call surface of pytorch-ada's AdaptiveDiscriminatorAugmentation
+    (reference train.py:175-188,206).  Exact while ADA p == 0; the augmentation pipeline itself
+    is out of scope for the hot path."""
+
+    def __init__(self, **_kw):
+        super().__init__()
+        self.p = 0.0
+
+    def set_p(self, p):
+        if p != 0:
+            raise NotImplementedError("non-zero ADA probability needs the pytorch-ada pipeline")
+        self.p = p
+
+    def forward(self, x):
+        return x
+
+
+def style_cycle_loss_func(original_w, reconstructed_w, *, normalise=True, cos_l2_ratio: float = 0.2):
+    """Reference loss.py:60-75 on [B, w_dim] tensors."""
+    if normalise:
+        original_w = F.normalize(original_w, dim=-1)
+        reconstructed_w = F.normalize(reconstructed_w, dim=-1)
+    cos_loss = 1 - F.cosine_similarity(original_w, reconstructed_w, dim=-1).mean()
+    return cos_loss + cos_l2_ratio * F.mse_loss(original_w, reconstructed_w)
+
+
+def _floats(*tensors) -> list[float]:
+    """One device->host copy for all logged scalars."""
+    return torch.stack([t.detach().reshape(()).float() for t in tensors]).cpu().tolist()
+
+
+def discriminator_step(
+    config,
+    device: torch.device,
+    discriminator: Discriminator,
+    generator: Generator,
+    mapping_network: MappingNetwork,
+    discriminator_optimiser,
+    shoeprint_iter: Iterator[torch.Tensor],
+    shoemark_iter: Iterator[torch.Tensor],
+    image_buffer: ImageBuffer,
+    ada,
+    ada_p: ADAp,
+):
+    """Take a step with the discriminator and return (loss, (real confidence, fake confidence))."""
+    discriminator_optimiser.zero_grad()
+    batch = config["training"]["batch_size"]
+
+    shoeprint_images = next(shoeprint_iter).to(device)
+    w = mapping_network.get_single_w(
+        batch_size=batch, n_gen_blocks=generator.n_style_blocks, device=device, domain_variable=1
+    )
+    with torch.no_grad():
+        generated_shoemarks = generator(shoeprint_images, w)
+    buffered_shoemarks = image_buffer(generated_shoemarks)
+    augmented_fake = ada(buffered_shoemarks)
+    real_shoemarks = next(shoemark_iter).to(device)
+    augmented_real = ada(real_shoemarks)
+
+    scores = discriminator(torch.cat([augmented_fake, augmented_real], dim=0))
+    fake_scores, real_scores = scores[:batch], scores[batch:]
+    # disc_loss = (mse(real, 1) + mse(fake, 0)) / 2  (reference training.py:111-113)
+    real_loss, sign_real = ops.lsgan(real_scores, 1.0, 0.5)
+    fake_loss, sign_fake = ops.lsgan(fake_scores, 0.0, 0.5)
+    disc_loss = real_loss + fake_loss
+    sign_fake = -sign_fake
+
+    ada_p.update_p(sign_real.reshape(()))
+
+    ops.UNIT_LOSS_GRADS = True
+    try:
+        disc_loss.backward()
+    finally:
+        ops.UNIT_LOSS_GRADS = False
+    discriminator_optimiser.step()
+
+    loss, s_real, s_fake = _floats(disc_loss, sign_real, sign_fake)
+    return loss, (s_real, s_fake)
+
+
+def generator_step(
+    config,
+    device: torch.device,
+    generator: Generator,
+    discriminator: Discriminator,
+    mapping_network: MappingNetwork,
+    style_extractor: StyleExtractor,
+    generator_optimiser,
+    mapping_network_optimiser,
+    style_extractor_optimiser,
+    shoeprint_iter: Iterator[torch.Tensor],
+    shoemark_iter: Iterator[torch.Tensor],
+    ada,
+    *,
+    cent_fin_diff_h: torch.Tensor | None = None,
+):
+    """Take a step with the generator and return (total, (gan, rec, idt, kl, path, style)).
+
+    `cent_fin_diff_h` (optional, not in the reference signature) injects the finite-difference
+    step the reference draws from the device generator (training.py:216-223) so seeded parity
+    tests can replay it."""
+    generator_optimiser.zero_grad()
+    mapping_network_optimiser.zero_grad()
+    style_extractor_optimiser.zero_grad()
+    opt = config["optimisation"]
+    batch = config["training"]["batch_size"]
+    nb = generator.n_style_blocks
+
+    real_shoeprint_images = next(shoeprint_iter).to(device)
+    real_shoemark_images = next(shoemark_iter).to(device)
+
+    combined_latents = generator.encode(torch.cat([real_shoeprint_images, real_shoemark_images], dim=0))
+    kl_loss = ops.kl(combined_latents, opt["kl_loss_lambda"])
+    if config["architecture"]["add_latent_noise"]:
+        combined_latents = combined_latents + torch.randn_like(combined_latents)
+    shoeprint_latent, shoemark_latent = combined_latents.chunk(2, dim=0)
+
+    # --- styles, in the reference's host-RNG draw order ----------------------
+    reconstruct_w = mapping_network.get_single_w(
+        batch_size=batch, n_gen_blocks=nb, device=device, domain_variable=0
+    )
+    real_shoemark_w = style_extractor(real_shoemark_images)
+    identity_w = real_shoemark_w.expand(nb, *real_shoemark_w.shape)
+    translation_w = mapping_network.get_single_w(
+        batch_size=batch, n_gen_blocks=nb, device=device, domain_variable=1
+    )
+    theta = torch.rand(batch).to(device)
+    if cent_fin_diff_h is None:
+        lo, hi = opt["path_loss_jacobian_granularity"]
+        cent_fin_diff_h = torch.ones_like(theta).uniform_(lo, hi)
+    else:
+        cent_fin_diff_h = cent_fin_diff_h.to(device=device, dtype=torch.float32)
+    d1 = (theta + cent_fin_diff_h / 2).clamp(0, 1)
+    d2 = (theta - cent_fin_diff_h / 2).clamp(0, 1)
+    w1, w2 = mapping_network.get_two_w(
+        batch_size=batch, n_gen_blocks=nb, device=device, domain_variables=(d1, d2)
+    )
+
+    # --- reconstruction / identity / translation as one 3B decode ----------------------------
+    dec_latents = torch.cat([shoeprint_latent, shoemark_latent, shoeprint_latent], dim=0)
+    dec_w = torch.cat([reconstruct_w, identity_w, translation_w], dim=1)
+    images = generator.decode(dec_latents, dec_w)
+    reconstructed_shoeprints = images[:batch]
+    reconstructed_shoemarks = images[batch : 2 * batch]
+    generated_shoemarks = images[2 * batch :]
+
+    reconstruction_loss = ops.l1(
+        reconstructed_shoeprints, real_shoeprint_images, opt["reconstruction_loss_lambda"]
+    )
+    identity_loss = ops.l1(reconstructed_shoemarks, real_shoemark_images, opt["identity_loss_lambda"])
+
+    # --- GAN loss (the discriminator's own weight gradients are not needed here) -------------
+    d_params = [p for p in discriminator.parameters() if p.requires_grad]
+    for p in d_params:
+        p.requires_grad_(False)
+    try:
+        fake_shoemark_scores = discriminator(ada(generated_shoemarks))
+    finally:
+        for p in d_params:
+            p.requires_grad_(True)
+    gan_loss, _ = ops.lsgan(fake_shoemark_scores, 1.0, 1.0)
+
+    # --- style cycle -------------------------------------------------------------------------
+    reconstructed_w = style_extractor(generated_shoemarks)
+    style_loss = opt["style_cycle_loss_lambda"] * style_cycle_loss_func(
+        translation_w[-1], reconstructed_w
+    ).reshape(1)
+
+    # --- path length: two extractions of the same latent as one 2B batch ---------------------
+    feats = generator.extract(torch.cat([shoeprint_latent, shoeprint_latent], dim=0),
+                              torch.cat([w1, w2], dim=1))
+    path_loss = ops.path(feats, cent_fin_diff_h, opt["path_loss_lambda"])
+
+    total_gen_loss = gan_loss + identity_loss + reconstruction_loss + kl_loss + path_loss + style_loss
+
+    ops.UNIT_LOSS_GRADS = True
+    try:
+        total_gen_loss.backward()
+    finally:
+        ops.UNIT_LOSS_GRADS = False
+    generator_optimiser.step()
+    mapping_network_optimiser.step()
+    style_extractor_optimiser.step()
+
+    # report the UNWEIGHTED terms like the reference (training.py:250-257)
+    vals = _floats(total_gen_loss, gan_loss, reconstruction_loss, identity_loss, kl_loss, path_loss,
+                   style_loss)
+    lam = [1.0, 1.0, opt["reconstruction_loss_lambda"], opt["identity_loss_lambda"],
+           opt["kl_loss_lambda"], opt["path_loss_lambda"], opt["style_cycle_loss_lambda"]]
+    vals = [v / l if l != 0 else 0.0 for v, l in zip(vals, lam)]
+    return vals[0], tuple(vals[1:])
