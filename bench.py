@@ -1,0 +1,370 @@
+"""Headline benchmark: G+D training iterations per second (images/sec) of the one-to-many GAN.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): default architecture at 128x128, batch 32 per GPU, bf16
+activations / fp32 accumulation, synthetic U(-1,1) images, random-init weights (seed 42).
+One step = `discriminator_step` + `generator_step` (reference src/core/training.py:71,136).
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how each field is produced."""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+IMAGE = (128, 128)
+BATCH = 32
+GFLOP_PER_IMAGE = 301.7  # dense-conv algorithmic FLOPs per image per iteration, SURVEY.md §8(d)
+CONFIG = {
+    "training": {"batch_size": BATCH, "style_mixing_prob": 0.9, "random_seed": 42,
+                 "image_buffer_size": 100},
+    "optimisation": {
+        "style_cycle_loss_lambda": 5.0, "identity_loss_lambda": 5.0,
+        "reconstruction_loss_lambda": 5.0, "kl_loss_lambda": 0.01, "path_loss_lambda": 0.1,
+        "path_loss_jacobian_granularity": [0.1, 0.2], "learning_rate": 2e-3,
+        "mapping_network_learning_rate": 2e-5, "adam_betas": [0.5, 0.99],
+    },
+    "architecture": {"w_dim": 6, "add_latent_noise": False, "min_latent_resolution": 64,
+                     "n_resnet_blocks": 7, "mapping_network_layers": 2},
+    "data": {"image_size": list(IMAGE), "image_channels": 1},
+}
+WORKLOAD = "G+D train iteration, default arch, 128x128, batch 32/GPU, bf16 act / fp32 accum"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(index), "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class HostBatches:
+    """Pinned host batches: the e2e leg copies its inputs host->device every step."""
+
+    def __init__(self, shape, seed, n_distinct=4):
+        g = torch.Generator().manual_seed(seed)
+        self.pool = [(torch.rand(*shape, generator=g) * 2 - 1).pin_memory() for _ in range(n_distinct)]
+        self.i = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        t = self.pool[self.i % len(self.pool)]
+        self.i += 1
+        return t
+
+
+def build_trainer(device, rank):
+    from one_to_many_gan_b200 import builder, training
+    from one_to_many_gan_b200.optim import FlatAdam
+
+    torch.manual_seed(42)
+    arch = CONFIG["architecture"]
+    dt = torch.bfloat16
+    D = builder.Discriminator(1, act_dtype=dt).to(device)
+    G = builder.Generator(1, arch["w_dim"], IMAGE, arch["min_latent_resolution"],
+                          arch["n_resnet_blocks"], act_dtype=dt).to(device)
+    M = builder.MappingNetwork(arch["w_dim"], arch["mapping_network_layers"], 0.9).to(device)
+    S = builder.StyleExtractor(1, arch["w_dim"], act_dtype=dt).to(device)
+    o = CONFIG["optimisation"]
+    betas = tuple(o["adam_betas"])
+    opts = dict(
+        D=FlatAdam(D.parameters(), o["learning_rate"], betas),
+        G=FlatAdam(G.parameters(), o["learning_rate"], betas),
+        M=FlatAdam(M.parameters(), o["mapping_network_learning_rate"], betas),
+        S=FlatAdam(S.parameters(), o["learning_rate"], betas),
+    )
+    state = dict(D=D, G=G, M=M, S=S, opts=opts, buf=training.ImageBuffer(100),
+                 ada=training.IdentityAugment(), ada_p=training.ADAp(256, 5.12e-4, BATCH, 0.6))
+    torch.manual_seed(1234 + rank)  # per-rank style / theta draws
+
+    def step(prints, marks):
+        d = training.discriminator_step(CONFIG, device, D, G, M, opts["D"], prints, marks,
+                                        state["buf"], state["ada"], state["ada_p"])
+        g = training.generator_step(CONFIG, device, G, D, M, S, opts["G"], opts["M"], opts["S"],
+                                    prints, marks, state["ada"])
+        return d, g
+
+    return step
+
+
+def time_steps(step, prints, marks, steps, warmup, dist_on, device):
+    import torch.distributed as dist
+
+    for _ in range(warmup):
+        step(prints, marks)
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for _ in range(steps):
+        last = step(prints, marks)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms, last
+
+
+def dominant_kernel_roofline(device):
+    """The modulated / plain 3x3 128->128 conv at 64x64 is ~69 % of the dense MACs of this
+    workload.  Time that launch alone with CUDA events on the launching stream
+    (L2 flushed between launches) and quote achieved TFLOP/s against the measured burst peak."""
+    import math
+
+    from one_to_many_gan_b200 import kernels as K
+
+    n, c, hw = BATCH * 3, 128, 64  # the 3B decode batch the G step actually launches
+    x = K.alloc(n, c, hw, hw, torch.bfloat16, device, 1, zero=True)
+    K.padded_view(x, 1).normal_()
+    w = torch.randn(c, c, 3, 3, device=device)
+    s = torch.rand(n, c, device=device) + 0.5
+    sig = torch.rand(n, c, device=device) + 0.5
+    wp = K.weight_pack(w, 1 / math.sqrt(c * 9), torch.bfloat16, cs=s, nb=n)
+    y = K.alloc(n, c, hw, hw, torch.bfloat16, device, 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    flops = 2.0 * n * hw * hw * c * c * 9
+
+    def launch():
+        K.conv_fwd(x, wp, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, act=K.ACT_RELU,
+                   per_sample=True, out=y)
+
+    launch()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        launch()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = statistics.mean(ts)
+    pk, how = peaks()
+    ach = flops / ms / 1e9
+    return {"bound": "tensor", "kernel": "conv_tc_fwd_kernel<128> modulated 3x3 128->128 @64x64, n=96",
+            "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "peak_source": how + " burst",
+            "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4), "traffic": None,
+            "launch_ms": round(ms, 4), "flops_per_launch": flops}
+
+
+def cpu_baseline(sample_batch=2, iters=1, warm=0):
+    """The oracle port (oracle/reference_port.py) of the same iteration on the host cores."""
+    from oracle import reference_port as rp
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    arch = rp.Arch(image_size=IMAGE)
+    tr = rp.Trainer(arch, rp.Hyper(batch_size=sample_batch), rp.init_all(arch, 42))
+    shape = (sample_batch, 1, *IMAGE)
+
+    def one(i):
+        tr.discriminator_step(rp.synthetic_batch(sample_batch, arch, 10 + i), rp.synthetic_batch(sample_batch, arch, 20 + i))
+        tr.generator_step(rp.synthetic_batch(sample_batch, arch, 30 + i), rp.synthetic_batch(sample_batch, arch, 40 + i))
+
+    for i in range(warm):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(iters):
+        one(100 + i)
+    dt = time.perf_counter() - t0
+    del shape
+    return {"value": round(sample_batch * iters / dt, 4), "unit": "images/sec",
+            "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{iters} D+G iteration(s) at 128x128, batch {sample_batch} (workload batch is {BATCH}), fp32, torch CPU"}, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    reference itself is pure Python/PyTorch and is pinned to the port by tests/golden)."""
+    if rank != 0:
+        return
+    sample_batch = 2
+    from oracle import reference_port as rp
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    arch = rp.Arch(image_size=IMAGE)
+    tr = rp.Trainer(arch, rp.Hyper(batch_size=sample_batch), rp.init_all(arch, 42))
+
+    def one(i):
+        tr.discriminator_step(rp.synthetic_batch(sample_batch, arch, 10 + i), rp.synthetic_batch(sample_batch, arch, 20 + i))
+        tr.generator_step(rp.synthetic_batch(sample_batch, arch, 30 + i), rp.synthetic_batch(sample_batch, arch, 40 + i))
+
+    for i in range(args.warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(1000 + i)
+    dt = time.perf_counter() - t0
+    val = sample_batch * args.steps / dt
+    sample = (f"each step = one D+G iteration at 128x128 on batch {sample_batch} (bounded sample of the "
+              f"batch-{BATCH} workload; per-image cost is batch-independent: per-sample norms)")
+    line = {
+        "impl": "reference", "metric": "G+D train-step images/sec", "value": round(val, 4),
+        "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1000 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_arm": sample},
+        "cpu_baseline": {"value": round(val, 4), "unit": "images/sec", "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": "images/sec", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist_on = world > 1
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from one_to_many_gan_b200 import kernels as K
+    from one_to_many_gan_b200.synthetic import SyntheticImages
+
+    warmup = max(args.warmup, 3)
+    step = build_trainer(device, rank)
+    prints = SyntheticImages(BATCH, 1, IMAGE, device, seed=42, rank=rank, stream_id=0)
+    marks = SyntheticImages(BATCH, 1, IMAGE, device, seed=42, rank=rank, stream_id=1)
+
+    # ---- leg 1: inputs resident in HBM (synthetic generator on device) ---------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = K.launch_count()
+    ms, last = time_steps(step, prints, marks, args.steps, warmup, dist_on, device)
+    launches = (K.launch_count() - l0) * 1.0 * args.steps / (args.steps + warmup)
+    clocks = sampler.stop() if sampler else None
+    value = world * BATCH * args.steps / (ms / 1e3)
+
+    # ---- leg 2: end to end through the public step API with pinned HOST batches -------------
+    shape = (BATCH, 1, *IMAGE)
+    hp, hm = HostBatches(shape, 1 + rank), HostBatches(shape, 1001 + rank)
+    ms_e2e, _ = time_steps(step, hp, hm, args.steps, 1, dist_on, device)
+    e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
+    h2d = 4 * BATCH * IMAGE[0] * IMAGE[1] * 4  # 2 batches per half-step x 2 half-steps, fp32
+    d2h = 10 * 4  # the 3 + 7 logged scalars
+
+    if rank == 0:
+        pk, how = peaks()
+        roof = dominant_kernel_roofline(device)
+        conv_tflops = GFLOP_PER_IMAGE * value / world / 1e3
+        line = {
+            "metric": "G+D train-step images/sec", "value": round(value, 2), "unit": "images/sec",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world,
+                       "parallelism": f"dp{world}", "l2": "activations per step (>1 GB) exceed the 126 MB L2",
+                       "losses": [float(last[0][0]), float(last[1][0])]},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(round(launches * args.steps)),
+            "roofline": roof,
+            "conv_step_roofline": {
+                "achieved_tflops_per_gpu": round(conv_tflops, 1), "peak": pk["bf16_tflops_sustained"],
+                "peak_source": how + " sustained",
+                "frac": round(conv_tflops / pk["bf16_tflops_sustained"], 4),
+                "note": "algorithmic dense-conv FLOPs/image (SURVEY 8d) x images/s / sustained bf16 peak",
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

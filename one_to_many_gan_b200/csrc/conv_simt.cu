@@ -251,6 +251,84 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
 }
 
 // ---------------------------------------------------------------------------
+// wgrad for skinny outputs (Cout <= 4): one CTA per (sample, TT x TT output tile).  The input
+// patch and the dy tile are staged in shared memory once; each thread owns up to WG_MAXI
+// (tap, channel, cout) accumulators, reads the patch conflict-free (consecutive threads ->
+// consecutive channels) and finishes with one atomicAdd per accumulator.
+// ---------------------------------------------------------------------------
+constexpr int WG_MAXI = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT, int tiles_w) {
+  extern __shared__ __align__(16) unsigned char wg_smem[];
+  const int n = blockIdx.z;
+  const int tile = blockIdx.x;
+  const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
+  const int PW = TT + p.kw - 1, PH = TT + p.kh - 1;
+  T* xs = reinterpret_cast<T*>(wg_smem);                       // [PH][PW][cin]
+  float* dys = reinterpret_cast<float*>(xs + (size_t)PH * PW * p.cin + 8);  // [TT*TT][cout]
+  const int H = p.x.h, W = p.x.w, halo = p.x_halo;
+  // stage the input patch (zero outside the readable region)
+  const int patch = PH * PW * p.cin;
+  for (int e = threadIdx.x; e < patch; e += 256) {
+    int c = e % p.cin, q = e / p.cin;
+    int pw = q % PW, ph = q / PW;
+    int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+    T v = from_f<T>(0.f);
+    if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo) v = *vptr<T>(p.x, n, ih, iw, c);
+    xs[e] = v;
+  }
+  for (int e = threadIdx.x; e < TT * TT * p.cout; e += 256) {
+    int o = e % p.cout, q = e / p.cout;
+    int oh = oh0 + q / TT, ow = ow0 + q % TT;
+    float v = 0.f;
+    if (oh < p.dy.h && ow < p.dy.w) v = to_f(*vptr<T>(p.dy, n, oh, ow, o));
+    dys[e] = v;
+  }
+  __syncthreads();
+  const int total = p.ktot * p.cout;  // items: (o, tap, c), c fastest
+  float acc[WG_MAXI];
+  int base[WG_MAXI];
+#pragma unroll
+  for (int i = 0; i < WG_MAXI; ++i) {
+    acc[i] = 0.f;
+    int item = threadIdx.x + i * 256;
+    if (item < total) {
+      int kk = item % p.ktot;
+      int tap = kk / p.cin, c = kk - tap * p.cin;
+      int r = tap / p.kw, s2 = tap - r * p.kw;
+      base[i] = (r * PW + s2) * p.cin + c;
+    } else {
+      base[i] = -1;
+    }
+  }
+  for (int q = 0; q < TT * TT; ++q) {
+    const int pixoff = ((q / TT) * PW + (q % TT)) * p.cin;
+    const float* dq = dys + q * p.cout;
+#pragma unroll
+    for (int i = 0; i < WG_MAXI; ++i) {
+      if (base[i] >= 0) {
+        int item = threadIdx.x + i * 256;
+        float d = dq[item / p.ktot];
+        acc[i] = fmaf(d, to_f(xs[base[i] + pixoff]), acc[i]);
+      }
+    }
+  }
+  const int taps = p.kh * p.kw;
+#pragma unroll
+  for (int i = 0; i < WG_MAXI; ++i) {
+    if (base[i] < 0) continue;
+    int item = threadIdx.x + i * 256;
+    int o = item / p.ktot, kk = item % p.ktot;
+    int tap = kk / p.cin, c = kk - tap * p.cin;
+    float v = acc[i] * p.alpha;
+    if (p.rs) v *= p.rs[(long long)n * p.cout + o];
+    if (p.cs) v *= p.cs[(long long)n * p.cin + c];
+    atomicAdd(p.dw + ((long long)o * p.cin + c) * taps + tap, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // weight staging / modulation coefficients
 // ---------------------------------------------------------------------------
 template <typename TO>
@@ -385,6 +463,32 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
   p.x_halo = a->x_halo; p.kh = a->kh; p.kw = a->kw; p.pad = a->pad;
   p.cin = a->x.c; p.cout = a->dy.c; p.ktot = a->kh * a->kw * a->x.c;
   p.dw = a->dw; p.alpha = a->alpha; p.rs = a->rs; p.cs = a->cs;
+  // skinny output: smem-tiled kernel
+  if (p.cout <= 4 && (long long)p.ktot * p.cout <= 256LL * WG_MAXI) {
+    const size_t es = dtype_size(a->x.dtype);
+    int TT = 16;
+    auto smem_for = [&](int tt) {
+      return (size_t)(tt + p.kh - 1) * (tt + p.kw - 1) * p.cin * es + 8 * es +
+             (size_t)tt * tt * p.cout * sizeof(float) + 16;
+    };
+    while (TT > 2 && smem_for(TT) > 96 * 1024) TT /= 2;
+    if (smem_for(TT) <= 200 * 1024) {
+      const int tiles_w = (a->dy.w + TT - 1) / TT, tiles_h = (a->dy.h + TT - 1) / TT;
+      dim3 grid(tiles_w * tiles_h, 1, a->dy.n);
+      const size_t smem = smem_for(TT);
+      if (a->x.dtype == OTM_BF16) {
+        auto kern = wgrad_small_cout_kernel<__nv_bfloat16>;
+        OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, st>>>(p, TT, tiles_w);
+      } else {
+        auto kern = wgrad_small_cout_kernel<float>;
+        OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, st>>>(p, TT, tiles_w);
+      }
+      OTM_LAUNCH_CHECK();
+      return OTM_OK;
+    }
+  }
   const int HW = a->dy.h * a->dy.w;
   const int base_ctas = ((p.ktot + TN - 1) / TN) * ((p.cout + TM - 1) / TM) * a->dy.n;
   int splits = (num_sms() * 4 + base_ctas - 1) / base_ctas;

@@ -40,22 +40,27 @@ def eq_scale(weight: torch.Tensor) -> float:
     return 1.0 / math.sqrt(weight[0].numel())
 
 
+def _cached(key, weight: torch.Tensor, make):
+    # The entry keeps a reference to the weight's storage, so its data_ptr cannot be recycled
+    # by another tensor while the entry is alive (a bare data_ptr key would alias).
+    hit = _PACKS.get(key)
+    if hit is None:
+        if len(_PACKS) > 512:
+            _PACKS.clear()
+        hit = (make(), weight.detach())
+        _PACKS[key] = hit
+    return hit[0]
+
+
 def _pack(weight: torch.Tensor, dtype, transpose: bool):
     key = (weight.data_ptr(), weight._version, _EPOCH, dtype, transpose)
-    p = _PACKS.get(key)
-    if p is None:
-        p = K.weight_pack(weight.detach(), eq_scale(weight), dtype, transpose=transpose)
-        _PACKS[key] = p
-    return p
+    return _cached(key, weight, lambda: K.weight_pack(weight.detach(), eq_scale(weight), dtype,
+                                                       transpose=transpose))
 
 
 def _sqsum(weight: torch.Tensor):
     key = (weight.data_ptr(), weight._version, _EPOCH, "q")
-    q = _PACKS.get(key)
-    if q is None:
-        q = K.weight_sqsum(weight.detach(), eq_scale(weight))
-        _PACKS[key] = q
-    return q
+    return _cached(key, weight, lambda: K.weight_sqsum(weight.detach(), eq_scale(weight)))
 
 
 def nhwc(t: torch.Tensor, dtype=None) -> torch.Tensor:

@@ -17,16 +17,16 @@ from . import ops
 _ALIGN = 64  # elements; keeps every tensor 256-byte aligned inside the arena
 
 
-class FlatAdam:
-    def __init__(self, params, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, *,
-                 process_group=None, data_parallel: bool | None = None):
+class GradArena:
+    """Flat parameter / gradient arenas of one network plus the data-parallel all-reduce.
+    Pure tensor plumbing (device agnostic): `param.data` and `param.grad` become views of two
+    contiguous fp32 buffers, so autograd accumulates straight into the all-reduce bucket."""
+
+    def __init__(self, params, *, process_group=None, data_parallel: bool | None = None):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
-            raise ValueError("FlatAdam got an empty parameter list")
+            raise ValueError("empty parameter list")
         dev = self.params[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("FlatAdam needs CUDA parameters (no CPU fallback)")
-        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.offsets = []
         total = 0
         for p in self.params:
@@ -35,10 +35,6 @@ class FlatAdam:
         self.numel = total
         self.param_arena = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.steps = 0
         with torch.no_grad():
             for p, off in zip(self.params, self.offsets):
                 view = self.param_arena[off : off + p.numel()].view_as(p)
@@ -47,11 +43,11 @@ class FlatAdam:
         self._attach_grads()
         self.group = process_group
         if data_parallel is None:
-            data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+            data_parallel = (dist.is_available() and dist.is_initialized()
+                             and dist.get_world_size(process_group) > 1)
         self.data_parallel = data_parallel
         self.world = dist.get_world_size(process_group) if data_parallel else 1
         self._pending = None
-        ops.invalidate_packs()
 
     def _attach_grads(self):
         for p, off in zip(self.params, self.offsets):
@@ -61,21 +57,41 @@ class FlatAdam:
         """One memset over the arena; gradients stay views of it (set_to_none is accepted for
         signature compatibility and ignored)."""
         self.grad_arena.zero_()
-        if any(p.grad is None or p.grad.data_ptr() != self.grad_arena.data_ptr() + 4 * off
+        base = self.grad_arena.data_ptr()
+        if any(p.grad is None or p.grad.data_ptr() != base + 4 * off
                for p, off in zip(self.params, self.offsets)):
             self._attach_grads()
 
     def all_reduce_async(self):
-        """Sum-all-reduce the gradient arena (NCCL over NVLink); averaged inside the Adam kernel."""
+        """Sum-all-reduce the gradient arena (NCCL over NVLink on the GPU box); the 1/world
+        averaging is folded into the Adam kernel's grad_scale."""
         if self.data_parallel and self._pending is None:
             self._pending = dist.all_reduce(self.grad_arena, op=dist.ReduceOp.SUM, group=self.group,
                                             async_op=True)
 
-    def step(self):
+    def wait_all_reduce(self):
         if self.data_parallel:
             self.all_reduce_async()
             self._pending.wait()
             self._pending = None
+
+
+class FlatAdam(GradArena):
+    def __init__(self, params, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, *,
+                 process_group=None, data_parallel: bool | None = None):
+        super().__init__(params, process_group=process_group, data_parallel=data_parallel)
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdam needs CUDA parameters (no CPU fallback)")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.exp_avg = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.steps = 0
+        ops.invalidate_packs()
+
+    def step(self):
+        self.wait_all_reduce()
         self.steps += 1
         self.step_dev += 1
         K.adam(self.param_arena, self.grad_arena, self.exp_avg, self.exp_avg_sq, self.step_dev,

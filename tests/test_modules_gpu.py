@@ -161,14 +161,16 @@ def test_training_step_matches_oracle_fp32(case):
             mine = {"D": gD, "G": dict(G.named_parameters()), "M": dict(M.named_parameters()),
                     "S": dict(S.named_parameters())}
             for net in "DGMS":
-                for k, g64 in ref64[0][1][net].items():
-                    if (net, k) in DEAD:
-                        continue
+                live = [k for k in ref64[0][1][net] if (net, k) not in DEAD]
+                floors = {k: relerr(ref32[0][1][net][k], ref64[0][1][net][k]) for k in live}
+                # the oracle's own fp32-vs-fp64 noise: per tensor, and the network's median
+                # (one tensor's sample of the sign/ReLU-flip noise can be accidentally tiny)
+                net_floor = sorted(floors.values())[len(floors) // 2]
+                for k in live:
                     gm = mine[net][k] if net == "D" else mine[net][k].grad
-                    floor = relerr(ref32[0][1][net][k], g64)
-                    e = relerr(gm, g64)
+                    e = relerr(gm, ref64[0][1][net][k])
                     worst = max(worst, e)
-                    assert e <= max(3 * floor, 1e-4), (net, k, e, floor)
+                    assert e <= max(3 * floors[k], 3 * net_floor, 1e-4), (net, k, e, floors[k], net_floor)
     print(f"[{case}] worst end-to-end gradient error vs fp64 oracle: {worst:.2e}")
     # weights after the optimiser steps (Adam moves every weight by ~lr: sign flips at g~0 only)
     for net, mod in (("D", D), ("G", G), ("M", M), ("S", S)):
