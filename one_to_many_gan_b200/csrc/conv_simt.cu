@@ -160,6 +160,123 @@ __global__ void __launch_bounds__(128) conv_small_cout_kernel(ConvP p) {
 }
 
 // ---------------------------------------------------------------------------
+// Cout == 1, K x K (K = 4 or 7) with the input patch staged in shared memory:
+// persistent CTAs over 16x16 output tiles; a thread owns 8 channels x 4 consecutive pixels and
+// slides a 4-vector register window along the filter row, so each filter row costs K+3 patch
+// loads + 2K weight loads for 32*K FMAs; the 8 channel-group lanes of a pixel are combined
+// with three shuffles.  This is the generator's 64->1 7x7 output conv and the dgrad of the
+// 1->64 4x4 input convs (HBM traffic = the input, once).
+// ---------------------------------------------------------------------------
+template <typename TI, typename TO, int KS>
+__global__ void __launch_bounds__(256)
+conv_cout1_tiled_kernel(ConvP p, int tiles_w, int tiles_per_img, int total_tiles) {
+  constexpr int TT = 16, PW = TT + KS - 1, CC = 64;
+  extern __shared__ __align__(16) unsigned char c1_smem[];
+  TI* xs = reinterpret_cast<TI*>(c1_smem);                         // [PW*PW][CC]
+  float* ws = reinterpret_cast<float*>(xs + (size_t)PW * PW * CC);  // [KS*KS][CC]
+  const int cg = threadIdx.x % 8, pg = threadIdx.x / 8;
+  const int H = p.x.h, W = p.x.w, halo = p.x_halo;
+  const int nchunks = p.cin / CC;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
+    const TI* wbase = (const TI*)p.w + (long long)n * p.w_bstride;
+    float acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int c0 = ch * CC;
+      __syncthreads();
+      for (int e = threadIdx.x; e < KS * KS * CC; e += 256) {
+        int c = e % CC, tap = e / CC;
+        ws[e] = to_f(wbase[(long long)tap * p.cin + c0 + c]);
+      }
+      for (int e = threadIdx.x; e < PW * PW * 8; e += 256) {
+        int v = e % 8, q = e / 8;
+        int pw = q % PW, ph = q / PW;
+        int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+        float tmp[8];
+        if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo) {
+          load_vec<TI, 8>(vptr<TI>(p.x, n, ih, iw, c0 + v * 8), tmp);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tmp[i] = 0.f;
+        }
+        store_vec<TI, 8>(xs + (size_t)q * CC + v * 8, tmp);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int g = pass * 32 + pg;
+        const int row = g / 4, col4 = (g % 4) * 4;
+#pragma unroll 1
+        for (int r = 0; r < KS; ++r) {
+          const TI* xrow = xs + ((size_t)(row + r) * PW + col4) * CC + cg * 8;
+          float xw[4][8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) load_vec<TI, 8>(xrow + j * CC, xw[j]);
+#pragma unroll
+          for (int s2 = 0; s2 < KS; ++s2) {
+            float wv[8];
+            load_vec<float, 8>(ws + (r * KS + s2) * CC + cg * 8, wv);
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+              const float* xv = xw[(s2 + px) % 4];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[pass][px] = fmaf(xv[i], wv[i], acc[pass][px]);
+            }
+            if (s2 + 1 < KS) load_vec<TI, 8>(xrow + (s2 + 4) * CC, xw[s2 % 4]);
+          }
+        }
+      }
+    }
+    // combine the 8 channel-group lanes of each pixel group, then lanes 0..3 write one pixel each
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        float v = acc[pass][px];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        acc[pass][px] = v;
+      }
+      if (cg < 4) {
+        const int g = pass * 32 + pg;
+        const int oh = oh0 + g / 4, ow = ow0 + (g % 4) * 4 + cg;
+        if (oh < p.y.h && ow < p.y.w) {
+          float v = (cg == 0 ? acc[pass][0] : cg == 1 ? acc[pass][1] : cg == 2 ? acc[pass][2] : acc[pass][3]);
+          v *= p.alpha;
+          if (p.row_scale) v *= p.row_scale[n];
+          if (p.bias) v += p.bias[0];
+          v = act_fwd(v, p.act);
+          if (p.res.ptr) v += to_f(*vptr<TO>(p.res, n, oh, ow, 0));
+          float vv[1] = {v};
+          store_halo<TO, 1>(p.y, p.y_halo, n, oh, ow, 0, vv);
+        }
+      }
+    }
+  }
+}
+
+template <typename TI, typename TO, int KS>
+static int launch_cout1_tiled(const ConvP& p, int n, cudaStream_t st) {
+  constexpr int TT = 16, PW = TT + KS - 1, CC = 64;
+  const size_t smem = (size_t)PW * PW * CC * sizeof(TI) + (size_t)KS * KS * CC * sizeof(float);
+  const int tiles_w = (p.y.w + TT - 1) / TT, tiles_h = (p.y.h + TT - 1) / TT;
+  const int per_img = tiles_w * tiles_h, total = per_img * n;
+  auto kern = conv_cout1_tiled_kernel<TI, TO, KS>;
+  OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ctas = num_sms() * (smem > 110 * 1024 ? 1 : 2);
+  if (ctas > total) ctas = total;
+  kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
+// ---------------------------------------------------------------------------
 // wgrad, generic tile: M = 64 couts, N = 64 flattened (r,s,i), K = pixels of one sample
 // chunk.  grid = (ceil(ktot/64), ceil(cout/64), n * splits); atomicAdd into dw.
 // ---------------------------------------------------------------------------
@@ -258,34 +375,18 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
 // ---------------------------------------------------------------------------
 constexpr int WG_MAXI = 32;
 
+// Persistent: gridDim.x CTAs stride over all (sample, tile) pairs and keep their partial sums in
+// registers, so the final reduction is gridDim.x atomics per weight instead of one per tile.
+// Per-sample factors (rs/cs) are not supported here (the skinny layers are never modulated).
 template <typename T>
-__global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT, int tiles_w) {
+__global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT, int tiles_w,
+                                                               int tiles_per_img, int total_tiles) {
   extern __shared__ __align__(16) unsigned char wg_smem[];
-  const int n = blockIdx.z;
-  const int tile = blockIdx.x;
-  const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
   const int PW = TT + p.kw - 1, PH = TT + p.kh - 1;
-  T* xs = reinterpret_cast<T*>(wg_smem);                       // [PH][PW][cin]
+  T* xs = reinterpret_cast<T*>(wg_smem);                                   // [PH][PW][cin]
   float* dys = reinterpret_cast<float*>(xs + (size_t)PH * PW * p.cin + 8);  // [TT*TT][cout]
   const int H = p.x.h, W = p.x.w, halo = p.x_halo;
-  // stage the input patch (zero outside the readable region)
   const int patch = PH * PW * p.cin;
-  for (int e = threadIdx.x; e < patch; e += 256) {
-    int c = e % p.cin, q = e / p.cin;
-    int pw = q % PW, ph = q / PW;
-    int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
-    T v = from_f<T>(0.f);
-    if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo) v = *vptr<T>(p.x, n, ih, iw, c);
-    xs[e] = v;
-  }
-  for (int e = threadIdx.x; e < TT * TT * p.cout; e += 256) {
-    int o = e % p.cout, q = e / p.cout;
-    int oh = oh0 + q / TT, ow = ow0 + q % TT;
-    float v = 0.f;
-    if (oh < p.dy.h && ow < p.dy.w) v = to_f(*vptr<T>(p.dy, n, oh, ow, o));
-    dys[e] = v;
-  }
-  __syncthreads();
   const int total = p.ktot * p.cout;  // items: (o, tap, c), c fastest
   float acc[WG_MAXI];
   int base[WG_MAXI];
@@ -302,15 +403,36 @@ __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT,
       base[i] = -1;
     }
   }
-  for (int q = 0; q < TT * TT; ++q) {
-    const int pixoff = ((q / TT) * PW + (q % TT)) * p.cin;
-    const float* dq = dys + q * p.cout;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
+    __syncthreads();  // previous tile fully consumed
+    for (int e = threadIdx.x; e < patch; e += 256) {
+      int c = e % p.cin, q = e / p.cin;
+      int pw = q % PW, ph = q / PW;
+      int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+      T v = from_f<T>(0.f);
+      if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo) v = *vptr<T>(p.x, n, ih, iw, c);
+      xs[e] = v;
+    }
+    for (int e = threadIdx.x; e < TT * TT * p.cout; e += 256) {
+      int o = e % p.cout, q = e / p.cout;
+      int oh = oh0 + q / TT, ow = ow0 + q % TT;
+      float v = 0.f;
+      if (oh < p.dy.h && ow < p.dy.w) v = to_f(*vptr<T>(p.dy, n, oh, ow, o));
+      dys[e] = v;
+    }
+    __syncthreads();
+    for (int q = 0; q < TT * TT; ++q) {
+      const int pixoff = ((q / TT) * PW + (q % TT)) * p.cin;
+      const float* dq = dys + q * p.cout;
 #pragma unroll
-    for (int i = 0; i < WG_MAXI; ++i) {
-      if (base[i] >= 0) {
-        int item = threadIdx.x + i * 256;
-        float d = dq[item / p.ktot];
-        acc[i] = fmaf(d, to_f(xs[base[i] + pixoff]), acc[i]);
+      for (int i = 0; i < WG_MAXI; ++i) {
+        if (base[i] >= 0) {
+          int item = threadIdx.x + i * 256;
+          float d = dq[item / p.ktot];
+          acc[i] = fmaf(d, to_f(xs[base[i] + pixoff]), acc[i]);
+        }
       }
     }
   }
@@ -321,20 +443,62 @@ __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT,
     int item = threadIdx.x + i * 256;
     int o = item / p.ktot, kk = item % p.ktot;
     int tap = kk / p.cin, c = kk - tap * p.cin;
-    float v = acc[i] * p.alpha;
-    if (p.rs) v *= p.rs[(long long)n * p.cout + o];
-    if (p.cs) v *= p.cs[(long long)n * p.cin + c];
-    atomicAdd(p.dw + ((long long)o * p.cin + c) * taps + tap, v);
+    atomicAdd(p.dw + ((long long)o * p.cin + c) * taps + tap, acc[i] * p.alpha);
   }
 }
 
 // ---------------------------------------------------------------------------
 // weight staging / modulation coefficients
 // ---------------------------------------------------------------------------
+// One thread stages 8 consecutive output elements (one 128-bit store for bf16) for ALL nb
+// per-sample packs: the 8 weights are gathered from the [O,I,kh,kw] parameter once, then scaled
+// by the per-sample factors and streamed out.
 template <typename TO>
-__global__ void weight_pack_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw,
-                                   float alpha, const float* cs, const float* rs, int nb,
-                                   int transpose, TO* out) {
+__global__ void __launch_bounds__(256)
+weight_pack_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw, float alpha,
+                   const float* __restrict__ cs, const float* __restrict__ rs, int nb, int transpose,
+                   TO* out) {
+  const int taps = kh * kw;
+  const long long per = (long long)cout * cin * taps;
+  const long long groups = per / 8;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups;
+       gidx += (long long)gridDim.x * blockDim.x) {
+    const long long e = gidx * 8;
+    float wv[8];
+    int o0, i0, r, s2;
+    if (!transpose) {  // [o][r][s][i], vector along i
+      i0 = (int)(e % cin); long long t = e / cin;
+      s2 = (int)(t % kw); t /= kw;
+      r = (int)(t % kh); o0 = (int)(t / kh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = alpha * w[((long long)o0 * cin + i0 + j) * taps + r * kw + s2];
+    } else {  // [i][kh-1-r][kw-1-s][o], vector along o
+      o0 = (int)(e % cout); long long t = e / cout;
+      int sf = (int)(t % kw); t /= kw;
+      int rf = (int)(t % kh); i0 = (int)(t / kh);
+      r = kh - 1 - rf; s2 = kw - 1 - sf;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = alpha * w[((long long)(o0 + j) * cin + i0) * taps + r * kw + s2];
+    }
+    for (int b = 0; b < nb; ++b) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f = 1.f;
+        if (cs) f *= cs[(long long)b * cin + (transpose ? i0 : i0 + j)];
+        if (rs) f *= rs[(long long)b * cout + (transpose ? o0 + j : o0)];
+        v[j] = wv[j] * f;
+      }
+      store_vec<TO, 8>(out + (long long)b * per + e, v);
+    }
+  }
+}
+
+// scalar fallback for shapes whose innermost packed dimension is not a multiple of 8
+template <typename TO>
+__global__ void weight_pack_scalar_kernel(const float* __restrict__ w, int cout, int cin, int kh,
+                                          int kw, float alpha, const float* cs, const float* rs,
+                                          int nb, int transpose, TO* out) {
   const int taps = kh * kw;
   const long long per = (long long)cout * cin * taps;
   const long long total = per * nb;
@@ -342,13 +506,12 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, int cout, int ci
        idx += (long long)gridDim.x * blockDim.x) {
     int b = (int)(idx / per);
     long long e = idx - (long long)b * per;
-    // output-major decode so writes are coalesced
     int o, i, r, s;
-    if (!transpose) {  // [o][r][s][i]
+    if (!transpose) {
       i = (int)(e % cin); long long t = e / cin;
       s = (int)(t % kw); t /= kw;
       r = (int)(t % kh); o = (int)(t / kh);
-    } else {           // [i][r'][s'][o] with r' = kh-1-r
+    } else {
       o = (int)(e % cout); long long t = e / cout;
       int s2 = (int)(t % kw); t /= kw;
       int r2 = (int)(t % kh); i = (int)(t / kh);
@@ -428,6 +591,16 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
   p.tiles_w = (a->y.w + 7) / 8;
   const int tiles_h = (a->y.h + 7) / 8;
   const bool in_bf = a->x.dtype == OTM_BF16, out_bf = a->y.dtype == OTM_BF16;
+  if (p.cout == 1 && p.cin % 64 == 0 && a->kh == a->kw && (a->kh == 4 || a->kh == 7) &&
+      vec_ok(a->x, 8) && a->y.h * a->y.w >= 256) {
+#define OTM_C1(TI, TO) \
+  (a->kh == 7 ? launch_cout1_tiled<TI, TO, 7>(p, a->y.n, st) : launch_cout1_tiled<TI, TO, 4>(p, a->y.n, st))
+    if (in_bf && out_bf) return OTM_C1(__nv_bfloat16, __nv_bfloat16);
+    if (in_bf) return OTM_C1(__nv_bfloat16, float);
+    if (out_bf) return OTM_C1(float, __nv_bfloat16);
+    return OTM_C1(float, float);
+#undef OTM_C1
+  }
   if (p.cout <= 4 && (size_t)p.cout * p.ktot * 4 <= 160 * 1024) {
     size_t smem = (size_t)p.cout * p.ktot * sizeof(float);
     bool v8 = vec_ok(a->x, 8);
@@ -463,27 +636,29 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
   p.x_halo = a->x_halo; p.kh = a->kh; p.kw = a->kw; p.pad = a->pad;
   p.cin = a->x.c; p.cout = a->dy.c; p.ktot = a->kh * a->kw * a->x.c;
   p.dw = a->dw; p.alpha = a->alpha; p.rs = a->rs; p.cs = a->cs;
-  // skinny output: smem-tiled kernel
-  if (p.cout <= 4 && (long long)p.ktot * p.cout <= 256LL * WG_MAXI) {
+  // skinny output: persistent smem-tiled kernel
+  if (p.cout <= 4 && (long long)p.ktot * p.cout <= 256LL * WG_MAXI && !a->rs && !a->cs) {
     const size_t es = dtype_size(a->x.dtype);
     int TT = 16;
     auto smem_for = [&](int tt) {
       return (size_t)(tt + p.kh - 1) * (tt + p.kw - 1) * p.cin * es + 8 * es +
              (size_t)tt * tt * p.cout * sizeof(float) + 16;
     };
-    while (TT > 2 && smem_for(TT) > 96 * 1024) TT /= 2;
+    while (TT > 2 && smem_for(TT) > 100 * 1024) TT /= 2;
     if (smem_for(TT) <= 200 * 1024) {
       const int tiles_w = (a->dy.w + TT - 1) / TT, tiles_h = (a->dy.h + TT - 1) / TT;
-      dim3 grid(tiles_w * tiles_h, 1, a->dy.n);
+      const int per_img = tiles_w * tiles_h, total_tiles = per_img * a->dy.n;
       const size_t smem = smem_for(TT);
+      int ctas = num_sms() * (smem > 110 * 1024 ? 1 : 2);
+      if (ctas > total_tiles) ctas = total_tiles;
       if (a->x.dtype == OTM_BF16) {
         auto kern = wgrad_small_cout_kernel<__nv_bfloat16>;
         OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 256, smem, st>>>(p, TT, tiles_w);
+        kern<<<ctas, 256, smem, st>>>(p, TT, tiles_w, per_img, total_tiles);
       } else {
         auto kern = wgrad_small_cout_kernel<float>;
         OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 256, smem, st>>>(p, TT, tiles_w);
+        kern<<<ctas, 256, smem, st>>>(p, TT, tiles_w, per_img, total_tiles);
       }
       OTM_LAUNCH_CHECK();
       return OTM_OK;
@@ -514,18 +689,33 @@ extern "C" {
 int otm_weight_pack(const otm_weight_pack_args* a, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OTM_REQUIRE(a && a->w && a->out && a->nb >= 1, "weight_pack: bad arguments");
-  long long total = (long long)a->cout * a->cin * a->kh * a->kw * a->nb;
-  int blocks = (int)((total + 255) / 256);
-  int cap = num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  if (a->out_dtype == OTM_BF16)
-    weight_pack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
-        a->w, a->cout, a->cin, a->kh, a->kw, a->alpha, a->cs, a->rs, a->nb, a->transpose,
-        (__nv_bfloat16*)a->out);
-  else
-    weight_pack_kernel<float><<<blocks, 256, 0, st>>>(a->w, a->cout, a->cin, a->kh, a->kw,
-                                                      a->alpha, a->cs, a->rs, a->nb,
-                                                      a->transpose, (float*)a->out);
+  const long long per = (long long)a->cout * a->cin * a->kh * a->kw;
+  const int inner = a->transpose ? a->cout : a->cin;
+  const int cap = num_sms() * 16;
+  if (inner % 8 == 0 && ((uintptr_t)a->out % 16 == 0)) {
+    int blocks = (int)((per / 8 + 255) / 256);
+    if (blocks > cap) blocks = cap;
+    if (a->out_dtype == OTM_BF16)
+      weight_pack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+          a->w, a->cout, a->cin, a->kh, a->kw, a->alpha, a->cs, a->rs, a->nb, a->transpose,
+          (__nv_bfloat16*)a->out);
+    else
+      weight_pack_kernel<float><<<blocks, 256, 0, st>>>(a->w, a->cout, a->cin, a->kh, a->kw,
+                                                        a->alpha, a->cs, a->rs, a->nb,
+                                                        a->transpose, (float*)a->out);
+  } else {
+    long long total = per * a->nb;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > cap) blocks = cap;
+    if (a->out_dtype == OTM_BF16)
+      weight_pack_scalar_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+          a->w, a->cout, a->cin, a->kh, a->kw, a->alpha, a->cs, a->rs, a->nb, a->transpose,
+          (__nv_bfloat16*)a->out);
+    else
+      weight_pack_scalar_kernel<float><<<blocks, 256, 0, st>>>(
+          a->w, a->cout, a->cin, a->kh, a->kw, a->alpha, a->cs, a->rs, a->nb, a->transpose,
+          (float*)a->out);
+  }
   OTM_LAUNCH_CHECK();
   return OTM_OK;
 }

@@ -20,6 +20,7 @@
 // Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected lane),
 // warp2 = TMEM allocator, warps4-7 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -201,8 +202,8 @@ __device__ __forceinline__ void epilogue_store16(const TcFwdP& p, int n, int oh,
     }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int STAGES, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    TcFwdP p) {
   constexpr int B_STAGE_BYTES = BN * 128;
@@ -519,11 +520,11 @@ bool conv_fwd_tc_eligible(const otm_conv_fwd_args* a) {
   return true;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int OCC>
 static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcFwdP& p, dim3 grid,
                       cudaStream_t st) {
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + 1024 + 256;
-  auto kern = conv_tc_fwd_kernel<BN, STAGES>;
+  auto kern = conv_tc_fwd_kernel<BN, STAGES, OCC>;
   static bool attr_set = false;
   if (!attr_set) {
     OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -566,9 +567,17 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   p.TW = TW; p.TH = TH; p.tiles_w = (Wo + TW - 1) / TW;
   p.w_rows_per_sample = a->w_batch_stride ? cout : 0;
   dim3 grid(best_tiles, cout / BN, a->y.n);
-  if (BN == 64) return launch_fwd<64, 6>(tmA, tmB, p, grid, st);
-  if (BN == 128) return launch_fwd<128, 6>(tmA, tmB, p, grid, st);
-  return launch_fwd<256, 4>(tmA, tmB, p, grid, st);
+  // variant 0 (default): 2 CTAs per SM with a short ring, so one CTA's prologue/epilogue
+  // overlaps the other's MMA main loop; variant 1: 1 CTA per SM with a deep ring.
+  static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
+  if (variant == 1) {
+    if (BN == 64) return launch_fwd<64, 6, 1>(tmA, tmB, p, grid, st);
+    if (BN == 128) return launch_fwd<128, 6, 1>(tmA, tmB, p, grid, st);
+    return launch_fwd<256, 4, 1>(tmA, tmB, p, grid, st);
+  }
+  if (BN == 64) return launch_fwd<64, 4, 2>(tmA, tmB, p, grid, st);
+  if (BN == 128) return launch_fwd<128, 3, 2>(tmA, tmB, p, grid, st);
+  return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
 }
 
 bool conv_wgrad_tc_eligible(const otm_conv_wgrad_args* a) {

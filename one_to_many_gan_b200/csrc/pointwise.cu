@@ -125,31 +125,39 @@ static int launch_nc_reduce(F f, int N, int H, int W, int C, float* out, cudaStr
 // ---------------------------------------------------------------------------
 // instance-norm statistics
 // ---------------------------------------------------------------------------
+// Sums are accumulated about a per-(n,c) shift k = x[n,0,0,c] so that the one-pass variance
+// E[(x-k)^2] - E[x-k]^2 does not cancel catastrophically when |mean| >> std (the parity mode
+// needs ~1e-7 relative statistics: a 4e-6 error flips LeakyReLU masks in the 2x4-pixel layers).
 template <typename T, int V>
 struct StatsF {
   static constexpr int NQ = 2;
   View x;
   int C;
   __device__ void operator()(int n, int h, int w, int c, float (&acc)[2][V]) const {
-    float v[V];
+    float v[V], k[V];
     load_vec<T, V>(vptr<T>(x, n, h, w, c), v);
+    load_vec<T, V>(vptr<T>(x, n, 0, 0, c), k);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      acc[0][i] += v[i];
-      acc[1][i] += v[i] * v[i];
+      float d = v[i] - k[i];
+      acc[0][i] += d;
+      acc[1][i] += d * d;
     }
   }
   __device__ int out_index(int n, int c, int q) const { return (n * C + c) * 2 + q; }
 };
 
-__global__ void stats_finalize_kernel(const float* ws, float* stats, int count, float inv_n,
+template <typename T>
+__global__ void stats_finalize_kernel(const float* ws, float* stats, View x, int count, float inv_n,
                                       float eps) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
+  int n = i / x.c, c = i - n * x.c;
+  float k = to_f(*vptr<T>(x, n, 0, 0, c));
   float s = ws[2 * i], ss = ws[2 * i + 1];
-  float mean = s * inv_n;
-  float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-  stats[2 * i] = mean;
+  float dm = s * inv_n;
+  float var = fmaxf(ss * inv_n - dm * dm, 0.f);
+  stats[2 * i] = k + dm;
   stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
@@ -602,8 +610,12 @@ int otm_instnorm_stats(const otm_tensor* x, float eps, float* ws, float* stats,
     rc = launch_nc_reduce<V>(f, x->n, x->h, x->w, x->c, ws, st);
   });
   if (rc) return rc;
-  stats_finalize_kernel<<<(count + 255) / 256, 256, 0, st>>>(ws, stats, count,
-                                                             1.f / (float)(x->h * x->w), eps);
+  if (x->dtype == OTM_BF16)
+    stats_finalize_kernel<__nv_bfloat16><<<(count + 255) / 256, 256, 0, st>>>(
+        ws, stats, make_view(*x), count, 1.f / (float)(x->h * x->w), eps);
+  else
+    stats_finalize_kernel<float><<<(count + 255) / 256, 256, 0, st>>>(
+        ws, stats, make_view(*x), count, 1.f / (float)(x->h * x->w), eps);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
 }

@@ -60,6 +60,9 @@ CONV_CASES = [
     (64, 1, 7, 3, 3, 16, 12, 2),
     (1, 64, 4, 1, 0, 33, 20, 2),
     (24, 40, 3, 1, 0, 9, 11, 1),
+    (64, 1, 7, 3, 3, 40, 24, 2),   # smem-tiled Cout=1 kernel (G output conv)
+    (64, 1, 4, 2, 0, 33, 20, 2),   # ... as the dgrad of a 1->64 4x4 conv
+    (128, 1, 4, 1, 0, 20, 20, 1),  # ... two channel chunks
 ]
 
 
