@@ -325,8 +325,8 @@ struct TcWgP {
 
 constexpr int WG_CHUNK_BYTES = 64 * 128;  // 64 pixels x 64 channels bf16
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int STAGES, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmB, TcWgP p) {
   constexpr int A_BYTES = 2 * WG_CHUNK_BYTES;
@@ -587,11 +587,11 @@ bool conv_wgrad_tc_eligible(const otm_conv_wgrad_args* a) {
   return true;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int OCC>
 static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcWgP& p, dim3 grid,
                         cudaStream_t st) {
   constexpr int smem = STAGES * (2 * WG_CHUNK_BYTES + (BN / 64) * WG_CHUNK_BYTES) + 1024 + 256;
-  auto kern = conv_tc_wgrad_kernel<BN, STAGES>;
+  auto kern = conv_tc_wgrad_kernel<BN, STAGES, OCC>;
   static bool attr_set = false;
   if (!attr_set) {
     OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -618,8 +618,8 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const int m_tiles = M / 128;
   p.n_tiles_n = N / BN;
   long long base = (long long)taps * m_tiles * p.n_tiles_n * a->dy.n;
-  int splits = (int)((2LL * num_sms() + base - 1) / base);
-  int max_splits = (p.tiles_total + 15) / 16;  // keep >= 16 K-stages per CTA when possible
+  int splits = (int)((4LL * num_sms() + base - 1) / base);  // ~2 waves at 2 CTAs per SM
+  int max_splits = (p.tiles_total + 31) / 32;  // keep >= 32 K-stages per CTA (amortise the reds)
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.splits = splits;
@@ -633,9 +633,15 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const CUtensorMap& tmA = p.a_is_x ? tmX : tmDy;
   const CUtensorMap& tmB = p.a_is_x ? tmDy : tmX;
   dim3 grid(taps, m_tiles * p.n_tiles_n, a->dy.n * splits);
-  if (BN == 64) return launch_wgrad<64, 6>(tmA, tmB, p, grid, st);
-  if (BN == 128) return launch_wgrad<128, 6>(tmA, tmB, p, grid, st);
-  return launch_wgrad<256, 4>(tmA, tmB, p, grid, st);
+  static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
+  if (variant == 1) {
+    if (BN == 64) return launch_wgrad<64, 6, 1>(tmA, tmB, p, grid, st);
+    if (BN == 128) return launch_wgrad<128, 6, 1>(tmA, tmB, p, grid, st);
+    return launch_wgrad<256, 4, 1>(tmA, tmB, p, grid, st);
+  }
+  if (BN == 64) return launch_wgrad<64, 4, 2>(tmA, tmB, p, grid, st);
+  if (BN == 128) return launch_wgrad<128, 3, 2>(tmA, tmB, p, grid, st);
+  return launch_wgrad<256, 2, 2>(tmA, tmB, p, grid, st);
 }
 
 int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st);
