@@ -290,7 +290,7 @@ struct WgradP {
   int splits, pix_per_split;
 };
 
-template <typename T>
+template <typename T, typename TDY>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
   __shared__ float As[TK][TM + 4];  // dy: [pixel][cout]
   __shared__ float Bs[TK][TN + 4];  // x : [pixel][k]
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
       float a = 0.f, b = 0.f;
       if (pix < pend) {
         int oh = pix / Wo, ow = pix - oh * Wo;
-        if (o0 + m < p.cout) a = to_f(*vptr<T>(p.dy, n, oh, ow, o0 + m));
+        if (o0 + m < p.cout) a = to_f(*vptr<TDY>(p.dy, n, oh, ow, o0 + m));
         int c = koff_c[m];
         if (c >= 0) {
           int ih = oh + koff_r[m], iw = ow + koff_s[m];
@@ -378,7 +378,7 @@ constexpr int WG_MAXI = 32;
 // Persistent: gridDim.x CTAs stride over all (sample, tile) pairs and keep their partial sums in
 // registers, so the final reduction is gridDim.x atomics per weight instead of one per tile.
 // Per-sample factors (rs/cs) are not supported here (the skinny layers are never modulated).
-template <typename T>
+template <typename T, typename TDY>
 __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT, int tiles_w,
                                                                int tiles_per_img, int total_tiles) {
   extern __shared__ __align__(16) unsigned char wg_smem[];
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT,
   const int patch = PH * PW * p.cin;
   const int total = p.ktot * p.cout;  // items: (o, tap, c), c fastest
   float acc[WG_MAXI];
-  int base[WG_MAXI];
+  int base[WG_MAXI], oidx[WG_MAXI];
 #pragma unroll
   for (int i = 0; i < WG_MAXI; ++i) {
     acc[i] = 0.f;
@@ -399,10 +399,13 @@ __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT,
       int tap = kk / p.cin, c = kk - tap * p.cin;
       int r = tap / p.kw, s2 = tap - r * p.kw;
       base[i] = (r * PW + s2) * p.cin + c;
+      oidx[i] = item / p.ktot;
     } else {
       base[i] = -1;
+      oidx[i] = 0;
     }
   }
+  const int n_items = (total + 255) / 256;  // block-uniform trip count
   for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
     const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
     const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
@@ -419,19 +422,18 @@ __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT,
       int o = e % p.cout, q = e / p.cout;
       int oh = oh0 + q / TT, ow = ow0 + q % TT;
       float v = 0.f;
-      if (oh < p.dy.h && ow < p.dy.w) v = to_f(*vptr<T>(p.dy, n, oh, ow, o));
+      if (oh < p.dy.h && ow < p.dy.w) v = to_f(*vptr<TDY>(p.dy, n, oh, ow, o));
       dys[e] = v;
     }
     __syncthreads();
-    for (int q = 0; q < TT * TT; ++q) {
-      const int pixoff = ((q / TT) * PW + (q % TT)) * p.cin;
-      const float* dq = dys + q * p.cout;
+    for (int qh = 0; qh < TT; ++qh) {
+      for (int qw = 0; qw < TT; ++qw) {
+        const int pixoff = (qh * PW + qw) * p.cin;
+        const float* dq = dys + (qh * TT + qw) * p.cout;
 #pragma unroll
-      for (int i = 0; i < WG_MAXI; ++i) {
-        if (base[i] >= 0) {
-          int item = threadIdx.x + i * 256;
-          float d = dq[item / p.ktot];
-          acc[i] = fmaf(d, to_f(xs[base[i] + pixoff]), acc[i]);
+        for (int i = 0; i < WG_MAXI; ++i) {
+          if (i < n_items && base[i] >= 0)
+            acc[i] = fmaf(dq[oidx[i]], to_f(xs[base[i] + pixoff]), acc[i]);
         }
       }
     }
@@ -651,15 +653,19 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
       const size_t smem = smem_for(TT);
       int ctas = num_sms() * (smem > 110 * 1024 ? 1 : 2);
       if (ctas > total_tiles) ctas = total_tiles;
-      if (a->x.dtype == OTM_BF16) {
-        auto kern = wgrad_small_cout_kernel<__nv_bfloat16>;
-        OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<ctas, 256, smem, st>>>(p, TT, tiles_w, per_img, total_tiles);
-      } else {
-        auto kern = wgrad_small_cout_kernel<float>;
-        OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<ctas, 256, smem, st>>>(p, TT, tiles_w, per_img, total_tiles);
-      }
+#define OTM_WG_SMALL(TX, TDY)                                                                   \
+  do {                                                                                          \
+    auto kern = wgrad_small_cout_kernel<TX, TDY>;                                               \
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        (int)smem));                                            \
+    kern<<<ctas, 256, smem, st>>>(p, TT, tiles_w, per_img, total_tiles);                        \
+  } while (0)
+      const bool xb = a->x.dtype == OTM_BF16, yb = a->dy.dtype == OTM_BF16;
+      if (xb && yb) OTM_WG_SMALL(__nv_bfloat16, __nv_bfloat16);
+      else if (xb) OTM_WG_SMALL(__nv_bfloat16, float);
+      else if (yb) OTM_WG_SMALL(float, __nv_bfloat16);
+      else OTM_WG_SMALL(float, float);
+#undef OTM_WG_SMALL
       OTM_LAUNCH_CHECK();
       return OTM_OK;
     }
@@ -674,8 +680,11 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
   p.pix_per_split = ((HW + splits - 1) / splits + TK - 1) / TK * TK;
   dim3 grid((p.ktot + TN - 1) / TN, (p.cout + TM - 1) / TM, a->dy.n * splits);
   OTM_REQUIRE(a->dy.n * splits <= 65535, "wgrad: grid.z too large");
-  if (a->x.dtype == OTM_BF16) wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
-  else wgrad_simt_kernel<float><<<grid, 256, 0, st>>>(p);
+  const bool xb = a->x.dtype == OTM_BF16, yb = a->dy.dtype == OTM_BF16;
+  if (xb && yb) wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  else if (xb) wgrad_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(p);
+  else if (yb) wgrad_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  else wgrad_simt_kernel<float, float><<<grid, 256, 0, st>>>(p);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
 }

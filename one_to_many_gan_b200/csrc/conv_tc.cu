@@ -699,7 +699,6 @@ int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream) {
                   a->dy.n == a->x.n,
               "conv_wgrad: dy %dx%d does not match x %dx%d k=%d pad=%d", a->dy.h, a->dy.w, a->x.h,
               a->x.w, a->kh, a->pad);
-  OTM_REQUIRE(a->x.dtype == a->dy.dtype, "conv_wgrad: dtype mismatch");
   OTM_REQUIRE(a->x_halo <= a->pad, "conv_wgrad: x_halo larger than pad");
   const bool tc = conv_wgrad_tc_eligible(a);
   if (a->path == OTM_PATH_TCGEN05 && !tc)

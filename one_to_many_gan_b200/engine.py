@@ -1,0 +1,235 @@
+"""One full training iteration (D step + G step) as a replayable CUDA graph.
+
+The reference drives its iteration from Python with ten `.cpu().item()` syncs, host RNG
+draws interleaved with device work and a Python image pool (train.py:204-251,
+training.py:22-65).  At 128x128 / batch 32 an iteration is ~2,800 kernel launches, so the host
+would bound the GPU.  This engine keeps the SAME mathematics and the SAME host-RNG draw
+order, but separates the iteration into
+
+  host part   : draw the style noise / mixing coin / crossover / theta (host generator) and the
+                image-pool decisions (python `random`) -> one pinned staging buffer,
+  device part : everything else, static shapes, no host sync -> captured once with
+                torch.cuda.graph and replayed.
+
+Differences from the eager step functions that make the device part static (numerically
+identical): style mixing is a `where(block < crossover, s1, s2)` instead of expand+cat
+(builder.py:115-132); the image pool is a device tensor indexed by host-decided slots."""
+
+from __future__ import annotations
+
+import random
+
+import torch
+
+from . import ops, training
+
+
+class PoolIndexer:
+    """Host half of the image history pool (reference ImageBuffer, training.py:22-65): consumes
+    python `random` exactly like the reference and resolves every per-image decision of a batch
+    to gather/scatter indices for the device half.
+
+    decide(B) -> (src[B], dst[B], sto[B]):
+      returned image j = sources[src[j]], sources = [pool slots 0..P-1, scratch slot P, new 0..B-1]
+      after the batch   pool[dst[i]] = new[sto[i]]  (padding writes go to the scratch slot P)."""
+
+    def __init__(self, pool_size: int):
+        if pool_size < 1:
+            raise ValueError
+        self.size = pool_size
+        self.count = 0
+
+    def decide(self, batch: int):
+        P = self.size
+        new0 = P + 1
+        content: dict[int, int] = {}  # slot -> index of the new image written this batch
+        src = []
+        for j in range(batch):
+            if self.count < P:
+                content[self.count] = j
+                self.count += 1
+                src.append(new0 + j)
+            elif random.uniform(0, 1) > 0.5:
+                k = random.randint(0, P - 1)
+                src.append(new0 + content[k] if k in content else k)
+                content[k] = j
+            else:
+                src.append(new0 + j)
+        dst = list(content.keys())  # last writer wins
+        sto = list(content.values())
+        while len(dst) < batch:
+            dst.append(P)
+            sto.append(0)
+        return src, dst, sto
+
+
+class TrainIteration:
+    LOSS_NAMES = ("disc", "sign_real", "sign_fake", "total_gen", "gan", "rec", "idt", "kl", "path",
+                  "style")
+
+    def __init__(self, config, device, discriminator, generator, mapping_network, style_extractor,
+                 opt_d, opt_g, opt_m, opt_s, *, use_graph: bool = True, warmup: int = 2):
+        self.cfg = config
+        self.dev = torch.device(device)
+        self.D, self.G, self.M, self.S = discriminator, generator, mapping_network, style_extractor
+        self.oD, self.oG, self.oM, self.oS = opt_d, opt_g, opt_m, opt_s
+        self.B = config["training"]["batch_size"]
+        self.nb = generator.n_style_blocks
+        self.wd = mapping_network.d_latent
+        self.mix_p = mapping_network.style_mixing_prob
+        size = config["data"]["image_size"]
+        ch = config["data"].get("image_channels", 1)
+        B, wd = self.B, self.wd
+        # static inputs: [d_prints, d_marks, g_prints, g_marks]
+        self.x = torch.zeros(4, B, ch, size[0], size[1], device=self.dev)
+        # host-drawn randomness: 3 style draws x (z1, z2) + theta (+ optional injected h)
+        self.n_rng = 3 * 2 * B * wd + 2 * B
+        self.rng_host = torch.zeros(self.n_rng, dtype=torch.float32).pin_memory()
+        self.rng_dev = torch.zeros(self.n_rng, dtype=torch.float32, device=self.dev)
+        # integer controls: 3 crossovers, B pool sources, B pool destinations, B stored images
+        self.n_idx = 3 + 3 * B
+        self.idx_host = torch.zeros(self.n_idx, dtype=torch.int64).pin_memory()
+        self.idx_dev = torch.zeros(self.n_idx, dtype=torch.int64, device=self.dev)
+        self.pool_size = config["training"].get("image_buffer_size", 100)
+        if self.pool_size < 1:
+            raise ValueError
+        self.pool = torch.zeros(self.pool_size + 1, ch, size[0], size[1], device=self.dev)
+        self.pool_index = PoolIndexer(self.pool_size)
+        self.losses = torch.zeros(len(self.LOSS_NAMES), dtype=torch.float32, device=self.dev)
+        self.losses_host = torch.zeros(len(self.LOSS_NAMES), dtype=torch.float32).pin_memory()
+        self.inject_h = False
+        self.use_graph = use_graph
+        self.graph = None
+        self._warm_left = warmup
+        self.iterations = 0
+
+    # ---------------------------------------------------------------- host part
+    def _draw_style(self, slot: int):
+        """builder.py:106-132 draw order: rand(()), [randint, randn, randn] | [randn]."""
+        B, wd = self.B, self.wd
+        base = slot * 2 * B * wd
+        if torch.rand(()).lt(self.mix_p):
+            cross = int(torch.randint(0, self.nb, ()))
+            z1 = torch.randn(B, wd)
+            z2 = torch.randn(B, wd)
+        else:
+            cross = self.nb
+            z1 = torch.randn(B, wd)
+            z2 = z1
+        self.rng_host[base : base + B * wd] = z1.reshape(-1)
+        self.rng_host[base + B * wd : base + 2 * B * wd] = z2.reshape(-1)
+        self.idx_host[slot] = cross
+
+    def _pool_decisions(self):
+        src, dst, sto = self.pool_index.decide(self.B)
+        o, B = 3, self.B
+        self.idx_host[o : o + B] = torch.tensor(src)
+        self.idx_host[o + B : o + 2 * B] = torch.tensor(dst)
+        self.idx_host[o + 2 * B : o + 3 * B] = torch.tensor(sto)
+
+    def _sample_host(self, h):
+        B, wd = self.B, self.wd
+        self._draw_style(0)              # D step: get_single_w(d=1)
+        self._pool_decisions()           # ImageBuffer
+        self._draw_style(1)              # G step: translation w
+        tbase = 3 * 2 * B * wd
+        self.rng_host[tbase : tbase + B] = torch.rand(B)  # theta
+        if h is not None:
+            self.rng_host[tbase + B : tbase + 2 * B] = h.float().cpu()
+        self._draw_style(2)              # G step: get_two_w
+
+    # ---------------------------------------------------------------- device part
+    def _style(self, slot: int):
+        B, wd, nb = self.B, self.wd, self.nb
+        base = slot * 2 * B * wd
+        z1 = self.rng_dev[base : base + B * wd].view(B, wd)
+        z2 = self.rng_dev[base + B * wd : base + 2 * B * wd].view(B, wd)
+        s1, s2 = self.M(z1), self.M(z2)
+        first = (torch.arange(nb, device=self.dev) < self.idx_dev[slot]).view(nb, 1, 1)
+        return torch.where(first, s1[None], s2[None])
+
+    def _body(self):
+        cfg, B, P = self.cfg, self.B, self.pool_size
+        opt = cfg["optimisation"]
+        # ---- discriminator step (training.py:71-128) ----
+        self.oD.zero_grad()
+        with torch.no_grad():
+            w = self._style(0)
+            generated = self.G(self.x[0], w)
+            o = 3
+            sources = torch.cat([self.pool, generated], dim=0)
+            fake = sources.index_select(0, self.idx_dev[o : o + B])
+            self.pool.index_copy_(0, self.idx_dev[o + B : o + 2 * B],
+                                  generated.index_select(0, self.idx_dev[o + 2 * B : o + 3 * B]))
+        disc_loss, sign_real, sign_fake = training.discriminator_losses(self.D, fake, self.x[1])
+        training.backward_unit(disc_loss)
+        self.oD.step()
+        # ---- generator step (training.py:136-257) ----
+        self.oG.zero_grad()
+        self.oM.zero_grad()
+        self.oS.zero_grad()
+        zero = self.M.shoeprint_style_vector
+        reconstruct_w = zero.expand(self.nb, B, self.wd)
+        translation_w = self._style(1)
+        tbase = 3 * 2 * B * self.wd
+        theta = self.rng_dev[tbase : tbase + B]
+        if self.inject_h:
+            h = self.rng_dev[tbase + B : tbase + 2 * B]
+        else:
+            lo, hi = opt["path_loss_jacobian_granularity"]
+            h = torch.empty(B, device=self.dev).uniform_(lo, hi)
+        d1 = (theta + h / 2).clamp(0, 1)
+        d2 = (theta - h / 2).clamp(0, 1)
+        s = self._style(2)
+        w1 = torch.lerp(zero, s, d1.view(1, -1, 1))  # builder.py:66-71
+        w2 = torch.lerp(zero, s, d2.view(1, -1, 1))
+        losses = training.generator_losses(cfg, self.G, self.D, self.S, self.x[2], self.x[3],
+                                           reconstruct_w, translation_w, w1, w2, h)
+        training.backward_unit(losses[0])
+        self.oG.step()
+        self.oM.step()
+        self.oS.step()
+        vals = [disc_loss, sign_real, sign_fake, *losses]
+        self.losses.copy_(torch.cat([v.detach().reshape(1).float() for v in vals]))
+
+    # ---------------------------------------------------------------- driver
+    def load_inputs(self, d_prints, d_marks, g_prints, g_marks):
+        """Copy the four batches of this iteration into the static input buffers (device
+        tensors: device-to-device; pinned host tensors: asynchronous H2D)."""
+        for i, t in enumerate((d_prints, d_marks, g_prints, g_marks)):
+            self.x[i].copy_(t, non_blocking=True)
+
+    def run(self, *, h: torch.Tensor | None = None, sync_losses: bool = True):
+        """Run one iteration on the batches last given to load_inputs().  Returns the ten
+        logged scalars as floats (one device->host copy) or None if sync_losses is False."""
+        if (h is not None) != self.inject_h:
+            if self.graph is not None:
+                raise RuntimeError("cannot switch h injection after the graph was captured")
+            self.inject_h = h is not None
+        self._sample_host(h)
+        self.rng_dev.copy_(self.rng_host, non_blocking=True)
+        self.idx_dev.copy_(self.idx_host, non_blocking=True)
+        if not self.use_graph:
+            self._body()
+        elif self._warm_left > 0:  # eager warm-up: lazy inits, allocator pools, cuBLAS handles
+            self._warm_left -= 1
+            self._body()
+        elif self.graph is None:
+            torch.cuda.synchronize()
+            ops.invalidate_packs()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.graph.replay()
+        else:
+            self.graph.replay()
+        ops.invalidate_packs()  # replays update the weights behind Python's back
+        self.iterations += 1
+        if not sync_losses:
+            return None
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        v = self.losses_host.tolist()
+        g = training.unweighted(self.cfg, v[3:])
+        return {"disc": v[0], "sign_real": v[1], "sign_fake": v[2], "total_gen": g[0], "gan": g[1],
+                "rec": g[2], "idt": g[3], "kl": g[4], "path": g[5], "style": g[6]}

@@ -124,8 +124,7 @@ class ConvFn(torch.autograd.Function):
         gw = gb = gx = None
         if ctx.needs_input_grad[1]:
             gw = torch.zeros_like(weight)
-            gq = g if g.dtype == x.dtype else K.cast(g, x.dtype)
-            K.conv_wgrad(x, gq, gw, k, k, pad, x_halo=x_halo, alpha=eq_scale(weight))
+            K.conv_wgrad(x, g, gw, k, k, pad, x_halo=x_halo, alpha=eq_scale(weight))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = K.channel_sum(g)
         if ctx.needs_input_grad[0]:

@@ -118,6 +118,90 @@ def _floats(*tensors) -> list[float]:
     return torch.stack([t.detach().reshape(()).float() for t in tensors]).cpu().tolist()
 
 
+# ---------------------------------------------------------------------------
+# device-side cores shared by the reference-signature step functions below and by the
+# CUDA-graph engine (engine.py).  No host synchronisation, no host RNG in here.
+# ---------------------------------------------------------------------------
+def discriminator_losses(discriminator, fake, real):
+    """(reference training.py:107-117) one 2B discriminator pass; returns
+    (disc_loss, sign_real, sign_fake) as 1-element tensors."""
+    batch = real.shape[0]
+    scores = discriminator(torch.cat([fake, real], dim=0))
+    fake_scores, real_scores = scores[:batch], scores[batch:]
+    # disc_loss = (mse(real, 1) + mse(fake, 0)) / 2
+    real_loss, sign_real = ops.lsgan(real_scores, 1.0, 0.5)
+    fake_loss, sign_fake = ops.lsgan(fake_scores, 0.0, 0.5)
+    return real_loss + fake_loss, sign_real, -sign_fake
+
+
+def generator_losses(config, generator, discriminator, style_extractor, prints, marks,
+                     reconstruct_w, translation_w, w1, w2, cent_fin_diff_h, ada=None):
+    """(reference training.py:158-243) all generator-side losses with their lambdas folded in.
+    Returns (total, gan, rec, idt, kl, path, style): WEIGHTED 1-element tensors."""
+    opt = config["optimisation"]
+    batch = prints.shape[0]
+    nb = generator.n_style_blocks
+    combined_latents = generator.encode(torch.cat([prints, marks], dim=0))
+    kl_loss = ops.kl(combined_latents, opt["kl_loss_lambda"])
+    if config["architecture"]["add_latent_noise"]:
+        combined_latents = combined_latents + torch.randn_like(combined_latents)
+    shoeprint_latent, shoemark_latent = combined_latents.chunk(2, dim=0)
+
+    real_shoemark_w = style_extractor(marks)
+    identity_w = real_shoemark_w.expand(nb, *real_shoemark_w.shape)
+
+    # reconstruction / identity / translation as one 3B decode
+    dec_latents = torch.cat([shoeprint_latent, shoemark_latent, shoeprint_latent], dim=0)
+    dec_w = torch.cat([reconstruct_w, identity_w, translation_w], dim=1)
+    images = generator.decode(dec_latents, dec_w)
+    reconstruction_loss = ops.l1(images[:batch], prints, opt["reconstruction_loss_lambda"])
+    identity_loss = ops.l1(images[batch : 2 * batch], marks, opt["identity_loss_lambda"])
+    generated_shoemarks = images[2 * batch :]
+
+    # GAN loss (the discriminator's own weight gradients are not needed here)
+    d_params = [p for p in discriminator.parameters() if p.requires_grad]
+    for p in d_params:
+        p.requires_grad_(False)
+    try:
+        fake_in = generated_shoemarks if ada is None else ada(generated_shoemarks)
+        fake_shoemark_scores = discriminator(fake_in)
+    finally:
+        for p in d_params:
+            p.requires_grad_(True)
+    gan_loss, _ = ops.lsgan(fake_shoemark_scores, 1.0, 1.0)
+
+    reconstructed_w = style_extractor(generated_shoemarks)
+    style_loss = opt["style_cycle_loss_lambda"] * style_cycle_loss_func(
+        translation_w[-1], reconstructed_w
+    ).reshape(1)
+
+    # path length: two extractions of the same latent as one 2B batch
+    feats = generator.extract(torch.cat([shoeprint_latent, shoeprint_latent], dim=0),
+                              torch.cat([w1, w2], dim=1))
+    path_loss = ops.path(feats, cent_fin_diff_h, opt["path_loss_lambda"])
+
+    total = gan_loss + identity_loss + reconstruction_loss + kl_loss + path_loss + style_loss
+    return total, gan_loss, reconstruction_loss, identity_loss, kl_loss, path_loss, style_loss
+
+
+def unweighted(config, values):
+    """Undo the folded lambdas so the logged numbers are the reference's (training.py:250-257).
+    values = [total, gan, rec, idt, kl, path, style]."""
+    opt = config["optimisation"]
+    lam = [1.0, 1.0, opt["reconstruction_loss_lambda"], opt["identity_loss_lambda"],
+           opt["kl_loss_lambda"], opt["path_loss_lambda"], opt["style_cycle_loss_lambda"]]
+    return [v / l if l != 0 else 0.0 for v, l in zip(values, lam)]
+
+
+def backward_unit(loss):
+    """loss.backward() with the loss-seed fast path (each term's lambda is already folded in)."""
+    ops.UNIT_LOSS_GRADS = True
+    try:
+        loss.backward()
+    finally:
+        ops.UNIT_LOSS_GRADS = False
+
+
 def discriminator_step(
     config,
     device: torch.device,
@@ -146,21 +230,11 @@ def discriminator_step(
     real_shoemarks = next(shoemark_iter).to(device)
     augmented_real = ada(real_shoemarks)
 
-    scores = discriminator(torch.cat([augmented_fake, augmented_real], dim=0))
-    fake_scores, real_scores = scores[:batch], scores[batch:]
-    # disc_loss = (mse(real, 1) + mse(fake, 0)) / 2  (reference training.py:111-113)
-    real_loss, sign_real = ops.lsgan(real_scores, 1.0, 0.5)
-    fake_loss, sign_fake = ops.lsgan(fake_scores, 0.0, 0.5)
-    disc_loss = real_loss + fake_loss
-    sign_fake = -sign_fake
+    disc_loss, sign_real, sign_fake = discriminator_losses(discriminator, augmented_fake, augmented_real)
 
     ada_p.update_p(sign_real.reshape(()))
 
-    ops.UNIT_LOSS_GRADS = True
-    try:
-        disc_loss.backward()
-    finally:
-        ops.UNIT_LOSS_GRADS = False
+    backward_unit(disc_loss)
     discriminator_optimiser.step()
 
     loss, s_real, s_fake = _floats(disc_loss, sign_real, sign_fake)
@@ -198,18 +272,10 @@ def generator_step(
     real_shoeprint_images = next(shoeprint_iter).to(device)
     real_shoemark_images = next(shoemark_iter).to(device)
 
-    combined_latents = generator.encode(torch.cat([real_shoeprint_images, real_shoemark_images], dim=0))
-    kl_loss = ops.kl(combined_latents, opt["kl_loss_lambda"])
-    if config["architecture"]["add_latent_noise"]:
-        combined_latents = combined_latents + torch.randn_like(combined_latents)
-    shoeprint_latent, shoemark_latent = combined_latents.chunk(2, dim=0)
-
     # --- styles, in the reference's host-RNG draw order ----------------------
     reconstruct_w = mapping_network.get_single_w(
         batch_size=batch, n_gen_blocks=nb, device=device, domain_variable=0
     )
-    real_shoemark_w = style_extractor(real_shoemark_images)
-    identity_w = real_shoemark_w.expand(nb, *real_shoemark_w.shape)
     translation_w = mapping_network.get_single_w(
         batch_size=batch, n_gen_blocks=nb, device=device, domain_variable=1
     )
@@ -225,56 +291,13 @@ def generator_step(
         batch_size=batch, n_gen_blocks=nb, device=device, domain_variables=(d1, d2)
     )
 
-    # --- reconstruction / identity / translation as one 3B decode ----------------------------
-    dec_latents = torch.cat([shoeprint_latent, shoemark_latent, shoeprint_latent], dim=0)
-    dec_w = torch.cat([reconstruct_w, identity_w, translation_w], dim=1)
-    images = generator.decode(dec_latents, dec_w)
-    reconstructed_shoeprints = images[:batch]
-    reconstructed_shoemarks = images[batch : 2 * batch]
-    generated_shoemarks = images[2 * batch :]
-
-    reconstruction_loss = ops.l1(
-        reconstructed_shoeprints, real_shoeprint_images, opt["reconstruction_loss_lambda"]
-    )
-    identity_loss = ops.l1(reconstructed_shoemarks, real_shoemark_images, opt["identity_loss_lambda"])
-
-    # --- GAN loss (the discriminator's own weight gradients are not needed here) -------------
-    d_params = [p for p in discriminator.parameters() if p.requires_grad]
-    for p in d_params:
-        p.requires_grad_(False)
-    try:
-        fake_shoemark_scores = discriminator(ada(generated_shoemarks))
-    finally:
-        for p in d_params:
-            p.requires_grad_(True)
-    gan_loss, _ = ops.lsgan(fake_shoemark_scores, 1.0, 1.0)
-
-    # --- style cycle -------------------------------------------------------------------------
-    reconstructed_w = style_extractor(generated_shoemarks)
-    style_loss = opt["style_cycle_loss_lambda"] * style_cycle_loss_func(
-        translation_w[-1], reconstructed_w
-    ).reshape(1)
-
-    # --- path length: two extractions of the same latent as one 2B batch ---------------------
-    feats = generator.extract(torch.cat([shoeprint_latent, shoeprint_latent], dim=0),
-                              torch.cat([w1, w2], dim=1))
-    path_loss = ops.path(feats, cent_fin_diff_h, opt["path_loss_lambda"])
-
-    total_gen_loss = gan_loss + identity_loss + reconstruction_loss + kl_loss + path_loss + style_loss
-
-    ops.UNIT_LOSS_GRADS = True
-    try:
-        total_gen_loss.backward()
-    finally:
-        ops.UNIT_LOSS_GRADS = False
+    losses = generator_losses(config, generator, discriminator, style_extractor,
+                              real_shoeprint_images, real_shoemark_images, reconstruct_w,
+                              translation_w, w1, w2, cent_fin_diff_h, ada)
+    backward_unit(losses[0])
     generator_optimiser.step()
     mapping_network_optimiser.step()
     style_extractor_optimiser.step()
 
-    # report the UNWEIGHTED terms like the reference (training.py:250-257)
-    vals = _floats(total_gen_loss, gan_loss, reconstruction_loss, identity_loss, kl_loss, path_loss,
-                   style_loss)
-    lam = [1.0, 1.0, opt["reconstruction_loss_lambda"], opt["identity_loss_lambda"],
-           opt["kl_loss_lambda"], opt["path_loss_lambda"], opt["style_cycle_loss_lambda"]]
-    vals = [v / l if l != 0 else 0.0 for v, l in zip(vals, lam)]
+    vals = unweighted(config, _floats(*losses))
     return vals[0], tuple(vals[1:])

@@ -17,7 +17,7 @@ args = ap.parse_args()
 bench.BATCH = args.batch
 bench.CONFIG["training"]["batch_size"] = args.batch
 dev = torch.device("cuda", 0)
-step = bench.build_trainer(dev, 0)
+step = bench.build_trainer(dev, 0, use_graph=False)
 prints = SyntheticImages(args.batch, 1, bench.IMAGE, dev, seed=42, stream_id=0)
 marks = SyntheticImages(args.batch, 1, bench.IMAGE, dev, seed=42, stream_id=1)
 for _ in range(args.warm):
