@@ -21,6 +21,16 @@ struct ConvP {
   int tiles_w;
 };
 
+struct WgradP {
+  View x, dy;
+  int x_halo, kh, kw, pad, cin, cout, ktot;
+  float* dw;
+  float alpha;
+  const float* rs;
+  const float* cs;
+  int splits, pix_per_split;
+};
+
 // ---------------------------------------------------------------------------
 // generic tile kernel: 64 output pixels (8x8) x 64 output channels per CTA, K chunk 16
 // ---------------------------------------------------------------------------
@@ -268,7 +278,11 @@ static int launch_cout1_tiled(const ConvP& p, int n, cudaStream_t st) {
   const int tiles_w = (p.y.w + TT - 1) / TT, tiles_h = (p.y.h + TT - 1) / TT;
   const int per_img = tiles_w * tiles_h, total = per_img * n;
   auto kern = conv_cout1_tiled_kernel<TI, TO, KS>;
-  OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;  // once, outside any stream capture
+  if (!attr_set) {
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   int ctas = num_sms() * (smem > 110 * 1024 ? 1 : 2);
   if (ctas > total) ctas = total;
   kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);
@@ -277,18 +291,144 @@ static int launch_cout1_tiled(const ConvP& p, int n, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
+// Cin == 1 (the image-side 7x7 / 4x4 convs, Cout = 64): FFMA-bound, K = 49 / 16 is far below a
+// tensor-core tile.  One thread per output pixel holds all 64 accumulators; the image patch and
+// the weights sit in shared memory (weights read as broadcast 128-bit loads).
+// ---------------------------------------------------------------------------
+template <typename TO, int KS>
+__global__ void __launch_bounds__(256)
+conv_cin1_kernel(ConvP p, int tiles_w, int tiles_per_img, int total_tiles) {
+  constexpr int TT = 16, PW = TT + KS - 1, CO = 64;
+  __shared__ float xs[PW * PW];
+  __shared__ __align__(16) float ws[KS * KS * CO];  // [tap][cout]
+  const int tx = threadIdx.x % TT, ty = threadIdx.x / TT;
+  const int H = p.x.h, W = p.x.w, halo = p.x_halo;
+  const float* wbase = (const float*)p.w;
+  for (int e = threadIdx.x; e < KS * KS * CO; e += 256) {
+    int o = e % CO, tap = e / CO;
+    ws[e] = wbase[o * KS * KS + tap];
+  }
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
+    __syncthreads();
+    for (int e = threadIdx.x; e < PW * PW; e += 256) {
+      int pw = e % PW, ph = e / PW;
+      int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+      float v = 0.f;
+      if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo)
+        v = *vptr<float>(p.x, n, ih, iw, 0);
+      xs[e] = v;
+    }
+    __syncthreads();
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+#pragma unroll 1
+    for (int r = 0; r < KS; ++r) {
+#pragma unroll
+      for (int s2 = 0; s2 < KS; ++s2) {
+        const float xv = xs[(ty + r) * PW + tx + s2];
+        const float4* w4 = reinterpret_cast<const float4*>(ws + (r * KS + s2) * CO);
+#pragma unroll
+        for (int o4 = 0; o4 < CO / 4; ++o4) {
+          float4 w = w4[o4];
+          acc[4 * o4] = fmaf(xv, w.x, acc[4 * o4]);
+          acc[4 * o4 + 1] = fmaf(xv, w.y, acc[4 * o4 + 1]);
+          acc[4 * o4 + 2] = fmaf(xv, w.z, acc[4 * o4 + 2]);
+          acc[4 * o4 + 3] = fmaf(xv, w.w, acc[4 * o4 + 3]);
+        }
+      }
+    }
+    const int oh = oh0 + ty, ow = ow0 + tx;
+    if (oh < p.y.h && ow < p.y.w) {
+#pragma unroll
+      for (int g = 0; g < CO / 8; ++g) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = acc[g * 8 + j] * p.alpha;
+          if (p.row_scale) a *= p.row_scale[(long long)n * CO + g * 8 + j];
+          if (p.bias) a += p.bias[g * 8 + j];
+          v[j] = act_fwd(a, p.act);
+        }
+        if (p.res.ptr) {
+          float rr[8];
+          load_vec<TO, 8>(vptr<TO>(p.res, n, oh, ow, g * 8), rr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += rr[j];
+        }
+        store_halo<TO, 8>(p.y, p.y_halo, n, oh, ow, g * 8, v);
+      }
+    }
+  }
+}
+
+// wgrad of the same layers: dw[o][tap] = sum_px dy[px][o] * x[px + tap].  A thread owns one tap
+// and 8 output channels; per pixel it needs one image value (broadcast) and one 128-bit dy load.
+template <typename TDY, int KS>
+__global__ void __launch_bounds__(KS * KS * 8 <= 128 ? 128 : 416)
+wgrad_cin1_kernel(WgradP p, int tiles_w, int tiles_per_img, int total_tiles) {
+  constexpr int TT = 16, PW = TT + KS - 1, CO = 64;
+  constexpr int NT = KS * KS * 8 <= 128 ? 128 : 416;
+  extern __shared__ __align__(16) unsigned char wc1_smem[];
+  TDY* dys = reinterpret_cast<TDY*>(wc1_smem);                                  // [256 px][64]
+  float* xs = reinterpret_cast<float*>(wc1_smem + sizeof(TDY) * TT * TT * CO);  // [PW*PW]
+  const int tap = threadIdx.x / 8, og = threadIdx.x % 8;
+  const bool active = tap < KS * KS;
+  const int r = tap / KS, s2 = tap % KS;
+  const int H = p.x.h, W = p.x.w, halo = p.x_halo;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
+    __syncthreads();
+    for (int e = threadIdx.x; e < PW * PW; e += NT) {
+      int pw = e % PW, ph = e / PW;
+      int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+      float v = 0.f;
+      if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo)
+        v = *vptr<float>(p.x, n, ih, iw, 0);
+      xs[e] = v;
+    }
+    for (int e = threadIdx.x; e < TT * TT * 8; e += NT) {
+      int v8 = e % 8, q = e / 8;
+      int oh = oh0 + q / TT, ow = ow0 + q % TT;
+      float tmp[8];
+      if (oh < p.dy.h && ow < p.dy.w) {
+        load_vec<TDY, 8>(vptr<TDY>(p.dy, n, oh, ow, v8 * 8), tmp);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tmp[j] = 0.f;
+      }
+      store_vec<TDY, 8>(dys + q * CO + v8 * 8, tmp);
+    }
+    __syncthreads();
+    if (active) {
+      for (int qh = 0; qh < TT; ++qh) {
+#pragma unroll 4
+        for (int qw = 0; qw < TT; ++qw) {
+          const float xv = xs[(qh + r) * PW + qw + s2];
+          float d[8];
+          load_vec<TDY, 8>(dys + (qh * TT + qw) * CO + og * 8, d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, d[j], acc[j]);
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(p.dw + (og * 8 + j) * KS * KS + tap, acc[j] * p.alpha);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // wgrad, generic tile: M = 64 couts, N = 64 flattened (r,s,i), K = pixels of one sample
 // chunk.  grid = (ceil(ktot/64), ceil(cout/64), n * splits); atomicAdd into dw.
 // ---------------------------------------------------------------------------
-struct WgradP {
-  View x, dy;
-  int x_halo, kh, kw, pad, cin, cout, ktot;
-  float* dw;
-  float alpha;
-  const float* rs;
-  const float* cs;
-  int splits, pix_per_split;
-};
 
 template <typename T, typename TDY>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradP p) {
@@ -380,7 +520,8 @@ constexpr int WG_MAXI = 32;
 // Per-sample factors (rs/cs) are not supported here (the skinny layers are never modulated).
 template <typename T, typename TDY>
 __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT, int tiles_w,
-                                                               int tiles_per_img, int total_tiles) {
+                                                               int tiles_per_img, int total_tiles,
+                                                               int vec8) {
   extern __shared__ __align__(16) unsigned char wg_smem[];
   const int PW = TT + p.kw - 1, PH = TT + p.kh - 1;
   T* xs = reinterpret_cast<T*>(wg_smem);                                   // [PH][PW][cin]
@@ -410,13 +551,30 @@ __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT,
     const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
     const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
     __syncthreads();  // previous tile fully consumed
-    for (int e = threadIdx.x; e < patch; e += 256) {
-      int c = e % p.cin, q = e / p.cin;
-      int pw = q % PW, ph = q / PW;
-      int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
-      T v = from_f<T>(0.f);
-      if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo) v = *vptr<T>(p.x, n, ih, iw, c);
-      xs[e] = v;
+    if (vec8) {  // 128-bit staging: 8 channels per load
+      const int cv = p.cin / 8;
+      for (int e = threadIdx.x; e < PH * PW * cv; e += 256) {
+        int v = e % cv, q = e / cv;
+        int pw = q % PW, ph = q / PW;
+        int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+        float tmp[8];
+        if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo) {
+          load_vec<T, 8>(vptr<T>(p.x, n, ih, iw, v * 8), tmp);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tmp[i] = 0.f;
+        }
+        store_vec<T, 8>(xs + (size_t)q * p.cin + v * 8, tmp);
+      }
+    } else {
+      for (int e = threadIdx.x; e < patch; e += 256) {
+        int c = e % p.cin, q = e / p.cin;
+        int pw = q % PW, ph = q / PW;
+        int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+        T v = from_f<T>(0.f);
+        if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo) v = *vptr<T>(p.x, n, ih, iw, c);
+        xs[e] = v;
+      }
     }
     for (int e = threadIdx.x; e < TT * TT * p.cout; e += 256) {
       int o = e % p.cout, q = e / p.cout;
@@ -593,6 +751,23 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
   p.tiles_w = (a->y.w + 7) / 8;
   const int tiles_h = (a->y.h + 7) / 8;
   const bool in_bf = a->x.dtype == OTM_BF16, out_bf = a->y.dtype == OTM_BF16;
+  if (p.cin == 1 && p.cout == 64 && a->kh == a->kw && (a->kh == 4 || a->kh == 7) && !in_bf &&
+      a->w_batch_stride == 0 && vec_ok(a->y, 8) && vec_ok(a->residual, 8)) {
+    constexpr int TT = 16;
+    const int tiles_w = (a->y.w + TT - 1) / TT, tiles_h = (a->y.h + TT - 1) / TT;
+    const int per_img = tiles_w * tiles_h, total = per_img * a->y.n;
+    int ctas = num_sms() * 2;
+    if (ctas > total) ctas = total;
+    if (a->kh == 7) {
+      if (out_bf) conv_cin1_kernel<__nv_bfloat16, 7><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
+      else conv_cin1_kernel<float, 7><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
+    } else {
+      if (out_bf) conv_cin1_kernel<__nv_bfloat16, 4><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
+      else conv_cin1_kernel<float, 4><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
+    }
+    OTM_LAUNCH_CHECK();
+    return OTM_OK;
+  }
   if (p.cout == 1 && p.cin % 64 == 0 && a->kh == a->kw && (a->kh == 4 || a->kh == 7) &&
       vec_ok(a->x, 8) && a->y.h * a->y.w >= 256) {
 #define OTM_C1(TI, TO) \
@@ -610,9 +785,12 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
 #define OTM_LAUNCH_SMALL(TI, TO, V)                                                          \
   do {                                                                                        \
     auto kern = conv_small_cout_kernel<TI, TO, V>;                                            \
-    if (smem > 48 * 1024)                                                                     \
+    static bool set_ = false;                                                                 \
+    if (!set_) {                                                                              \
       OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                          (int)smem));                                        \
+                                          160 * 1024));                                       \
+      set_ = true;                                                                            \
+    }                                                                                         \
     kern<<<grid, 128, smem, st>>>(p);                                                         \
   } while (0)
     if (in_bf && out_bf) { if (v8) OTM_LAUNCH_SMALL(__nv_bfloat16, __nv_bfloat16, 8); else OTM_LAUNCH_SMALL(__nv_bfloat16, __nv_bfloat16, 1); }
@@ -638,6 +816,36 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
   p.x_halo = a->x_halo; p.kh = a->kh; p.kw = a->kw; p.pad = a->pad;
   p.cin = a->x.c; p.cout = a->dy.c; p.ktot = a->kh * a->kw * a->x.c;
   p.dw = a->dw; p.alpha = a->alpha; p.rs = a->rs; p.cs = a->cs;
+  // single input channel (image-side convs)
+  if (p.cin == 1 && p.cout == 64 && a->kh == a->kw && (a->kh == 4 || a->kh == 7) &&
+      a->x.dtype == OTM_F32 && !a->rs && !a->cs && vec_ok(a->dy, 8)) {
+    constexpr int TT = 16;
+    const int tiles_w = (a->dy.w + TT - 1) / TT, tiles_h = (a->dy.h + TT - 1) / TT;
+    const int per_img = tiles_w * tiles_h, total = per_img * a->dy.n;
+    int ctas = num_sms() * 2;
+    if (ctas > total) ctas = total;
+    const bool yb = a->dy.dtype == OTM_BF16;
+#define OTM_WC1(TDY, KS, NT)                                                                      \
+  do {                                                                                            \
+    const size_t smem = sizeof(TDY) * TT * TT * 64 + sizeof(float) * (TT + KS - 1) * (TT + KS - 1); \
+    auto kern = wgrad_cin1_kernel<TDY, KS>;                                                       \
+    static bool set_ = false;                                                                     \
+    if (!set_) {                                                                                  \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                          (int)smem));                                            \
+      set_ = true;                                                                                \
+    }                                                                                             \
+    kern<<<ctas, NT, smem, st>>>(p, tiles_w, per_img, total);                                     \
+  } while (0)
+    if (a->kh == 7) {
+      if (yb) OTM_WC1(__nv_bfloat16, 7, 416); else OTM_WC1(float, 7, 416);
+    } else {
+      if (yb) OTM_WC1(__nv_bfloat16, 4, 128); else OTM_WC1(float, 4, 128);
+    }
+#undef OTM_WC1
+    OTM_LAUNCH_CHECK();
+    return OTM_OK;
+  }
   // skinny output: persistent smem-tiled kernel
   if (p.cout <= 4 && (long long)p.ktot * p.cout <= 256LL * WG_MAXI && !a->rs && !a->cs) {
     const size_t es = dtype_size(a->x.dtype);
@@ -656,10 +864,15 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
 #define OTM_WG_SMALL(TX, TDY)                                                                   \
   do {                                                                                          \
     auto kern = wgrad_small_cout_kernel<TX, TDY>;                                               \
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                        (int)smem));                                            \
-    kern<<<ctas, 256, smem, st>>>(p, TT, tiles_w, per_img, total_tiles);                        \
+    static bool set_ = false;                                                                   \
+    if (!set_) {                                                                                \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          200 * 1024));                                         \
+      set_ = true;                                                                              \
+    }                                                                                           \
+    kern<<<ctas, 256, smem, st>>>(p, TT, tiles_w, per_img, total_tiles, vec8);                  \
   } while (0)
+      const int vec8 = vec_ok(a->x, 8) ? 1 : 0;
       const bool xb = a->x.dtype == OTM_BF16, yb = a->dy.dtype == OTM_BF16;
       if (xb && yb) OTM_WG_SMALL(__nv_bfloat16, __nv_bfloat16);
       else if (xb) OTM_WG_SMALL(__nv_bfloat16, float);

@@ -155,6 +155,30 @@ def test_conv_dgrad_wgrad(K, case, dtype):
     assert relerr(dw - 0.5, gw_ref * alpha) < TOL[dtype] * 2, f"wgrad {case}"
 
 
+@pytest.mark.parametrize("k,pad,halo,H,W", [(7, 3, 3, 40, 24), (4, 1, 0, 33, 20), (7, 3, 3, 16, 16)])
+def test_image_side_convs_mixed_dtype(K, k, pad, halo, H, W):
+    """Cin == 1 kernels: fp32 image in, bf16 activations out; wgrad with fp32 x and bf16 dy."""
+    n, cout = 3, 64
+    x = rnd(n, 1, H, W, seed=60)
+    w = rnd(cout, 1, k, k, seed=61)
+    bias = rnd(cout, seed=62)
+    alpha = 1 / math.sqrt(k * k)
+    xp = F.pad(x, (halo,) * 4, mode="reflect") if halo else x
+    ref = F.leaky_relu(F.conv2d(xp, w * alpha, bias, padding=pad - halo), 0.2)
+    wp = K.weight_pack(w, alpha, torch.float32)
+    for dt in (torch.bfloat16, torch.float32):
+        y = K.conv_fwd(nhwc(x, torch.float32, halo), wp, cout, k, k, pad, x_halo=halo, bias=bias,
+                       act=K.ACT_LRELU, out_dtype=dt, y_halo=1)
+        assert y.dtype == dt and relerr(y.float(), ref) < TOL[dt]
+        assert torch.equal(K.padded_view(y, 1).float(), F.pad(y.float(), (1,) * 4, mode="reflect"))
+        dy = rnd(*ref.shape, seed=63).to(dt)
+        gw_ref = torch.nn.grad.conv2d_weight(xp, w.shape, dy.float(), padding=pad - halo) * alpha
+        dw = torch.zeros_like(w)
+        K.conv_wgrad(nhwc(x, torch.float32, halo), nhwc(dy.float(), dt), dw, k, k, pad, x_halo=halo,
+                     alpha=alpha)
+        assert relerr(dw, gw_ref) < 2e-4, (k, dt)
+
+
 @pytest.mark.parametrize("case", [(128, 128, 16, 16, 3), (64, 128, 16, 24, 2), (128, 64, 16, 16, 2),
                                   (256, 256, 8, 8, 2), (128, 256, 15, 15, 2)])
 def test_wgrad_tc_modulated(K, case):
