@@ -608,6 +608,75 @@ __global__ void __launch_bounds__(256) wgrad_small_cout_kernel(WgradP p, int TT,
 }
 
 // ---------------------------------------------------------------------------
+// wgrad for Cout == 1 (generator output conv 64->1 7x7, discriminator output conv 512->1 4x4):
+// dw[tap][c] = sum_px dy[px] * x[px + tap][c].  A thread owns one tap and 8 channels: per pixel
+// one broadcast dy value and one 128-bit patch load feed 8 FMAs.  Persistent over tiles.
+// blockDim = taps * cin/8 (<= 1024).
+// ---------------------------------------------------------------------------
+template <typename T, typename TDY>
+__global__ void __launch_bounds__(1024)
+wgrad_cout1_kernel(WgradP p, int TT, int tiles_w, int tiles_per_img, int total_tiles) {
+  extern __shared__ __align__(16) unsigned char wo1_smem[];
+  const int PW = TT + p.kw - 1, PH = TT + p.kh - 1;
+  const int cv = p.cin / 8;
+  T* xs = reinterpret_cast<T*>(wo1_smem);                                   // [PH*PW][cin]
+  float* dys = reinterpret_cast<float*>(xs + (size_t)PH * PW * p.cin);      // [TT*TT]
+  const int nthreads = blockDim.x;
+  const int tap = threadIdx.x / cv, cg = threadIdx.x % cv;
+  const int r = tap / p.kw, s2 = tap % p.kw;
+  const bool active = tap < p.kh * p.kw;
+  const int H = p.x.h, W = p.x.w, halo = p.x_halo;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
+    __syncthreads();
+    for (int e = threadIdx.x; e < PH * PW * cv; e += nthreads) {
+      int v = e % cv, q = e / cv;
+      int pw = q % PW, ph = q / PW;
+      int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+      float tmp[8];
+      if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo) {
+        load_vec<T, 8>(vptr<T>(p.x, n, ih, iw, v * 8), tmp);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tmp[i] = 0.f;
+      }
+      store_vec<T, 8>(xs + (size_t)q * p.cin + v * 8, tmp);
+    }
+    for (int e = threadIdx.x; e < TT * TT; e += nthreads) {
+      int oh = oh0 + e / TT, ow = ow0 + e % TT;
+      float v = 0.f;
+      if (oh < p.dy.h && ow < p.dy.w) v = to_f(*vptr<TDY>(p.dy, n, oh, ow, 0));
+      dys[e] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int qh = 0; qh < TT; ++qh) {
+        const T* xrow = xs + ((size_t)(qh + r) * PW + s2) * p.cin + cg * 8;
+        const float* drow = dys + qh * TT;
+#pragma unroll 4
+        for (int qw = 0; qw < TT; ++qw) {
+          float xv[8];
+          load_vec<T, 8>(xrow + (size_t)qw * p.cin, xv);
+          const float d = drow[qw];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(d, xv[j], acc[j]);
+        }
+      }
+    }
+  }
+  if (active) {
+    const int taps = p.kh * p.kw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      atomicAdd(p.dw + (long long)(cg * 8 + j) * taps + tap, acc[j] * p.alpha);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // weight staging / modulation coefficients
 // ---------------------------------------------------------------------------
 // One thread stages 8 consecutive output elements (one 128-bit store for bf16) for ALL nb
@@ -845,6 +914,43 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
 #undef OTM_WC1
     OTM_LAUNCH_CHECK();
     return OTM_OK;
+  }
+  // single output channel: (tap, 8-channel) threads over a shared-memory patch
+  if (p.cout == 1 && p.cin % 8 == 0 && a->kh * a->kw * (p.cin / 8) <= 1024 && !a->rs && !a->cs &&
+      vec_ok(a->x, 8)) {
+    const size_t es = dtype_size(a->x.dtype);
+    int TT = 16;
+    auto smem_for = [&](int tt) {
+      return (size_t)(tt + p.kh - 1) * (tt + p.kw - 1) * p.cin * es + (size_t)tt * tt * sizeof(float);
+    };
+    while (TT > 2 && smem_for(TT) > 100 * 1024) TT /= 2;
+    if (smem_for(TT) <= 100 * 1024) {
+      const int tiles_w = (a->dy.w + TT - 1) / TT, tiles_h = (a->dy.h + TT - 1) / TT;
+      const int per_img = tiles_w * tiles_h, total_tiles = per_img * a->dy.n;
+      const size_t smem = smem_for(TT);
+      int nthreads = (a->kh * a->kw * (p.cin / 8) + 31) / 32 * 32;
+      int ctas = num_sms() * 2;
+      if (ctas > total_tiles) ctas = total_tiles;
+#define OTM_WO1(TX, TDY)                                                                        \
+  do {                                                                                          \
+    auto kern = wgrad_cout1_kernel<TX, TDY>;                                                    \
+    static bool set_ = false;                                                                   \
+    if (!set_) {                                                                                \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          100 * 1024));                                         \
+      set_ = true;                                                                              \
+    }                                                                                           \
+    kern<<<ctas, nthreads, smem, st>>>(p, TT, tiles_w, per_img, total_tiles);                   \
+  } while (0)
+      const bool xb = a->x.dtype == OTM_BF16, yb = a->dy.dtype == OTM_BF16;
+      if (xb && yb) OTM_WO1(__nv_bfloat16, __nv_bfloat16);
+      else if (xb) OTM_WO1(__nv_bfloat16, float);
+      else if (yb) OTM_WO1(float, __nv_bfloat16);
+      else OTM_WO1(float, float);
+#undef OTM_WO1
+      OTM_LAUNCH_CHECK();
+      return OTM_OK;
+    }
   }
   // skinny output: persistent smem-tiled kernel
   if (p.cout <= 4 && (long long)p.ktot * p.cout <= 256LL * WG_MAXI && !a->rs && !a->cs) {
