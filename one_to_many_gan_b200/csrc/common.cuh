@@ -194,22 +194,43 @@ __device__ __forceinline__ void load_fold(const View& g, int halo, int n, int h,
     }
 }
 
-__device__ __forceinline__ float act_fwd(float x, int act) {
-  switch (act) {
-    case OTM_ACT_RELU: return x > 0.f ? x : 0.f;
-    case OTM_ACT_LRELU: return x > 0.f ? x : 0.2f * x;
-    case OTM_ACT_TANH: return tanhf(x);
-    default: return x;
+// Activations are applied to whole register vectors with ONE (warp-uniform) branch per vector:
+// a per-element `switch` inlines tanhf() at every call site, which bloated the tcgen05 epilogue
+// past the instruction cache and cost ~100 us per launch (profiles/r1_epilogue_ablation.md).
+template <int V>
+__device__ __forceinline__ void act_fwd_vec(float (&v)[V], int act) {
+  if (act == OTM_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == OTM_ACT_LRELU) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
+  } else if (act == OTM_ACT_TANH) {
+#pragma unroll 1
+    for (int i = 0; i < V; ++i) v[i] = tanhf(v[i]);
   }
 }
-// derivative given the PRE-activation value
-__device__ __forceinline__ float act_bwd(float pre, int act) {
-  switch (act) {
-    case OTM_ACT_RELU: return pre > 0.f ? 1.f : 0.f;
-    case OTM_ACT_LRELU: return pre > 0.f ? 1.f : 0.2f;
-    case OTM_ACT_TANH: { float t = tanhf(pre); return 1.f - t * t; }
-    default: return 1.f;
+// g[i] *= act'(pre[i])  (derivative given the PRE-activation value)
+template <int V>
+__device__ __forceinline__ void act_bwd_vec(float (&g)[V], const float (&pre)[V], int act) {
+  if (act == OTM_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = pre[i] > 0.f ? g[i] : 0.f;
+  } else if (act == OTM_ACT_LRELU) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = pre[i] > 0.f ? g[i] : 0.2f * g[i];
+  } else if (act == OTM_ACT_TANH) {
+#pragma unroll 1
+    for (int i = 0; i < V; ++i) {
+      float t = tanhf(pre[i]);
+      g[i] *= 1.f - t * t;
+    }
   }
+}
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  float v[1] = {x};
+  act_fwd_vec<1>(v, act);
+  return v[0];
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -350,8 +350,9 @@ conv_cin1_kernel(ConvP p, int tiles_w, int tiles_per_img, int total_tiles) {
           float a = acc[g * 8 + j] * p.alpha;
           if (p.row_scale) a *= p.row_scale[(long long)n * CO + g * 8 + j];
           if (p.bias) a += p.bias[g * 8 + j];
-          v[j] = act_fwd(a, p.act);
+          v[j] = a;
         }
+        act_fwd_vec<8>(v, p.act);
         if (p.res.ptr) {
           float rr[8];
           load_vec<TO, 8>(vptr<TO>(p.res, n, oh, ow, g * 8), rr);

@@ -151,6 +151,7 @@ struct TcFwdP {
   const float* bias;
   float alpha;
   int act, y_halo;
+  int debug;  // 0 normal; 1 skip epilogue stores; 2 skip the TMEM read-out too (timing experiments)
   int cin, cout, kh, kw;
   int coord_off;  // x_halo - pad : added to (h0 + r), (w0 + s) to index the halo'd tensor map
   int TW, TH, tiles_w;
@@ -159,9 +160,14 @@ struct TcFwdP {
 
 constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 
+// Epilogue math for 16 consecutive output channels of one pixel, result packed to bf16 and
+// written to the shared-memory staging tile (row = pixel, pitch BN*2+16 bytes: conflict-free
+// for the 16-byte per-lane stores of a quarter warp).
 template <int BN>
-__device__ __forceinline__ void epilogue_store16(const TcFwdP& p, int n, int oh, int ow, int o,
-                                                 float (&v)[16]) {
+__device__ __forceinline__ void epilogue_math16(const TcFwdP& p, int n, int oh, int ow, int o,
+                                                bool valid, float (&v)[16], uint8_t* dst) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
   if (p.row_scale) {
     const float4* rs = reinterpret_cast<const float4*>(p.row_scale + (long long)n * p.cout + o);
 #pragma unroll
@@ -178,9 +184,8 @@ __device__ __forceinline__ void epilogue_store16(const TcFwdP& p, int n, int oh,
       v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
     }
   }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = act_fwd(v[i], p.act);
-  if (p.res.ptr) {
+  act_fwd_vec<16>(v, p.act);
+  if (p.res.ptr && valid) {
     const __nv_bfloat16* rp = vptr<__nv_bfloat16>(p.res, n, oh, ow, o);
     float r0[8], r1[8];
     load_vec<__nv_bfloat16, 8>(rp, r0);
@@ -188,18 +193,16 @@ __device__ __forceinline__ void epilogue_store16(const TcFwdP& p, int n, int oh,
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i] += r0[i]; v[8 + i] += r1[i]; }
   }
-  float lo[8], hi[8];
+  uint4 lo, hi;
+  __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
-  int hs[3], ws[3];
-  int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
-  int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
-  for (int a = 0; a < nh; ++a)
-    for (int b = 0; b < nw; ++b) {
-      __nv_bfloat16* yp = vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o);
-      store_vec<__nv_bfloat16, 8>(yp, lo);
-      store_vec<__nv_bfloat16, 8>(yp + 8, hi);
-    }
+  for (int i = 0; i < 4; ++i) {
+    l2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    h2[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+  }
+  *reinterpret_cast<uint4*>(dst) = lo;
+  *reinterpret_cast<uint4*>(dst + 16) = hi;
 }
 
 template <int BN, int STAGES, int OCC>
@@ -289,14 +292,47 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int m = wq * 32 + lane;
     const int oh = h0 + m / p.TW, ow = w0 + m % p.TW;
     const bool valid = (oh < p.y.h) && (ow < p.y.w);
+    // Phase 1: TMEM -> registers -> epilogue math -> bf16 staging tile in shared memory.  The
+    // operand ring is drained once accum_full has fired, so the tile aliases it.
+    constexpr int PITCH = BN * 2 + 16;
+    static_assert(128 * PITCH <= STAGES * STAGE_BYTES, "staging tile must fit inside the ring");
+    uint8_t* stage_out = smem;
+    if (p.debug < 2) {
 #pragma unroll 1
-    for (int j = 0; j < BN / 16; ++j) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
-      if (valid) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
-        epilogue_store16<BN>(p, n, oh, ow, o0 + j * 16, v);
+      for (int j = 0; j < BN / 16; ++j) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
+        epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, stage_out + m * PITCH + j * 32);
+      }
+    }
+    if (p.debug == 4) {  // experiment: TMEM read-out only, no math, no staging
+#pragma unroll 1
+      for (int j = 0; j < BN / 16; ++j) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
+        if (v[0] == 123.456f) stage_out[m] = 1;
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+    // Phase 2: coalesced write-out, one 16-byte lane per 8 channels, whole pixel rows per warp
+    // instruction; the reflect halo of the consumer conv is written from the same registers.
+    if (p.debug == 0 || p.debug == 3) {
+      constexpr int LPR = BN / 8;          // lanes per pixel row
+      constexpr int RPP = 128 / LPR;       // pixel rows per pass
+      const int t = threadIdx.x - 128;
+      const int lr = t % LPR, r0 = t / LPR;
+#pragma unroll 1
+      for (int row = r0; row < 128; row += RPP) {
+        const int rh = h0 + row / p.TW, rw = w0 + row % p.TW;
+        if (rh >= p.y.h || rw >= p.y.w) continue;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage_out + row * PITCH + lr * 16);
+        int hs[3], ws[3];
+        const int nh = mirror_set(rh, p.y.h, p.y_halo, hs);
+        const int nw = mirror_set(rw, p.y.w, p.y_halo, ws);
+        for (int a = 0; a < nh; ++a)
+          for (int b = 0; b < nw; ++b)
+            *reinterpret_cast<uint4*>(vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + lr * 8)) = val;
       }
     }
     tc_fence_before();
@@ -523,7 +559,9 @@ bool conv_fwd_tc_eligible(const otm_conv_fwd_args* a) {
 template <int BN, int STAGES, int OCC>
 static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcFwdP& p, dim3 grid,
                       cudaStream_t st) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + 1024 + 256;
+  constexpr int ring = STAGES * (A_STAGE_BYTES + BN * 128);
+  constexpr int tile = 128 * (BN * 2 + 16);  // epilogue staging tile aliases the ring
+  constexpr int smem = (ring > tile ? ring : tile) + 1024 + 256;
   auto kern = conv_tc_fwd_kernel<BN, STAGES, OCC>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -566,6 +604,8 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   p.coord_off = a->x_halo - a->pad;
   p.TW = TW; p.TH = TH; p.tiles_w = (Wo + TW - 1) / TW;
   p.w_rows_per_sample = a->w_batch_stride ? cout : 0;
+  static const int dbg = [] { const char* e = getenv("OTM_TC_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = dbg;
   dim3 grid(best_tiles, cout / BN, a->y.n);
   // variant 0 (default): 2 CTAs per SM with a short ring, so one CTA's prologue/epilogue
   // overlaps the other's MMA main loop; variant 1: 1 CTA per SM with a deep ring.
@@ -574,6 +614,11 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
     if (BN == 64) return launch_fwd<64, 6, 1>(tmA, tmB, p, grid, st);
     if (BN == 128) return launch_fwd<128, 6, 1>(tmA, tmB, p, grid, st);
     return launch_fwd<256, 4, 1>(tmA, tmB, p, grid, st);
+  }
+  if (variant == 2) {  // 3 CTAs per SM, 2-deep ring
+    if (BN == 64) return launch_fwd<64, 3, 3>(tmA, tmB, p, grid, st);
+    if (BN == 128) return launch_fwd<128, 2, 3>(tmA, tmB, p, grid, st);
+    return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
   }
   if (BN == 64) return launch_fwd<64, 4, 2>(tmA, tmB, p, grid, st);
   if (BN == 128) return launch_fwd<128, 3, 2>(tmA, tmB, p, grid, st);

@@ -177,8 +177,7 @@ struct NormActF {
 #pragma unroll
       for (int i = 0; i < V; ++i) v[i] = (v[i] - st[2 * i]) * st[2 * i + 1];
     }
-#pragma unroll
-    for (int i = 0; i < V; ++i) v[i] = act_fwd(v[i], act);
+    act_fwd_vec<V>(v, act);
     if (res.ptr) {
       float r[V];
       load_vec<T, V>(vptr<T>(res, n, h, w, c), r);
@@ -216,7 +215,8 @@ struct NormActBwdBase {
       for (int i = 0; i < V; ++i) pre[i] = (pre[i] - st[2 * i]) * st[2 * i + 1];
     }
 #pragma unroll
-    for (int i = 0; i < V; ++i) gn[i] = ga[i] * act_bwd(pre[i], act);
+    for (int i = 0; i < V; ++i) gn[i] = ga[i];
+    act_bwd_vec<V>(gn, pre, act);
   }
 };
 
@@ -330,11 +330,13 @@ struct DownF {
         if (wgt == 0.f) continue;
         float v[V];
         load_vec<T, V>(vptr<T>(x, n, ph[a], pw[b], c), v);
+        if (stats) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          float t = stats ? (v[i] - mean[i]) * rstd[i] : v[i];
-          acc[i] += wgt * act_fwd(t, act);
+          for (int i = 0; i < V; ++i) v[i] = (v[i] - mean[i]) * rstd[i];
         }
+        act_fwd_vec<V>(v, act);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += wgt * v[i];
       }
     }
     store_halo<T, V>(y, halo, n, ho, wo, c, acc);
