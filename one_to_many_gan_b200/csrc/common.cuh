@@ -108,14 +108,17 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
   return __float2bfloat16_rn(x);
 }
 
-// V-wide (1 or 8) channel vector load/store with fp32 registers
-template <typename T, int V>
-__device__ __forceinline__ void load_vec(const T* p, float (&v)[V]) {
+// V-wide (1 or 8) channel vector load/store with fp32 registers.
+// (Measured: routing these through ld.global.nc (__ldg) or unrolling the row loops x4 made the
+// stencil and reduce passes 10-80 % SLOWER on B200, so plain coherent loads are used.)
+template <typename T, int V, bool RO>
+__device__ __forceinline__ void load_vec_impl(const T* p, float (&v)[V]) {
   if constexpr (V == 1) {
-    v[0] = to_f(*p);
+    v[0] = to_f(RO ? __ldg(p) : *p);
   } else if constexpr (sizeof(T) == 2) {
     static_assert(V == 8, "V must be 1 or 8");
-    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 raw = RO ? __ldg(q) : *q;
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -124,12 +127,17 @@ __device__ __forceinline__ void load_vec(const T* p, float (&v)[V]) {
       v[2 * i + 1] = f.y;
     }
   } else {
-    float4 a = *reinterpret_cast<const float4*>(p);
-    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = RO ? __ldg(q) : q[0];
+    float4 b = RO ? __ldg(q + 1) : q[1];
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
 }
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T* p, float (&v)[V]) { load_vec_impl<T, V, false>(p, v); }
+template <typename T, int V>
+__device__ __forceinline__ void load_vec_rw(const T* p, float (&v)[V]) { load_vec_impl<T, V, false>(p, v); }
 template <typename T, int V>
 __device__ __forceinline__ void store_vec(T* p, const float (&v)[V]) {
   if constexpr (V == 1) {
@@ -165,6 +173,10 @@ __device__ __forceinline__ int mirror_set(int i, int n, int p, int (&out)[3]) {
 template <typename T, int V>
 __device__ __forceinline__ void store_halo(const View& y, int halo, int n, int h, int w, int c,
                                            const float (&v)[V]) {
+  if (halo == 0 || (h > halo && h < y.h - 1 - halo && w > halo && w < y.w - 1 - halo)) {
+    store_vec<T, V>(vptr_mut<T>(y, n, h, w, c), v);
+    return;
+  }
   int hs[3], ws[3];
   int nh = mirror_set(h, y.h, halo, hs);
   int nw = mirror_set(w, y.w, halo, ws);
@@ -176,7 +188,8 @@ __device__ __forceinline__ void store_halo(const View& y, int halo, int n, int h
 template <typename T, int V>
 __device__ __forceinline__ void load_fold(const View& g, int halo, int n, int h, int w, int c,
                                           float (&v)[V]) {
-  if (halo == 0) {
+  // interior pixels (all but a 2*halo+1 wide frame) alias nothing
+  if (halo == 0 || (h > halo && h < g.h - 1 - halo && w > halo && w < g.w - 1 - halo)) {
     load_vec<T, V>(vptr<T>(g, n, h, w, c), v);
     return;
   }

@@ -226,18 +226,18 @@ conv_cout1_tiled_kernel(ConvP p, int tiles_w, int tiles_per_img, int total_tiles
           const TI* xrow = xs + ((size_t)(row + r) * PW + col4) * CC + cg * 8;
           float xw[4][8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) load_vec<TI, 8>(xrow + j * CC, xw[j]);
+          for (int j = 0; j < 4; ++j) load_vec_rw<TI, 8>(xrow + j * CC, xw[j]);
 #pragma unroll
           for (int s2 = 0; s2 < KS; ++s2) {
             float wv[8];
-            load_vec<float, 8>(ws + (r * KS + s2) * CC + cg * 8, wv);
+            load_vec_rw<float, 8>(ws + (r * KS + s2) * CC + cg * 8, wv);
 #pragma unroll
             for (int px = 0; px < 4; ++px) {
               const float* xv = xw[(s2 + px) % 4];
 #pragma unroll
               for (int i = 0; i < 8; ++i) acc[pass][px] = fmaf(xv[i], wv[i], acc[pass][px]);
             }
-            if (s2 + 1 < KS) load_vec<TI, 8>(xrow + (s2 + 4) * CC, xw[s2 % 4]);
+            if (s2 + 1 < KS) load_vec_rw<TI, 8>(xrow + (s2 + 4) * CC, xw[s2 % 4]);
           }
         }
       }
@@ -413,7 +413,7 @@ wgrad_cin1_kernel(WgradP p, int tiles_w, int tiles_per_img, int total_tiles) {
         for (int qw = 0; qw < TT; ++qw) {
           const float xv = xs[(qh + r) * PW + qw + s2];
           float d[8];
-          load_vec<TDY, 8>(dys + (qh * TT + qw) * CO + og * 8, d);
+          load_vec_rw<TDY, 8>(dys + (qh * TT + qw) * CO + og * 8, d);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, d[j], acc[j]);
         }
@@ -661,7 +661,7 @@ wgrad_cout1_kernel(WgradP p, int TT, int tiles_w, int tiles_per_img, int total_t
 #pragma unroll 4
         for (int qw = 0; qw < TT; ++qw) {
           float xv[8];
-          load_vec<T, 8>(xrow + (size_t)qw * p.cin, xv);
+          load_vec_rw<T, 8>(xrow + (size_t)qw * p.cin, xv);
           const float d = drow[qw];
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(d, xv[j], acc[j]);

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) affine_grad_kernel(View x, View grad, con
     int n = (int)(p / H);
     float v[V], g[V];
     load_vec<T, V>(vptr<T>(x, n, h, w, cv * V), v);
-    if (accumulate) load_vec<T, V>(vptr<T>(grad, n, h, w, cv * V), g);
+    if (accumulate) load_vec_rw<T, V>(vptr<T>(grad, n, h, w, cv * V), g);
 #pragma unroll
     for (int i = 0; i < V; ++i) g[i] = (accumulate ? g[i] : 0.f) + c0 + c1 * v[i];
     store_vec<T, V>(vptr_mut<T>(grad, n, h, w, cv * V), g);

@@ -19,28 +19,47 @@ static inline int ew_grid(long long total, int threads) {
 
 // ---------------------------------------------------------------------------
 // generic element-wise driver: F::operator()(n,h,w,c0)
+// A CTA owns `rows` consecutive (n,h) image rows; a thread owns one (w, channel-vector) column
+// of them.  All index arithmetic is 32-bit, (n,h) is CTA-uniform, and the (w,cv) split is a
+// shift when C/V is a power of two -- the first version spent ~390 instructions per 16-byte
+// vector on 64-bit div/mod and reached only 0.4-1.4 TB/s (profiles/r1_ew_kernels.md).
 // ---------------------------------------------------------------------------
 template <int V, typename F>
-__global__ void __launch_bounds__(256) ew_kernel(F f, int N, int H, int W, int C) {
+__global__ void __launch_bounds__(256) ew_kernel(F f, int N, int H, int W, int C, int cv_shift,
+                                                 int rows) {
   const int CV = C / V;
-  const long long total = (long long)N * H * W * CV;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    long long p = idx / CV;
-    int w = (int)(p % W);
-    p /= W;
-    int h = (int)(p % H);
-    int n = (int)(p / H);
-    f(n, h, w, cv * V);
+  const int WC = W * CV;
+  const int nrows = N * H;
+  const int r0 = blockIdx.x * rows;
+  const int r1 = min(r0 + rows, nrows);
+  for (int i = threadIdx.x; i < WC; i += 256) {
+    int w, cv;
+    if (cv_shift >= 0) { w = i >> cv_shift; cv = i & (CV - 1); }
+    else { w = i / CV; cv = i - w * CV; }
+    typename F::State st;
+    int cur_n = -1;
+    for (int r = r0; r < r1; ++r) {
+      const int n = r / H, h = r - n * H;
+      if (n != cur_n) { f.prepare(n, cv * V, st); cur_n = n; }  // per-(n, channel) constants
+      f(n, h, w, cv * V, st);
+    }
   }
 }
 
 template <int V, typename F>
 static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
-  long long total = (long long)N * H * W * (C / V);
+  const long long total = (long long)N * H * W * (C / V);
   if (total == 0) return OTM_OK;
-  ew_kernel<V, F><<<ew_grid(total, 256), 256, 0, st>>>(f, N, H, W, C);
+  const int CV = C / V;
+  int cv_shift = -1;
+  if ((CV & (CV - 1)) == 0) { cv_shift = 0; while ((1 << cv_shift) < CV) ++cv_shift; }
+  const int nrows = N * H;
+  // enough CTAs for ~8 per SM; at most 4 rows per CTA
+  int rows = nrows / (num_sms() * 8);
+  if (rows < 1) rows = 1;
+  if (rows > 8) rows = 8;
+  const int grid = (nrows + rows - 1) / rows;
+  ew_kernel<V, F><<<grid, 256, 0, st>>>(f, N, H, W, C, cv_shift, rows);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
 }
@@ -72,9 +91,11 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(F f, int H, int W, int C
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
     if (cv < CV) {
+      typename F::State st;
+      f.prepare(n, cv * V, st);
       for (int p = p0 + row; p < p1; p += rows) {
         int h = p / W, w = p - h * W;
-        f(n, h, w, cv * V, acc);
+        f(n, h, w, cv * V, acc, st);
       }
     }
 #pragma unroll
@@ -133,13 +154,14 @@ struct StatsF {
   static constexpr int NQ = 2;
   View x;
   int C;
-  __device__ void operator()(int n, int h, int w, int c, float (&acc)[2][V]) const {
-    float v[V], k[V];
+  struct State { float k[V]; };
+  __device__ void prepare(int n, int c, State& st) const { load_vec<T, V>(vptr<T>(x, n, 0, 0, c), st.k); }
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[2][V], const State& st) const {
+    float v[V];
     load_vec<T, V>(vptr<T>(x, n, h, w, c), v);
-    load_vec<T, V>(vptr<T>(x, n, 0, 0, c), k);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float d = v[i] - k[i];
+      float d = v[i] - st.k[i];
       acc[0][i] += d;
       acc[1][i] += d * d;
     }
@@ -169,13 +191,20 @@ struct NormActF {
   View x, res, y;
   const float* stats;
   int act, halo, C;
-  __device__ void operator()(int n, int h, int w, int c) const {
+  struct State { float mean[V], rstd[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+    if (stats) {
+      const float* p = stats + ((long long)n * C + c) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { st.mean[i] = p[2 * i]; st.rstd[i] = p[2 * i + 1]; }
+    }
+  }
+  __device__ void operator()(int n, int h, int w, int c, const State& st) const {
     float v[V];
     load_vec<T, V>(vptr<T>(x, n, h, w, c), v);
     if (stats) {
-      const float* st = stats + ((long long)n * C + c) * 2;
 #pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = (v[i] - st[2 * i]) * st[2 * i + 1];
+      for (int i = 0; i < V; ++i) v[i] = (v[i] - st.mean[i]) * st.rstd[i];
     }
     act_fwd_vec<V>(v, act);
     if (res.ptr) {
@@ -194,8 +223,16 @@ struct NormActBwdBase {
   View g, g2, x;
   const float* stats;
   int act, g_halo, C;
+  struct State { float mean[V], rstd[V], m1[V], m2[V]; };
+  __device__ void prepare_stats(int n, int c, State& st) const {
+    if (stats) {
+      const float* p = stats + ((long long)n * C + c) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { st.mean[i] = p[2 * i]; st.rstd[i] = p[2 * i + 1]; }
+    }
+  }
   __device__ void compute(int n, int h, int w, int c, float (&ga)[V], float (&gn)[V],
-                          float (&pre)[V]) const {
+                          float (&pre)[V], const State& st) const {
     load_fold<T, V>(g, g_halo, n, h, w, c, ga);
     if (g2.ptr) {
       float t[V];
@@ -210,9 +247,8 @@ struct NormActBwdBase {
       for (int i = 0; i < V; ++i) pre[i] = 0.f;
     }
     if (stats) {
-      const float* st = stats + ((long long)n * C + c) * 2;
 #pragma unroll
-      for (int i = 0; i < V; ++i) pre[i] = (pre[i] - st[2 * i]) * st[2 * i + 1];
+      for (int i = 0; i < V; ++i) pre[i] = (pre[i] - st.mean[i]) * st.rstd[i];
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) gn[i] = ga[i];
@@ -223,9 +259,11 @@ struct NormActBwdBase {
 template <typename T, int V>
 struct NormActBwdReduceF : NormActBwdBase<T, V> {
   static constexpr int NQ = 2;
-  __device__ void operator()(int n, int h, int w, int c, float (&acc)[2][V]) const {
+  using State = typename NormActBwdBase<T, V>::State;
+  __device__ void prepare(int n, int c, State& st) const { this->prepare_stats(n, c, st); }
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[2][V], const State& st) const {
     float ga[V], gn[V], pre[V];
-    this->compute(n, h, w, c, ga, gn, pre);
+    this->compute(n, h, w, c, ga, gn, pre, st);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       acc[0][i] += gn[i];
@@ -240,16 +278,22 @@ struct NormActBwdApplyF : NormActBwdBase<T, V> {
   View gx, gres;
   const float* sums;
   float inv_hw;
-  __device__ void operator()(int n, int h, int w, int c) const {
-    float ga[V], gn[V], pre[V];
-    this->compute(n, h, w, c, ga, gn, pre);
-    if (gres.ptr) store_vec<T, V>(vptr_mut<T>(gres, n, h, w, c), ga);
+  using State = typename NormActBwdBase<T, V>::State;
+  __device__ void prepare(int n, int c, State& st) const {
+    this->prepare_stats(n, c, st);
     if (this->stats) {
-      const float* st = this->stats + ((long long)n * this->C + c) * 2;
       const float* sm = sums + ((long long)n * this->C + c) * 2;
 #pragma unroll
-      for (int i = 0; i < V; ++i)
-        gn[i] = st[2 * i + 1] * (gn[i] - sm[2 * i] * inv_hw - pre[i] * sm[2 * i + 1] * inv_hw);
+      for (int i = 0; i < V; ++i) { st.m1[i] = sm[2 * i] * inv_hw; st.m2[i] = sm[2 * i + 1] * inv_hw; }
+    }
+  }
+  __device__ void operator()(int n, int h, int w, int c, const State& st) const {
+    float ga[V], gn[V], pre[V];
+    this->compute(n, h, w, c, ga, gn, pre, st);
+    if (gres.ptr) store_vec<T, V>(vptr_mut<T>(gres, n, h, w, c), ga);
+    if (this->stats) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) gn[i] = st.rstd[i] * (gn[i] - st.m1[i] - pre[i] * st.m2[i]);
     }
     store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), gn);
   }
@@ -278,8 +322,17 @@ __device__ __forceinline__ void down_taps(int j, int n_in, float scale, int (&po
 }
 
 // UpSample = bilinear x2 then blur.  For output j in [0, 2n): positions base+k, k<4.
+// Interior outputs have the closed form  even j=2m: (.3125,.625,.0625) on x[m-1..m+1],
+// odd j=2m+1: (.0625,.625,.3125); the clamped borders take the general path.
 __device__ __forceinline__ void up_taps(int j, int n_in, int (&pos)[4], float (&wt)[4]) {
   const int n_out = 2 * n_in;
+  if (j >= 2 && j < n_out - 2) {
+    const int m = j >> 1;
+    pos[0] = m - 1; pos[1] = m; pos[2] = m + 1; pos[3] = m + 1;
+    const bool odd = j & 1;
+    wt[0] = odd ? 0.0625f : 0.3125f; wt[1] = 0.625f; wt[2] = odd ? 0.3125f : 0.0625f; wt[3] = 0.f;
+    return;
+  }
   wt[0] = wt[1] = wt[2] = wt[3] = 0.f;
   int jm = max(j - 1, 0);
   float srcm = fmaxf((jm + 0.5f) * 0.5f - 0.5f, 0.f);
@@ -307,17 +360,21 @@ struct DownF {
   const float* stats;
   int act, halo, C;
   float sch, scw;
-  __device__ void operator()(int n, int ho, int wo, int c) const {
+  struct State { float mean[V], rstd[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+    if (stats) {
+      const float* p = stats + ((long long)n * C + c) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { st.mean[i] = p[2 * i]; st.rstd[i] = p[2 * i + 1]; }
+    }
+  }
+  __device__ void operator()(int n, int ho, int wo, int c, const State& st) const {
     int ph[4], pw[4];
     float wh[4], ww[4];
     down_taps(ho, x.h, sch, ph, wh);
     down_taps(wo, x.w, scw, pw, ww);
-    float mean[V], rstd[V];
-    if (stats) {
-      const float* st = stats + ((long long)n * C + c) * 2;
-#pragma unroll
-      for (int i = 0; i < V; ++i) { mean[i] = st[2 * i]; rstd[i] = st[2 * i + 1]; }
-    }
+    const float (&mean)[V] = st.mean;
+    const float (&rstd)[V] = st.rstd;
     float acc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = 0.f;
@@ -343,13 +400,21 @@ struct DownF {
   }
 };
 
-// gather form of the transpose: for input index i, list (j, weight) of outputs touching it
+// gather form of the transpose: for input index i, list (j, weight) of outputs touching it.
+// Output j touches i iff floor(src_j) in [i-2, i+1] (positions i0-1..i0+2, clamped at the ends).
 template <int MAXC>
 __device__ __forceinline__ int down_bwd_taps(int i, int n_in, int n_out, float scale,
                                              int (&js)[MAXC], float (&wj)[MAXC]) {
   int cnt = 0;
-  int lo = max(0, (int)floorf((i - 2.5f) / scale) - 1);
-  int hi = min(n_out - 1, (int)ceilf((i + 1.5f) / scale) + 1);
+  if (n_in == 2 * n_out && i >= 2 && i <= n_in - 3) {  // exact /2: taps (.125,.375,.375,.125)
+    const int m = i >> 1;
+    if (i & 1) { js[0] = m; wj[0] = 0.375f; js[1] = m + 1; wj[1] = 0.125f; }
+    else { js[0] = m - 1; wj[0] = 0.125f; js[1] = m; wj[1] = 0.375f; }
+    return 2;
+  }
+  const float inv = 1.f / scale;
+  int lo = max(0, (int)floorf((i - 1.5f) * inv - 0.5f) - 1);
+  int hi = min(n_out - 1, (int)ceilf((i + 2.5f) * inv - 0.5f) + 1);
   for (int j = lo; j <= hi; ++j) {
     int pos[4];
     float wt[4];
@@ -365,8 +430,14 @@ __device__ __forceinline__ int down_bwd_taps(int i, int n_in, int n_out, float s
 
 template <int MAXC>
 __device__ __forceinline__ int up_bwd_taps(int i, int n_in, int (&js)[MAXC], float (&wj)[MAXC]) {
-  int cnt = 0;
   const int n_out = 2 * n_in;
+  if (i >= 2 && i <= n_in - 3) {  // interior: outputs 2i-2 .. 2i+3
+    const float w6[6] = {0.0625f, 0.3125f, 0.625f, 0.625f, 0.3125f, 0.0625f};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { js[k] = 2 * i - 2 + k; wj[k] = w6[k]; }
+    return 6;
+  }
+  int cnt = 0;
   int lo = max(0, 2 * i - 4), hi = min(n_out - 1, 2 * i + 5);
   for (int j = lo; j <= hi; ++j) {
     int pos[4];
@@ -386,7 +457,9 @@ struct DownBwdF {
   View g, ga;
   int g_halo;
   float sch, scw;
-  __device__ void operator()(int n, int h, int w, int c) const {
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int h, int w, int c, const State&) const {
     int jh[8], jw[8];
     float wh[8], ww[8];
     int nh = down_bwd_taps<8>(h, ga.h, g.h, sch, jh, wh);
@@ -410,7 +483,9 @@ template <typename T, int V>
 struct UpF {
   View x, y;
   int halo;
-  __device__ void operator()(int n, int ho, int wo, int c) const {
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int ho, int wo, int c, const State&) const {
     int ph[4], pw[4];
     float wh[4], ww[4];
     up_taps(ho, x.h, ph, wh);
@@ -439,7 +514,9 @@ template <typename T, int V>
 struct UpBwdF {
   View g, gx;
   int g_halo;
-  __device__ void operator()(int n, int h, int w, int c) const {
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int h, int w, int c, const State&) const {
     int jh[10], jw[10];
     float wh[10], ww[10];
     int nh = up_bwd_taps<10>(h, gx.h, jh, wh);
@@ -467,7 +544,9 @@ struct ModOutF {
   static constexpr int NQ = 1;
   View g, g2, out, res, gy;
   int g_halo, act, C;
-  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V]) const {
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V], const State&) const {
     float ga[V], o[V];
     load_fold<T, V>(g, g_halo, n, h, w, c, ga);
     if (g2.ptr) {
@@ -500,15 +579,19 @@ struct ModInF {
   View g, x, gadd, gx;
   const float* s;
   int g_halo, C;
-  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V]) const {
+  struct State { float s[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) st.s[i] = s[(long long)n * C + c + i];
+  }
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V], const State& st) const {
     float gt[V], xv[V];
     load_fold<T, V>(g, g_halo, n, h, w, c, gt);
     load_vec<T, V>(vptr<T>(x, n, h, w, c), xv);
-    const float* sp = s + (long long)n * C + c;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       acc[0][i] += gt[i] * xv[i];
-      gt[i] *= sp[i];
+      gt[i] *= st.s[i];
     }
     if (gadd.ptr) {
       float t[V];
@@ -527,7 +610,9 @@ struct ChannelSumF {
   View g;
   float scale;
   int per_sample, C;
-  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V]) const {
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V], const State&) const {
     float v[V];
     load_vec<T, V>(vptr<T>(g, n, h, w, c), v);
 #pragma unroll
@@ -542,7 +627,9 @@ struct AvgPoolBwdF {
   const float* g;
   float inv_hw;
   int C;
-  __device__ void operator()(int n, int h, int w, int c) const {
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int h, int w, int c, const State&) const {
     float v[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = g[(long long)n * C + c + i] * inv_hw;
@@ -553,7 +640,9 @@ struct AvgPoolBwdF {
 template <typename TX, typename TY>
 struct CastF {
   View x, y;
-  __device__ void operator()(int n, int h, int w, int c) const {
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int h, int w, int c, const State&) const {
     *vptr_mut<TY>(y, n, h, w, c) = from_f<TY>(to_f(*vptr<TX>(x, n, h, w, c)));
   }
 };
@@ -561,9 +650,11 @@ struct CastF {
 template <typename T, int V>
 struct AddF {
   View dst, src;
-  __device__ void operator()(int n, int h, int w, int c) const {
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int h, int w, int c, const State&) const {
     float a[V], b[V];
-    load_vec<T, V>(vptr<T>(dst, n, h, w, c), a);
+    load_vec_rw<T, V>(vptr<T>(dst, n, h, w, c), a);
     load_vec<T, V>(vptr<T>(src, n, h, w, c), b);
 #pragma unroll
     for (int i = 0; i < V; ++i) a[i] += b[i];
