@@ -102,6 +102,9 @@ typedef struct {
   const float* rs; /* [n, Cout] or NULL */
   const float* cs; /* [n, Cin] or NULL */
   int32_t path;
+  float* ws; /* optional fp32 workspace [kh*kw*Cout*Cin] for the tcgen05 path: split-K partials
+                are reduced there with 128-bit vector reds in GEMM-tile order and then folded
+                into dw by one pass; NULL = reduce straight into dw with scalar reds */
 } otm_conv_wgrad_args;
 int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream);
 int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a);

@@ -65,6 +65,7 @@ class ConvWgradArgs(C.Structure):
         ("rs", C.c_void_p),
         ("cs", C.c_void_p),
         ("path", C.c_int32),
+        ("ws", C.c_void_p),
     ]
 
 

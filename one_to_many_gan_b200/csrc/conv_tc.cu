@@ -165,23 +165,19 @@ constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 // for the 16-byte per-lane stores of a quarter warp).
 template <int BN>
 __device__ __forceinline__ void epilogue_math16(const TcFwdP& p, int n, int oh, int ow, int o,
-                                                bool valid, float (&v)[16], uint8_t* dst) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
-  if (p.row_scale) {
-    const float4* rs = reinterpret_cast<const float4*>(p.row_scale + (long long)n * p.cout + o);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 t = rs[q];
-      v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
-    }
-  }
-  if (p.bias) {
-    const float4* bs = reinterpret_cast<const float4*>(p.bias + o);
+                                                bool valid, float (&v)[16], uint8_t* dst,
+                                                const float* sc /* smem: alpha*row_scale */,
+                                                const float* bi /* smem: bias */) {
+  {
+    const float4* rs = reinterpret_cast<const float4*>(sc);
+    const float4* bs = reinterpret_cast<const float4*>(bi);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float4 t = bs[q];
-      v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+      float4 t = rs[q], u = bs[q];
+      v[4 * q] = fmaf(v[4 * q], t.x, u.x);
+      v[4 * q + 1] = fmaf(v[4 * q + 1], t.y, u.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], t.z, u.z);
+      v[4 * q + 3] = fmaf(v[4 * q + 3], t.w, u.w);
     }
   }
   act_fwd_vec<16>(v, p.act);
@@ -218,6 +214,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* empty = bars + STAGES;
   uint64_t* accum_full = bars + 2 * STAGES;
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 1);
+  float* s_scale = (float*)(bars + 2 * STAGES + 2);  // [BN] alpha * row_scale[n, o0..]
+  float* s_bias = s_scale + BN;                      // [BN]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n = blockIdx.z;
@@ -287,6 +285,12 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const int wq = warp - 4;
+    // stage the per-channel epilogue constants while the main loop runs
+    for (int t = threadIdx.x - 128; t < BN; t += 128) {
+      s_scale[t] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + t] : 1.f);
+      s_bias[t] = p.bias ? p.bias[o0 + t] : 0.f;
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");
     mbar_wait(smem_u32(accum_full), 0);
     tc_fence_after();
     const int m = wq * 32 + lane;
@@ -302,7 +306,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int j = 0; j < BN / 16; ++j) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
-        epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, stage_out + m * PITCH + j * 32);
+        epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, stage_out + m * PITCH + j * 32,
+                            s_scale + j * 16, s_bias + j * 16);
       }
     }
     if (p.debug == 4) {  // experiment: TMEM read-out only, no math, no staging
@@ -349,6 +354,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // ---------------------------------------------------------------------------
 struct TcWgP {
   float* dw;
+  float* ws;  // [tap][M][N] fp32 partial-sum workspace (NULL: scalar reds into dw)
   const float* rs;
   const float* cs;
   float alpha;
@@ -357,6 +363,7 @@ struct TcWgP {
   int x_coord_off;   // x_halo - pad
   int tiles_w, tiles_total, splits;
   int n_tiles_n;     // number of N tiles (grid.y = m_tiles * n_tiles_n)
+  int debug;         // 1: skip the reduction into dw (timing experiments)
 };
 
 constexpr int WG_CHUNK_BYTES = 64 * 128;  // 64 pixels x 64 channels bf16
@@ -459,18 +466,36 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
       float rowf = p.alpha;
       if (p.a_is_x) { if (p.cs) rowf *= p.cs[(long long)n * p.cin + m]; }
       else { if (p.rs) rowf *= p.rs[(long long)n * p.cout + m]; }
+      const int Mtot = p.a_is_x ? p.cin : p.cout, Ntot = p.a_is_x ? p.cout : p.cin;
+      const float* colv = p.a_is_x ? p.rs : p.cs;  // per-sample factor along the N (column) axis
 #pragma unroll 1
       for (int j = 0; j < BN / 16; ++j) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
+        const int nn0 = n0 + j * 16;
+        if (colv) {
+          const float4* cp = reinterpret_cast<const float4*>(colv + (long long)n * Ntot + nn0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int nn = n0 + j * 16 + i;
-          float colf = 1.f;
-          int o, ci;
-          if (p.a_is_x) { ci = m; o = nn; if (p.rs) colf = p.rs[(long long)n * p.cout + o]; }
-          else { o = m; ci = nn; if (p.cs) colf = p.cs[(long long)n * p.cin + ci]; }
-          atomicAdd(p.dw + ((long long)o * p.cin + ci) * taps + tap, v[i] * rowf * colf);
+          for (int q = 0; q < 4; ++q) {
+            float4 t = cp[q];
+            v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= rowf;
+        if (p.debug) continue;
+        if (p.ws) {  // 128-bit vector reds, contiguous along N
+          float4* dst = reinterpret_cast<float4*>(p.ws + ((long long)tap * Mtot + m) * Ntot + nn0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            atomicAdd(dst + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int nn = nn0 + i;
+            const int o = p.a_is_x ? nn : m, ci = p.a_is_x ? m : nn;
+            atomicAdd(p.dw + ((long long)o * p.cin + ci) * taps + tap, v[i]);
+          }
         }
       }
       tc_fence_before();
@@ -561,7 +586,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcFw
                       cudaStream_t st) {
   constexpr int ring = STAGES * (A_STAGE_BYTES + BN * 128);
   constexpr int tile = 128 * (BN * 2 + 16);  // epilogue staging tile aliases the ring
-  constexpr int smem = (ring > tile ? ring : tile) + 1024 + 256;
+  constexpr int smem = (ring > tile ? ring : tile) + 1024 + 256 + 2 * BN * 4;
   auto kern = conv_tc_fwd_kernel<BN, STAGES, OCC>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -615,13 +640,14 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
     if (BN == 128) return launch_fwd<128, 6, 1>(tmA, tmB, p, grid, st);
     return launch_fwd<256, 4, 1>(tmA, tmB, p, grid, st);
   }
-  if (variant == 2) {  // 3 CTAs per SM, 2-deep ring
-    if (BN == 64) return launch_fwd<64, 3, 3>(tmA, tmB, p, grid, st);
-    if (BN == 128) return launch_fwd<128, 2, 3>(tmA, tmB, p, grid, st);
+  if (variant == 3) {  // 2 CTAs per SM, 3/4-deep ring
+    if (BN == 64) return launch_fwd<64, 4, 2>(tmA, tmB, p, grid, st);
+    if (BN == 128) return launch_fwd<128, 3, 2>(tmA, tmB, p, grid, st);
     return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
   }
-  if (BN == 64) return launch_fwd<64, 4, 2>(tmA, tmB, p, grid, st);
-  if (BN == 128) return launch_fwd<128, 3, 2>(tmA, tmB, p, grid, st);
+  // default: 3 CTAs per SM with a 2-deep ring (measured ~10 % faster than 2 x 3-deep)
+  if (BN == 64) return launch_fwd<64, 3, 3>(tmA, tmB, p, grid, st);
+  if (BN == 128) return launch_fwd<128, 2, 3>(tmA, tmB, p, grid, st);
   return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
 }
 
@@ -630,6 +656,21 @@ bool conv_wgrad_tc_eligible(const otm_conv_wgrad_args* a) {
   const int cin = a->x.c, cout = a->dy.c;
   if (cout % 128 != 0 && cin % 128 != 0) return false;
   return true;
+}
+
+// dw[o][c][tap] += ws[tap][m][n]  (m,n = (o,c) or (c,o) in the GEMM's orientation)
+__global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict__ ws, float* dw,
+                                                        int cout, int cin, int taps, int a_is_x) {
+  const long long total = (long long)cout * cin * taps;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(idx % taps);
+    const long long oc = idx / taps;
+    const int ci = (int)(oc % cin), o = (int)(oc / cin);
+    const long long src = a_is_x ? ((long long)tap * cin + ci) * cout + o
+                                 : ((long long)tap * cout + o) * cin + ci;
+    dw[idx] += ws[src];
+  }
 }
 
 template <int BN, int STAGES, int OCC>
@@ -669,6 +710,8 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   if (splits < 1) splits = 1;
   p.splits = splits;
   OTM_REQUIRE((long long)a->dy.n * splits <= 65535, "wgrad_tc: grid.z too large");
+  static const int dbg = [] { const char* e = getenv("OTM_WG_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = dbg;
 
   CUtensorMap tmX, tmDy;
   int rc = make_act_map(&tmX, a->x, a->x_halo, 8, 8);
@@ -678,15 +721,27 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const CUtensorMap& tmA = p.a_is_x ? tmX : tmDy;
   const CUtensorMap& tmB = p.a_is_x ? tmDy : tmX;
   dim3 grid(taps, m_tiles * p.n_tiles_n, a->dy.n * splits);
+  p.ws = a->ws;
+  if (p.ws) OTM_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, sizeof(float) * (size_t)taps * cin * cout, st));
   static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
   if (variant == 1) {
-    if (BN == 64) return launch_wgrad<64, 6, 1>(tmA, tmB, p, grid, st);
-    if (BN == 128) return launch_wgrad<128, 6, 1>(tmA, tmB, p, grid, st);
-    return launch_wgrad<256, 4, 1>(tmA, tmB, p, grid, st);
+    if (BN == 64) rc = launch_wgrad<64, 6, 1>(tmA, tmB, p, grid, st);
+    else if (BN == 128) rc = launch_wgrad<128, 6, 1>(tmA, tmB, p, grid, st);
+    else rc = launch_wgrad<256, 4, 1>(tmA, tmB, p, grid, st);
+  } else {
+    if (BN == 64) rc = launch_wgrad<64, 4, 2>(tmA, tmB, p, grid, st);
+    else if (BN == 128) rc = launch_wgrad<128, 3, 2>(tmA, tmB, p, grid, st);
+    else rc = launch_wgrad<256, 2, 2>(tmA, tmB, p, grid, st);
   }
-  if (BN == 64) return launch_wgrad<64, 4, 2>(tmA, tmB, p, grid, st);
-  if (BN == 128) return launch_wgrad<128, 3, 2>(tmA, tmB, p, grid, st);
-  return launch_wgrad<256, 2, 2>(tmA, tmB, p, grid, st);
+  if (rc) return rc;
+  if (p.ws) {
+    const long long total = (long long)taps * cin * cout;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    wgrad_fold_kernel<<<blocks, 256, 0, st>>>(p.ws, p.dw, cout, cin, taps, p.a_is_x);
+    OTM_LAUNCH_CHECK();
+  }
+  return OTM_OK;
 }
 
 int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st);

@@ -60,7 +60,8 @@ def conv_fwd(x, wpack, cout, kh, kw, pad, *, x_halo=0, y_halo=0, alpha=1.0, row_
     return out
 
 
-def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None, path=PATH_AUTO):
+def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None, path=PATH_AUTO,
+               use_ws=True):
     a = L.ConvWgradArgs()
     a.x = L.tdesc(x)
     a.x_halo = x_halo
@@ -71,6 +72,10 @@ def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None,
     a.rs = L.ptr(rs)
     a.cs = L.ptr(cs)
     a.path = path
+    ws = None
+    if use_ws and L.lib.otm_conv_wgrad_uses_tcgen05(_byref(a)):
+        ws = torch.empty(dw.numel(), dtype=torch.float32, device=dw.device)
+    a.ws = L.ptr(ws)
     L.check(L.lib.otm_conv_wgrad(_byref(a), L.stream_ptr()), "otm_conv_wgrad")
     return dw
 
