@@ -307,9 +307,16 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist_on = world > 1
+    verbose = os.environ.get("OTM_BENCH_VERBOSE", "0") == "1"
+
+    def note(msg):
+        if verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+        note("process group up")
 
     from one_to_many_gan_b200 import kernels as K
     from one_to_many_gan_b200.synthetic import SyntheticImages
@@ -327,9 +334,11 @@ def main():
     l0 = K.launch_count()
     step(prints, marks)
     launches = K.launch_count() - l0
+    note("first eager iteration done")
     ms, last = time_steps(step, prints, marks, args.steps, warmup, dist_on, device)
     clocks = sampler.stop() if sampler else None
     value = world * BATCH * args.steps / (ms / 1e3)
+    note(f"device-resident leg done: {ms / args.steps:.2f} ms/step")
 
     # ---- leg 2: end to end through the public step API with pinned HOST batches -------------
     shape = (BATCH, 1, *IMAGE)

@@ -148,10 +148,14 @@ class TrainIteration:
         first = (torch.arange(nb, device=self.dev) < self.idx_dev[slot]).view(nb, 1, 1)
         return torch.where(first, s1[None], s2[None])
 
-    def _body(self):
-        cfg, B, P = self.cfg, self.B, self.pool_size
-        opt = cfg["optimisation"]
-        # ---- discriminator step (training.py:71-128) ----
+    # The iteration is three device segments with the two data-parallel exchanges between them
+    # (NCCL calls stay outside the captured graphs):
+    #   A: D forward/backward            -> all-reduce(D grads)
+    #   B: Adam(D), G forward/backward   -> all-reduce(G, M, S grads)
+    #   C: Adam(G), Adam(M), Adam(S)
+    def _segment_a(self):
+        B = self.B
+        ops.invalidate_packs()
         self.oD.zero_grad()
         with torch.no_grad():
             w = self._style(0)
@@ -163,8 +167,14 @@ class TrainIteration:
                                   generated.index_select(0, self.idx_dev[o + 2 * B : o + 3 * B]))
         disc_loss, sign_real, sign_fake = training.discriminator_losses(self.D, fake, self.x[1])
         training.backward_unit(disc_loss)
-        self.oD.step()
-        # ---- generator step (training.py:136-257) ----
+        self.losses[0:3].copy_(torch.cat([v.detach().reshape(1).float()
+                                          for v in (disc_loss, sign_real, sign_fake)]))
+
+    def _segment_b(self):
+        cfg, B = self.cfg, self.B
+        opt = cfg["optimisation"]
+        ops.invalidate_packs()
+        self.oD.step(reduced=True)
         self.oG.zero_grad()
         self.oM.zero_grad()
         self.oS.zero_grad()
@@ -186,11 +196,19 @@ class TrainIteration:
         losses = training.generator_losses(cfg, self.G, self.D, self.S, self.x[2], self.x[3],
                                            reconstruct_w, translation_w, w1, w2, h)
         training.backward_unit(losses[0])
-        self.oG.step()
-        self.oM.step()
-        self.oS.step()
-        vals = [disc_loss, sign_real, sign_fake, *losses]
-        self.losses.copy_(torch.cat([v.detach().reshape(1).float() for v in vals]))
+        self.losses[3:].copy_(torch.cat([v.detach().reshape(1).float() for v in losses]))
+
+    def _segment_c(self):
+        self.oG.step(reduced=True)
+        self.oM.step(reduced=True)
+        self.oS.step(reduced=True)
+        ops.invalidate_packs()
+
+    def _exchange(self, opts):
+        for o in opts:
+            o.all_reduce_async()
+        for o in opts:
+            o.wait_all_reduce()
 
     # ---------------------------------------------------------------- driver
     def load_inputs(self, d_prints, d_marks, g_prints, g_marks):
@@ -209,20 +227,30 @@ class TrainIteration:
         self._sample_host(h)
         self.rng_dev.copy_(self.rng_host, non_blocking=True)
         self.idx_dev.copy_(self.idx_host, non_blocking=True)
-        if not self.use_graph:
-            self._body()
-        elif self._warm_left > 0:  # eager warm-up: lazy inits, allocator pools, cuBLAS handles
-            self._warm_left -= 1
-            self._body()
-        elif self.graph is None:
-            torch.cuda.synchronize()
-            ops.invalidate_packs()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._body()
-            self.graph.replay()
+        segs = (self._segment_a, self._segment_b, self._segment_c)
+        exch = ((self.oD,), (self.oG, self.oM, self.oS), ())
+        if not self.use_graph or self._warm_left > 0:
+            # eager (also the warm-up: lazy inits, allocator pools, cuBLAS handles, NCCL comms)
+            self._warm_left = max(0, self._warm_left - 1)
+            for seg, ex in zip(segs, exch):
+                seg()
+                self._exchange(ex)
         else:
-            self.graph.replay()
+            if self.graph is None:
+                torch.cuda.synchronize()
+                self.graph = []
+                pool = torch.cuda.graph_pool_handle()
+                for seg, ex in zip(segs, exch):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        seg()
+                    self.graph.append(g)
+                    g.replay()
+                    self._exchange(ex)
+            else:
+                for g, ex in zip(self.graph, exch):
+                    g.replay()
+                    self._exchange(ex)
         ops.invalidate_packs()  # replays update the weights behind Python's back
         self.iterations += 1
         if not sync_losses:

@@ -90,8 +90,11 @@ class FlatAdam(GradArena):
         self.steps = 0
         ops.invalidate_packs()
 
-    def step(self):
-        self.wait_all_reduce()
+    def step(self, reduced: bool = False):
+        """`reduced=True`: the caller has already completed the gradient all-reduce (the graph
+        engine keeps NCCL outside its captured segments)."""
+        if not reduced:
+            self.wait_all_reduce()
         self.steps += 1
         self.step_dev += 1
         K.adam(self.param_arena, self.grad_arena, self.exp_avg, self.exp_avg_sq, self.step_dev,
@@ -104,7 +107,7 @@ class FlatAdam(GradArena):
         for i, (p, off) in enumerate(zip(self.params, self.offsets)):
             n = p.numel()
             state[i] = {
-                "step": torch.tensor(float(self.steps)),
+                "step": torch.tensor(float(int(self.step_dev.item()))),
                 "exp_avg": self.exp_avg[off : off + n].view_as(p).clone(),
                 "exp_avg_sq": self.exp_avg_sq[off : off + n].view_as(p).clone(),
             }
