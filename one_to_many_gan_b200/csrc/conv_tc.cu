@@ -80,6 +80,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {  // staged smem may be overwritten
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -167,7 +183,8 @@ template <int BN>
 __device__ __forceinline__ void epilogue_math16(const TcFwdP& p, int n, int oh, int ow, int o,
                                                 bool valid, float (&v)[16], uint8_t* dst,
                                                 const float* sc /* smem: alpha*row_scale */,
-                                                const float* bi /* smem: bias */) {
+                                                const float* bi /* smem: bias */,
+                                                uint8_t* dst_hi = nullptr) {
   {
     const float4* rs = reinterpret_cast<const float4*>(sc);
     const float4* bs = reinterpret_cast<const float4*>(bi);
@@ -198,7 +215,7 @@ __device__ __forceinline__ void epilogue_math16(const TcFwdP& p, int n, int oh, 
     h2[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
   }
   *reinterpret_cast<uint4*>(dst) = lo;
-  *reinterpret_cast<uint4*>(dst + 16) = hi;
+  *reinterpret_cast<uint4*>(dst_hi ? dst_hi : dst + 16) = hi;
 }
 
 template <int BN, int STAGES, int OCC>
@@ -214,7 +231,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* empty = bars + STAGES;
   uint64_t* accum_full = bars + 2 * STAGES;
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 1);
-  float* s_scale = (float*)(bars + 2 * STAGES + 2);  // [BN] alpha * row_scale[n, o0..]
+  float* s_scale = (float*)(((uintptr_t)(bars + 2 * STAGES + 2) + 15) & ~(uintptr_t)15);  // [BN]
   float* s_bias = s_scale + BN;                      // [BN]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -346,6 +363,214 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Persistent forward / dgrad kernel: one CTA per SM loops over output tiles; the fp32
+// accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i
+// (TMEM read-out, epilogue math, staged + coalesced write-out) overlaps the TMA/MMA main
+// loop of tile i+1, and barrier init / TMEM allocation / descriptor prefetch happen once.
+// Measured motivation (profiles/r1_epilogue_ablation.md): the main loop alone sustains
+// ~1.05 PFLOP/s on the 128-channel layers, the serialised epilogue brought that to 0.64.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcFwdPP {
+  TcFwdP p;
+  int total_tiles;     // batch * pixel tiles * cout tiles
+  int tiles_per_img;   // pixel tiles per image
+  int cout_tiles;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                           const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmY, TcFwdPP pp) {
+  const TcFwdP& p = pp.p;
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  // staging tile = BN/64 sub-tiles of [128 pixel rows][64 ch = 128 B], 128-byte swizzled: the
+  // layout a SWIZZLE_128B TMA store box {64, TW, TH, 1} reads, conflict-free for the writers
+  constexpr int SUB_BYTES = 128 * 128;
+  constexpr int TILE_BYTES = (BN / 64) * SUB_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_out = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(stage_out + TILE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
+  float* s_scale = (float*)(((uintptr_t)(bars + 2 * STAGES + 5) + 15) & ~(uintptr_t)15);
+  float* s_bias = s_scale + BN;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int cin_chunks = p.cin / 64;
+  const int num_k = p.kh * p.kw * cin_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), 128);  // every epilogue thread arrives
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // tile -> (n, pixel tile, cout tile); cout tile fastest so the A tile is reused from L2
+  auto decode = [&](int t, int& n, int& h0, int& w0, int& o0) {
+    const int ct = t % pp.cout_tiles;
+    const int rest = t / pp.cout_tiles;
+    const int pt = rest % pp.tiles_per_img;
+    n = rest / pp.tiles_per_img;
+    h0 = (pt / p.tiles_w) * p.TH;
+    w0 = (pt % p.tiles_w) * p.TW;
+    o0 = ct * BN;
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    int gi = 0;  // running k-iteration counter across tiles
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int wrow = n * p.w_rows_per_sample + o0;
+      for (int it = 0; it < num_k; ++it, ++gi) {
+        const int stage = gi % STAGES;
+        const uint32_t parity = ((gi / STAGES) & 1) ^ 1;
+        mbar_wait(smem_u32(&empty[stage]), parity);
+        if (lane == 0) {
+          const int tap = it / cin_chunks, cc = it - tap * cin_chunks;
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          const uint32_t bar = smem_u32(&full[stage]);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          mbar_expect_tx(bar, STAGE_BYTES);
+          tma_load_4d(sa, &tmA, bar, cc * 64, w0 + s + p.coord_off, h0 + r + p.coord_off, n);
+          tma_load_2d(sa + A_STAGE_BYTES, &tmB, bar, tap * p.cin + cc * 64, wrow);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    int gi = 0, lt = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      // wait until the epilogue has drained this accumulator buffer (first use: free)
+      mbar_wait(smem_u32(&tmem_empty[buf]), ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+      for (int it = 0; it < num_k; ++it, ++gi) {
+        const int stage = gi % STAGES;
+        const uint32_t parity = (gi / STAGES) & 1;
+        mbar_wait(smem_u32(&full[stage]), parity);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da = make_desc(sa, 16, 1024);
+          const uint64_t db = make_desc(sa + A_STAGE_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                      (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&empty[stage]));
+          if (it == num_k - 1) umma_commit(smem_u32(&tmem_full[buf]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (4 warps, TMEM lane quarter = warp - 4) ----------------
+    const int wq = warp - 4;
+    const int te = threadIdx.x - 128;
+    const int m = wq * 32 + lane;
+    int lt = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int buf = lt & 1;
+      for (int c = te; c < BN; c += 128) {
+        s_scale[c] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + c] : 1.f);
+        s_bias[c] = p.bias ? p.bias[o0 + c] : 0.f;
+      }
+      // the TMA store of the previous tile must have finished READING the staging tile
+      if (te == 0) tma_store_wait_read();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
+      tc_fence_after();
+      const int oh = h0 + m / p.TW, ow = w0 + m % p.TW;
+      const bool valid = (oh < p.y.h) && (ow < p.y.w);
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(wq * 32) << 16);
+      uint8_t* myrow = stage_out + m * 128;
+      const int sw = m & 7;
+      if (p.debug == 2) {  // timing experiment: main loop only
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty[buf]));
+        continue;
+      }
+#pragma unroll 1
+      for (int j = 0; j < BN / 16; ++j) {
+        float v[16];
+        tmem_ld16(tacc + (uint32_t)(j * 16), v);
+        uint8_t* sub = myrow + (j >> 2) * SUB_BYTES;
+        const int c = (j & 3) * 2;
+        epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, sub + ((c ^ sw) << 4),
+                            s_scale + j * 16, s_bias + j * 16, sub + (((c + 1) ^ sw) << 4));
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tmem_empty[buf]));  // accumulator buffer may be overwritten
+      fence_proxy_async();                      // generic-proxy smem writes -> async proxy
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (te == 0 && p.debug != 1) {
+#pragma unroll
+        for (int sb = 0; sb < BN / 64; ++sb)
+          tma_store_4d(&tmY, smem_u32(stage_out + sb * SUB_BYTES), o0 + sb * 64, w0, h0, n);
+        tma_store_commit();
+      }
+      // reflect halo of the consumer conv: only pixels in the border frame have mirror images
+      if (p.y_halo > 0 && valid) {
+        int hs[3], ws[3];
+        const int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
+        const int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
+        if (nh * nw > 1) {
+          for (int piece = 0; piece < BN / 8; ++piece) {
+            const uint4 val = *reinterpret_cast<const uint4*>(
+                myrow + (piece >> 3) * SUB_BYTES + (((piece & 7) ^ sw) << 4));
+            for (int a = 0; a < nh; ++a)
+              for (int b = 0; b < nw; ++b)
+                if (a + b > 0)
+                  *reinterpret_cast<uint4*>(
+                      vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + piece * 8)) = val;
+          }
+        }
+      }
+    }
+    if (te == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -598,6 +823,25 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcFw
   return OTM_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB,
+                              const CUtensorMap& tmY, const TcFwdPP& pp, int ctas,
+                              cudaStream_t st) {
+  constexpr int ring = STAGES * (A_STAGE_BYTES + BN * 128);
+  constexpr int tile = (BN / 64) * 128 * 128;
+  constexpr int smem = ring + tile + 1024 + 256 + 2 * BN * 4;
+  static_assert(smem <= 227 * 1024, "persistent conv kernel exceeds shared memory");
+  auto kern = conv_tc_fwd_persist_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
 int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   const int Ho = a->y.h, Wo = a->y.w, cout = a->y.c, cin = a->x.c;
   // pixel tile shape: 128 = TW x TH, minimise the number of tiles (ties -> squarer)
@@ -645,7 +889,22 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
     if (BN == 128) return launch_fwd<128, 3, 2>(tmA, tmB, p, grid, st);
     return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
   }
-  // default: 3 CTAs per SM with a 2-deep ring (measured ~10 % faster than 2 x 3-deep)
+  if (variant == 0) {  // default: persistent, double-buffered TMEM accumulator
+    TcFwdPP pp;
+    pp.p = p;
+    pp.cout_tiles = cout / BN;
+    pp.tiles_per_img = best_tiles;
+    pp.total_tiles = best_tiles * pp.cout_tiles * a->y.n;
+    int ctas = num_sms();
+    if (ctas > pp.total_tiles) ctas = pp.total_tiles;
+    CUtensorMap tmY;  // interior of y only: the TMA store clips tile tails at the image edge
+    rc = make_act_map(&tmY, a->y, 0, TW, TH);
+    if (rc) return rc;
+    if (BN == 64) return launch_fwd_persist<64, 6>(tmA, tmB, tmY, pp, ctas, st);
+    if (BN == 128) return launch_fwd_persist<128, 5>(tmA, tmB, tmY, pp, ctas, st);
+    return launch_fwd_persist<256, 3>(tmA, tmB, tmY, pp, ctas, st);
+  }
+  // variant 2: 3 CTAs per SM with a 2-deep ring
   if (BN == 64) return launch_fwd<64, 3, 3>(tmA, tmB, p, grid, st);
   if (BN == 128) return launch_fwd<128, 2, 3>(tmA, tmB, p, grid, st);
   return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
