@@ -575,6 +575,211 @@ conv_tc_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA,
 }
 
 // ---------------------------------------------------------------------------
+// Row-reuse variant of the persistent kernel (square KxK filters, K = 3 or 4).
+// The main loop is bound by L2->SM operand traffic (16 KB of A + 16 KB of B per 256 MMA
+// cycles), so the A operand is loaded ONCE per (filter column s, channel chunk) as a
+// (16+K-1) x 8-pixel box and reused for the K filter rows: with an 8-pixel-wide tile one image
+// row of the box is exactly one 1024-byte swizzle atom, so the A descriptor of filter row r is
+// the same box advanced by r*1024 bytes.  A traffic drops K-fold (9 -> 3 boxes of 18 KB per
+// chunk for 3x3).  A and B live in separate rings with their own full/empty barriers.
+// ---------------------------------------------------------------------------
+template <int BN, int KS, int NA, int NB>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_fwd_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmY, TcFwdPP pp) {
+  const TcFwdP& p = pp.p;
+  constexpr int TW = 8, TH = 16;
+  constexpr int A_SLOT = (TH + KS - 1) * TW * 128;  // bytes
+  constexpr int B_SLOT = BN * 128;
+  constexpr int SUB_BYTES = 128 * 128;
+  constexpr int TILE_BYTES = (BN / 64) * SUB_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* ringA = smem;
+  uint8_t* ringB = ringA + NA * A_SLOT;
+  uint8_t* stage_out = ringB + NB * B_SLOT;
+  uint64_t* bars = (uint64_t*)(stage_out + TILE_BYTES);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + NA;
+  uint64_t* fullB = emptyA + NA;
+  uint64_t* emptyB = fullB + NB;
+  uint64_t* tmem_full = emptyB + NB;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+  float* s_scale = (float*)(((uintptr_t)(tmem_ptr + 2) + 15) & ~(uintptr_t)15);
+  float* s_bias = s_scale + BN;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int cin_chunks = p.cin / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(smem_u32(&fullA[i]), 1); mbar_init(smem_u32(&emptyA[i]), 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&fullB[i]), 1); mbar_init(smem_u32(&emptyB[i]), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  auto decode = [&](int t, int& n, int& h0, int& w0, int& o0) {
+    const int ct = t % pp.cout_tiles;
+    const int rest = t / pp.cout_tiles;
+    const int pt = rest % pp.tiles_per_img;
+    n = rest / pp.tiles_per_img;
+    h0 = (pt / p.tiles_w) * TH;
+    w0 = (pt % p.tiles_w) * TW;
+    o0 = ct * BN;
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    int ga = 0, gb = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int wrow = n * p.w_rows_per_sample + o0;
+      for (int cc = 0; cc < cin_chunks; ++cc) {
+        for (int s = 0; s < KS; ++s, ++ga) {
+          const int sa = ga % NA;
+          mbar_wait(smem_u32(&emptyA[sa]), ((ga / NA) & 1) ^ 1);
+          if (lane == 0) {
+            const uint32_t bar = smem_u32(&fullA[sa]);
+            mbar_expect_tx(bar, A_SLOT);
+            tma_load_4d(smem_u32(ringA + sa * A_SLOT), &tmA, bar, cc * 64, w0 + s + p.coord_off,
+                        h0 + p.coord_off, n);
+          }
+          __syncwarp();
+          for (int r = 0; r < KS; ++r, ++gb) {
+            const int sb = gb % NB;
+            mbar_wait(smem_u32(&emptyB[sb]), ((gb / NB) & 1) ^ 1);
+            if (lane == 0) {
+              const uint32_t bar = smem_u32(&fullB[sb]);
+              mbar_expect_tx(bar, B_SLOT);
+              tma_load_2d(smem_u32(ringB + sb * B_SLOT), &tmB, bar, (r * KS + s) * p.cin + cc * 64, wrow);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    int ga = 0, gb = 0, lt = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(smem_u32(&tmem_empty[buf]), ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+      uint32_t first = 1;
+      for (int cc = 0; cc < cin_chunks; ++cc) {
+        for (int s = 0; s < KS; ++s, ++ga) {
+          const int sa = ga % NA;
+          mbar_wait(smem_u32(&fullA[sa]), (ga / NA) & 1);
+          for (int r = 0; r < KS; ++r, ++gb) {
+            const int sb = gb % NB;
+            mbar_wait(smem_u32(&fullB[sb]), (gb / NB) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t da = make_desc(smem_u32(ringA + sa * A_SLOT + r * (TW * 128)), 16, 1024);
+              const uint64_t db = make_desc(smem_u32(ringB + sb * B_SLOT), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(smem_u32(&emptyB[sb]));
+              if (r == KS - 1) umma_commit(smem_u32(&emptyA[sa]));
+              if (r == KS - 1 && s == KS - 1 && cc == cin_chunks - 1)
+                umma_commit(smem_u32(&tmem_full[buf]));
+            }
+            first = 0;
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int wq = warp - 4;
+    const int te = threadIdx.x - 128;
+    const int m = wq * 32 + lane;
+    int lt = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int buf = lt & 1;
+      for (int c = te; c < BN; c += 128) {
+        s_scale[c] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + c] : 1.f);
+        s_bias[c] = p.bias ? p.bias[o0 + c] : 0.f;
+      }
+      if (te == 0) tma_store_wait_read();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
+      tc_fence_after();
+      const int oh = h0 + m / TW, ow = w0 + m % TW;
+      const bool valid = (oh < p.y.h) && (ow < p.y.w);
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(wq * 32) << 16);
+      uint8_t* myrow = stage_out + m * 128;
+      const int sw = m & 7;
+#pragma unroll 1
+      for (int j = 0; j < BN / 16; ++j) {
+        float v[16];
+        tmem_ld16(tacc + (uint32_t)(j * 16), v);
+        uint8_t* sub = myrow + (j >> 2) * SUB_BYTES;
+        const int c = (j & 3) * 2;
+        epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, sub + ((c ^ sw) << 4),
+                            s_scale + j * 16, s_bias + j * 16, sub + (((c + 1) ^ sw) << 4));
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tmem_empty[buf]));
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (te == 0) {
+#pragma unroll
+        for (int sb = 0; sb < BN / 64; ++sb)
+          tma_store_4d(&tmY, smem_u32(stage_out + sb * SUB_BYTES), o0 + sb * 64, w0, h0, n);
+        tma_store_commit();
+      }
+      if (p.y_halo > 0 && valid) {
+        int hs[3], ws[3];
+        const int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
+        const int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
+        if (nh * nw > 1) {
+          for (int piece = 0; piece < BN / 8; ++piece) {
+            const uint4 val = *reinterpret_cast<const uint4*>(
+                myrow + (piece >> 3) * SUB_BYTES + (((piece & 7) ^ sw) << 4));
+            for (int a = 0; a < nh; ++a)
+              for (int b = 0; b < nw; ++b)
+                if (a + b > 0)
+                  *reinterpret_cast<uint4*>(
+                      vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + piece * 8)) = val;
+          }
+        }
+      }
+    }
+    if (te == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // wgrad kernel
 // ---------------------------------------------------------------------------
 struct TcWgP {
@@ -842,6 +1047,23 @@ static int launch_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB,
   return OTM_OK;
 }
 
+template <int BN, int KS, int NA, int NB>
+static int launch_fwd_rr(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                         const TcFwdPP& pp, int ctas, cudaStream_t st) {
+  constexpr int smem = NA * (16 + KS - 1) * 8 * 128 + NB * BN * 128 + (BN / 64) * 128 * 128 + 1024 +
+                       512 + 2 * BN * 4;
+  static_assert(smem <= 227 * 1024, "row-reuse conv kernel exceeds shared memory");
+  auto kern = conv_tc_fwd_rr_kernel<BN, KS, NA, NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
 int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   const int Ho = a->y.h, Wo = a->y.w, cout = a->y.c, cin = a->x.c;
   // pixel tile shape: 128 = TW x TH, minimise the number of tiles (ties -> squarer)
@@ -852,13 +1074,19 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
     int tiles = ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
     if (tiles < best_tiles) { best_tiles = tiles; best_tw = tw; }
   }
+  static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
+  const bool rr = (variant == 0) && a->kh == a->kw && (a->kh == 3 || a->kh == 4);
+  if (rr) {  // row-reuse kernel: fixed 16 x 8 pixel tile
+    best_tw = 8;
+    best_tiles = ((Wo + 7) / 8) * ((Ho + 15) / 16);
+  }
   const int TW = best_tw, TH = 128 / TW;
   int BN = 128;
   if (cout % 128 != 0) BN = 64;
   else if (cout % 256 == 0 && (long long)best_tiles * a->y.n * (cout / 256) >= 2 * num_sms()) BN = 256;
 
   CUtensorMap tmA, tmB;
-  int rc = make_act_map(&tmA, a->x, a->x_halo, TW, TH);
+  int rc = make_act_map(&tmA, a->x, a->x_halo, TW, rr ? TH + a->kh - 1 : TH);
   if (rc) return rc;
   const long long ktot = (long long)a->kh * a->kw * cin;
   const long long rows = (a->w_batch_stride ? (long long)a->x.n : 1) * cout;
@@ -876,9 +1104,8 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   static const int dbg = [] { const char* e = getenv("OTM_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
   dim3 grid(best_tiles, cout / BN, a->y.n);
-  // variant 0 (default): 2 CTAs per SM with a short ring, so one CTA's prologue/epilogue
-  // overlaps the other's MMA main loop; variant 1: 1 CTA per SM with a deep ring.
-  static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
+  // variant 0 (default): persistent kernels (row-reuse for 3x3 / 4x4); 4: persistent without
+  // row reuse; 2/3: 3 or 2 CTAs per SM, one tile per CTA; 1: 1 CTA per SM with a deep ring.
   if (variant == 1) {
     if (BN == 64) return launch_fwd<64, 6, 1>(tmA, tmB, p, grid, st);
     if (BN == 128) return launch_fwd<128, 6, 1>(tmA, tmB, p, grid, st);
@@ -889,7 +1116,7 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
     if (BN == 128) return launch_fwd<128, 3, 2>(tmA, tmB, p, grid, st);
     return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
   }
-  if (variant == 0) {  // default: persistent, double-buffered TMEM accumulator
+  if (variant == 0 || variant == 4) {  // persistent, double-buffered TMEM accumulator
     TcFwdPP pp;
     pp.p = p;
     pp.cout_tiles = cout / BN;
@@ -900,6 +1127,16 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
     CUtensorMap tmY;  // interior of y only: the TMA store clips tile tails at the image edge
     rc = make_act_map(&tmY, a->y, 0, TW, TH);
     if (rc) return rc;
+    if (rr) {
+      if (a->kh == 3) {
+        if (BN == 64) return launch_fwd_rr<64, 3, 4, 12>(tmA, tmB, tmY, pp, ctas, st);
+        if (BN == 128) return launch_fwd_rr<128, 3, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
+        return launch_fwd_rr<256, 3, 3, 3>(tmA, tmB, tmY, pp, ctas, st);
+      }
+      if (BN == 64) return launch_fwd_rr<64, 4, 4, 12>(tmA, tmB, tmY, pp, ctas, st);
+      if (BN == 128) return launch_fwd_rr<128, 4, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
+      return launch_fwd_rr<256, 4, 3, 3>(tmA, tmB, tmY, pp, ctas, st);
+    }
     if (BN == 64) return launch_fwd_persist<64, 6>(tmA, tmB, tmY, pp, ctas, st);
     if (BN == 128) return launch_fwd_persist<128, 5>(tmA, tmB, tmY, pp, ctas, st);
     return launch_fwd_persist<256, 3>(tmA, tmB, tmY, pp, ctas, st);

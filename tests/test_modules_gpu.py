@@ -173,11 +173,17 @@ def test_training_step_matches_oracle_fp32(case):
                     assert e <= max(3 * floors[k], 3 * net_floor, 1e-4), (net, k, e, floors[k], net_floor)
     print(f"[{case}] worst end-to-end gradient error vs fp64 oracle: {worst:.2e}")
     # weights after the optimiser steps (Adam moves every weight by ~lr: sign flips at g~0 only)
+    # Element-wise: Adam moves every weight by ~lr per step whatever the gradient's size, so a
+    # norm-relative test is ill-conditioned for the zero-initialised biases; allow a quarter of
+    # one step of drift (a flipped update direction would be a full 2*lr = 4e-3 off).
+    lr = {"D": 2e-3, "G": 2e-3, "M": 2e-5, "S": 2e-3}
     for net, mod in (("D", D), ("G", G), ("M", M), ("S", S)):
         for k, p in mod.named_parameters():
             if (net, k) in DEAD:
                 continue
-            assert relerr(p, tr64.params[net][k]) < 2e-3, (net, k)
+            want = tr64.params[net][k].float()
+            bad = ((p.detach().cpu() - want).abs() > 2e-3 * want.abs() + 0.25 * lr[net]).float().mean()
+            assert bad.item() < 2e-3, (net, k, bad.item())
 
 
 @pytest.mark.parametrize("case", ["down1"])
