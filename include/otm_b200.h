@@ -105,9 +105,18 @@ typedef struct {
   float* ws; /* optional fp32 workspace [kh*kw*Cout*Cin] for the tcgen05 path: split-K partials
                 are reduced there with 128-bit vector reds in GEMM-tile order and then folded
                 into dw by one pass; NULL = reduce straight into dw with scalar reds */
+  /* Optional fused demodulation-gradient term of the modulated conv:
+   *   P[n,o] += rs[n,o] * sum_{r,s,i} G_n[o,i,r,s] * wfwd[n][o][r][s][i]
+   * where G_n is the un-scaled per-sample weight gradient this kernel already holds in TMEM and
+   * wfwd the per-sample forward pack (alpha*w*cs).  This equals sum_hw dy*y, so the separate
+   * pass over dy and y (otm_mod_out) is not needed.  tcgen05 path with Cout % 128 == 0 only
+   * (otm_conv_wgrad_fuses_P tells); P must be zeroed by the caller. */
+  const void* wfwd;
+  float* P;
 } otm_conv_wgrad_args;
 int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream);
 int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a);
+int otm_conv_wgrad_fuses_P(const otm_conv_wgrad_args* a);
 
 /* Weight staging.  Replaces EqualisedWeight.forward (layers.py:23-24) and the per-sample
  * `weights * s` materialisation (layers.py:152-161).
@@ -236,6 +245,8 @@ typedef struct {
   otm_tensor gadd; /* ptr NULL = none */
   otm_tensor gx;
   float* Q; /* [n, c] zeroed here then accumulated */
+  int32_t relu_mask; /* 1: gx *= (x > 0) -- x is a ReLU output, so this is the ReLU backward of
+                        the producer fused into this pass */
 } otm_mod_in_args;
 int otm_mod_in(const otm_mod_in_args* a, otm_stream stream);
 

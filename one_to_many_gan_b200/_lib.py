@@ -66,6 +66,8 @@ class ConvWgradArgs(C.Structure):
         ("cs", C.c_void_p),
         ("path", C.c_int32),
         ("ws", C.c_void_p),
+        ("wfwd", C.c_void_p),
+        ("P", C.c_void_p),
     ]
 
 
@@ -161,6 +163,7 @@ class ModInArgs(C.Structure):
         ("gadd", Tensor),
         ("gx", Tensor),
         ("Q", C.c_void_p),
+        ("relu_mask", C.c_int32),
     ]
 
 
@@ -190,6 +193,7 @@ SYMBOLS = {
     "otm_conv_fwd_uses_tcgen05": (C.c_int, [_P(ConvFwdArgs)]),
     "otm_conv_wgrad": (C.c_int, [_P(ConvWgradArgs), C.c_void_p]),
     "otm_conv_wgrad_uses_tcgen05": (C.c_int, [_P(ConvWgradArgs)]),
+    "otm_conv_wgrad_fuses_P": (C.c_int, [_P(ConvWgradArgs)]),
     "otm_weight_pack": (C.c_int, [_P(WeightPackArgs), C.c_void_p]),
     "otm_weight_sqsum": (
         C.c_int,

@@ -785,6 +785,8 @@ conv_tc_fwd_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 struct TcWgP {
   float* dw;
   float* ws;  // [tap][M][N] fp32 partial-sum workspace (NULL: scalar reds into dw)
+  const __nv_bfloat16* wfwd;  // per-sample forward pack [n][cout][taps][cin] (fused P term)
+  float* P;                   // [n][cout]
   const float* rs;
   const float* cs;
   float alpha;
@@ -898,11 +900,21 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
       else { if (p.rs) rowf *= p.rs[(long long)n * p.cout + m]; }
       const int Mtot = p.a_is_x ? p.cin : p.cout, Ntot = p.a_is_x ? p.cout : p.cin;
       const float* colv = p.a_is_x ? p.rs : p.cs;  // per-sample factor along the N (column) axis
+      float pacc = 0.f;  // sum_i G[o,i,tap] * wfwd[n][o][tap][i] over this tile's columns
+      const __nv_bfloat16* wrow =
+          p.P ? p.wfwd + (((long long)n * p.cout + m) * taps + tap) * p.cin : nullptr;
 #pragma unroll 1
       for (int j = 0; j < BN / 16; ++j) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
         const int nn0 = n0 + j * 16;
+        if (wrow) {
+          float w0[8], w1[8];
+          load_vec<__nv_bfloat16, 8>(wrow + nn0, w0);
+          load_vec<__nv_bfloat16, 8>(wrow + nn0 + 8, w1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pacc = fmaf(v[i], w0[i], fmaf(v[8 + i], w1[i], pacc));
+        }
         if (colv) {
           const float4* cp = reinterpret_cast<const float4*>(colv + (long long)n * Ntot + nn0);
 #pragma unroll
@@ -927,6 +939,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
             atomicAdd(p.dw + ((long long)o * p.cin + ci) * taps + tap, v[i]);
           }
         }
+      }
+      if (wrow && p.debug == 0) {
+        const float rsv = p.rs ? p.rs[(long long)n * p.cout + m] : 1.f;
+        atomicAdd(p.P + (long long)n * p.cout + m, pacc * rsv);
       }
       tc_fence_before();
     }
@@ -1218,6 +1234,9 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const CUtensorMap& tmB = p.a_is_x ? tmDy : tmX;
   dim3 grid(taps, m_tiles * p.n_tiles_n, a->dy.n * splits);
   p.ws = a->ws;
+  p.wfwd = (const __nv_bfloat16*)a->wfwd;
+  p.P = a->P;
+  if (p.P) OTM_REQUIRE(!p.a_is_x && p.wfwd, "conv_wgrad: fused P needs Cout %% 128 == 0 and wfwd");
   if (p.ws) OTM_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, sizeof(float) * (size_t)taps * cin * cout, st));
   static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
   if (variant == 1) {
@@ -1288,6 +1307,11 @@ int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a) {
   return conv_wgrad_tc_eligible(a) ? 1 : 0;
 }
 
+int otm_conv_wgrad_fuses_P(const otm_conv_wgrad_args* a) {
+  if (!a || a->path == OTM_PATH_SIMT || !conv_wgrad_tc_eligible(a)) return 0;
+  return (a->dy.c % 128 == 0) ? 1 : 0;
+}
+
 int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OTM_REQUIRE(a && a->x.ptr && a->dy.ptr && a->dw, "conv_wgrad: null argument");
@@ -1300,6 +1324,7 @@ int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream) {
   if (a->path == OTM_PATH_TCGEN05 && !tc)
     return fail(OTM_ERR_UNSUPPORTED, "conv_wgrad: tcgen05 path not available for this shape/dtype");
   if (tc && a->path != OTM_PATH_SIMT) return conv_wgrad_tc(a, st);
+  OTM_REQUIRE(!a->P, "conv_wgrad: the fused P term is only available on the tcgen05 path");
   return conv_wgrad_simt(a, st);
 }
 

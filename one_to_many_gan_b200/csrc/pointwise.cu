@@ -578,7 +578,7 @@ struct ModInF {
   static constexpr int NQ = 1;
   View g, x, gadd, gx;
   const float* s;
-  int g_halo, C;
+  int g_halo, C, relu_mask;
   struct State { float s[V]; };
   __device__ void prepare(int n, int c, State& st) const {
 #pragma unroll
@@ -598,6 +598,10 @@ struct ModInF {
       load_vec<T, V>(vptr<T>(gadd, n, h, w, c), t);
 #pragma unroll
       for (int i = 0; i < V; ++i) gt[i] += t[i];
+    }
+    if (relu_mask) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) gt[i] = xv[i] > 0.f ? gt[i] : 0.f;
     }
     store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), gt);
   }
@@ -868,7 +872,7 @@ int otm_mod_in(const otm_mod_in_args* a, otm_stream stream) {
   OTM_DISPATCH_TV(a->x.dtype, vok, {
     ModInF<T, V> f{make_view(a->g), make_view(a->x),
                    a->gadd.ptr ? make_view(a->gadd) : null_view(), make_view(a->gx),
-                   a->s, a->g_halo, C};
+                   a->s, a->g_halo, C, a->relu_mask};
     rc = launch_nc_reduce<V>(f, a->x.n, a->x.h, a->x.w, C, a->Q, st);
   });
   return rc;

@@ -61,7 +61,9 @@ def conv_fwd(x, wpack, cout, kh, kw, pad, *, x_halo=0, y_halo=0, alpha=1.0, row_
 
 
 def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None, path=PATH_AUTO,
-               use_ws=True):
+               use_ws=True, wfwd=None, P=None):
+    """P (zeroed [n, Cout] fp32) + wfwd (per-sample forward pack): also accumulate the
+    demodulation term sum_hw dy*y in the epilogue (check wgrad_fuses_P first)."""
     a = L.ConvWgradArgs()
     a.x = L.tdesc(x)
     a.x_halo = x_halo
@@ -76,8 +78,20 @@ def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None,
     if use_ws and L.lib.otm_conv_wgrad_uses_tcgen05(_byref(a)):
         ws = torch.empty(dw.numel(), dtype=torch.float32, device=dw.device)
     a.ws = L.ptr(ws)
+    a.wfwd = L.ptr(wfwd)
+    a.P = L.ptr(P)
     L.check(L.lib.otm_conv_wgrad(_byref(a), L.stream_ptr()), "otm_conv_wgrad")
     return dw
+
+
+def wgrad_fuses_P(x, dy, kh, kw, pad, x_halo=0) -> bool:
+    a = L.ConvWgradArgs()
+    a.x = L.tdesc(x)
+    a.x_halo = x_halo
+    a.dy = L.tdesc(dy)
+    a.kh, a.kw, a.pad = kh, kw, pad
+    a.path = PATH_AUTO
+    return bool(L.lib.otm_conv_wgrad_fuses_P(_byref(a)))
 
 
 def weight_pack(w, alpha, dtype, *, cs=None, rs=None, nb=1, transpose=False):
@@ -230,7 +244,7 @@ def mod_out(g, out, *, g_halo=0, g2=None, res=None, act=ACT_NONE, materialise=Tr
     return gy, P
 
 
-def mod_in(g, x, s, *, g_halo=0, gadd=None):
+def mod_in(g, x, s, *, g_halo=0, gadd=None, relu_mask=False):
     n, c, h, w = x.shape
     gx = alloc(n, c, h, w, x.dtype, x.device)
     Q = torch.empty((n, c), dtype=torch.float32, device=x.device)
@@ -242,6 +256,7 @@ def mod_in(g, x, s, *, g_halo=0, gadd=None):
     a.gadd = L.tdesc(gadd)
     a.gx = L.tdesc(gx)
     a.Q = L.ptr(Q)
+    a.relu_mask = int(relu_mask)
     L.check(L.lib.otm_mod_in(_byref(a), L.stream_ptr()), "otm_mod_in")
     return gx, Q
 

@@ -260,7 +260,8 @@ def res_block(x, w1, w2, *, y_halo):
 # modulated convolutions (reference layers.py:111-182, dense form SURVEY App. B.2)
 # ---------------------------------------------------------------------------
 def _modconv_fwd(x, s, weight, pad, x_halo, act, residual, y_halo):
-    """y = act(sigma_inv[b,o] * conv(x, cW * s[b,i])) (+ residual).  Returns (y, sigma_inv)."""
+    """y = act(sigma_inv[b,o] * conv(x, cW * s[b,i])) (+ residual).
+    Returns (y, sigma_inv, per-sample forward pack)."""
     n = x.shape[0]
     cout = weight.shape[0]
     c = eq_scale(weight)
@@ -268,21 +269,29 @@ def _modconv_fwd(x, s, weight, pad, x_halo, act, residual, y_halo):
     wp = K.weight_pack(weight.detach(), c, x.dtype, cs=s, nb=n)
     y = K.conv_fwd(x, wp, cout, 3, 3, pad, x_halo=x_halo, y_halo=y_halo, row_scale=sig, act=act,
                    residual=residual, per_sample=True)
-    return y, sig
+    return y, sig, wp
 
 
-def _modconv_bwd(gy, P, x, s, sig, weight, pad, x_halo, gadd, need_x):
-    """gy: gradient w.r.t. the pre-activation conv output; P[b,o] = sum_hw gy*y.
+def _modconv_bwd(gy, P, x, s, sig, weight, pad, x_halo, gadd, need_x, *, wfwd=None,
+                 relu_mask=False):
+    """gy: gradient w.r.t. the pre-activation conv output.  P[b,o] = sum_hw gy*y is either
+    given (computed by an otm_mod_out pass) or, when P is None, produced by the wgrad kernel's
+    epilogue from the per-sample forward pack `wfwd`.  relu_mask: x is a ReLU output and the
+    returned gx is masked by (x > 0), i.e. it is already the gradient of the ReLU's input.
     Returns (gx, ds, dw)."""
     n, cin, h, w = x.shape
     c = eq_scale(weight)
     dw = torch.zeros_like(weight)
-    K.conv_wgrad(x, gy, dw, 3, 3, pad, x_halo=x_halo, alpha=c, rs=sig, cs=s)
+    if P is None:
+        P = torch.zeros((n, weight.shape[0]), dtype=torch.float32, device=x.device)
+        K.conv_wgrad(x, gy, dw, 3, 3, pad, x_halo=x_halo, alpha=c, rs=sig, cs=s, wfwd=wfwd, P=P)
+    else:
+        K.conv_wgrad(x, gy, dw, 3, 3, pad, x_halo=x_halo, alpha=c, rs=sig, cs=s)
     # dgrad with the un-modulated, demodulated weights: gxt = d L / d (s*x)
     wpt = K.weight_pack(weight.detach(), c, gy.dtype, rs=sig, nb=n, transpose=True)
     gxt_p = K.conv_fwd(gy, wpt, cin, 3, 3, 2 - pad + x_halo, per_sample=True)
     gint = gxt_p[:, :, x_halo : x_halo + h, x_halo : x_halo + w] if x_halo else gxt_p
-    gx, Q = K.mod_in(gint, x, s, g_halo=x_halo, gadd=gadd)
+    gx, Q = K.mod_in(gint, x, s, g_halo=x_halo, gadd=gadd, relu_mask=relu_mask)
     ds = K.mod_bwd(weight.detach(), c, s, sig, _sqsum(weight), P, Q, dw)
     return (gx if need_x else None), ds, dw
 
@@ -294,7 +303,7 @@ class ModConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, s, weight, act, y_halo, pad):
         s = s.contiguous().float()
-        y, sig = _modconv_fwd(x, s, weight, pad, 0, act, None, y_halo)
+        y, sig, _ = _modconv_fwd(x, s, weight, pad, 0, act, None, y_halo)
         ctx.act, ctx.pad = act, pad
         ctx.save_for_backward(x, s, weight, sig, y)
         return y
@@ -317,19 +326,37 @@ def mod_conv(x, s, weight, *, act=ACT_RELU, y_halo=0, pad=1):
 
 class ModResBlockFn(torch.autograd.Function):
     """ModulatedResnetBlock (reference blocks.py:36-68):
-    x + modconv2(refl(ReLU(modconv1(refl(x), w))), w); x carries a reflect halo of 1."""
+    x + modconv2(refl(ReLU(modconv1(refl(x), w))), w); x carries a reflect halo of 1.
+
+    Backward on the tcgen05 path needs only TWO HBM passes besides the four GEMMs: the
+    demodulation terms P = sum_hw dy*y come out of the wgrad epilogues, and the ReLU backward
+    of conv1 is a mask inside conv2's input-side pass (otm_mod_in)."""
 
     @staticmethod
     def forward(ctx, x, s1, s2, w1, w2, y_halo):
         s1 = s1.contiguous().float()
         s2 = s2.contiguous().float()
-        h, sig1 = _modconv_fwd(x, s1, w1, 1, 1, ACT_RELU, None, 1)
-        out, sig2 = _modconv_fwd(h, s2, w2, 1, 1, ACT_NONE, x, y_halo)
-        ctx.save_for_backward(x, s1, s2, w1, w2, h, sig1, sig2, out)
+        h, sig1, wp1 = _modconv_fwd(x, s1, w1, 1, 1, ACT_RELU, None, 1)
+        out, sig2, wp2 = _modconv_fwd(h, s2, w2, 1, 1, ACT_NONE, x, y_halo)
+        fused = K.wgrad_fuses_P(x, out, 3, 3, 1, 1)
+        ctx.fused = fused
+        if fused:
+            ctx.save_for_backward(x, s1, s2, w1, w2, h, sig1, sig2, wp1, wp2)
+        else:
+            ctx.save_for_backward(x, s1, s2, w1, w2, h, sig1, sig2, out)
         return out
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.fused:
+            x, s1, s2, w1, w2, h, sig1, sig2, wp1, wp2 = ctx.saved_tensors
+            g = _g(g, x)
+            # conv2 (no activation): gy1 = ReLU'(h) * s2 * fold(dgrad2) comes straight out
+            gy1, ds2, dw2 = _modconv_bwd(g, None, h, s2, sig2, w2, 1, 1, None, True, wfwd=wp2,
+                                         relu_mask=True)
+            gx, ds1, dw1 = _modconv_bwd(gy1, None, x, s1, sig1, w1, 1, 1, g,
+                                        ctx.needs_input_grad[0], wfwd=wp1)
+            return gx, ds1, ds2, dw1, dw2, None
         x, s1, s2, w1, w2, h, sig1, sig2, out = ctx.saved_tensors
         g = _g(g, x)
         # conv2: y2 = out - x, no activation

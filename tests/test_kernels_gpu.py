@@ -201,6 +201,41 @@ def test_wgrad_tc_modulated(K, case):
         assert relerr(dw, ref * 0.25) < 5e-3, (case, path)
 
 
+def test_wgrad_fused_demodulation_term(K):
+    """P[n,o] = sum_hw dy*y produced by the tcgen05 wgrad epilogue from the per-sample forward
+    pack (SURVEY App. B.2 identity) vs the direct reduction; and the ReLU mask of otm_mod_in."""
+    n, c, H, W = 3, 128, 16, 16
+    alpha = 1 / math.sqrt(c * 9)
+    x = rnd(n, c, H, W, seed=70).bfloat16().float()
+    w = rnd(c, c, 3, 3, seed=71)
+    s = rnd(n, c, seed=72) * 0.3 + 1
+    dy = rnd(n, c, H, W, seed=73).bfloat16().float()
+    xt = nhwc(x, torch.bfloat16, 1)
+    q = K.weight_sqsum(w, alpha)
+    sig = K.demod(s, q)
+    wp = K.weight_pack(w, alpha, torch.bfloat16, cs=s, nb=n)
+    assert K.wgrad_fuses_P(xt, nhwc(dy, torch.bfloat16), 3, 3, 1, 1)
+    y = torch.cat([
+        F.conv2d(F.pad(x[i : i + 1], (1,) * 4, mode="reflect"), wp[i].permute(0, 3, 1, 2).float())
+        for i in range(n)
+    ]) * sig[:, :, None, None]
+    P_ref = (dy * y).sum((2, 3))
+    dw = torch.zeros_like(w)
+    P = torch.zeros(n, c, device="cuda")
+    K.conv_wgrad(xt, nhwc(dy, torch.bfloat16), dw, 3, 3, 1, x_halo=1, alpha=alpha, rs=sig, cs=s,
+                 wfwd=wp, P=P)
+    assert relerr(P, P_ref) < 5e-3
+    dw2 = torch.zeros_like(w)
+    K.conv_wgrad(xt, nhwc(dy, torch.bfloat16), dw2, 3, 3, 1, x_halo=1, alpha=alpha, rs=sig, cs=s)
+    assert relerr(dw, dw2) < 1e-5
+    # relu mask fused into the input-side pass
+    g = rnd(n, c, H, W, seed=74).bfloat16().float()
+    xr = F.relu(rnd(n, c, H, W, seed=75)).bfloat16().float()
+    gx, Q = K.mod_in(nhwc(g, torch.bfloat16), nhwc(xr, torch.bfloat16), s, relu_mask=True)
+    assert relerr(gx.float(), g * s[:, :, None, None] * (xr > 0)) < 2e-2
+    assert relerr(Q, (g * xr).sum((2, 3))) < 2e-2
+
+
 def test_modulation_coefficients(K):
     n, cin, cout = 3, 64, 128
     w = rnd(cout, cin, 3, 3, seed=14)
