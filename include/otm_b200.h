@@ -198,6 +198,9 @@ typedef struct {
   otm_tensor gx;
   otm_tensor gres; /* ptr NULL = none */
   float* sums;
+  int32_t g_down; /* 1: g is the gradient w.r.t. DownSample(y) (shape [n,H/2,W/2,c]); the
+                     transposed blur+bilinear stencil is applied on load, so the backward of the
+                     fused otm_down needs no full-resolution intermediate */
 } otm_norm_act_bwd_args;
 int otm_norm_act_bwd(const otm_norm_act_bwd_args* a, otm_stream stream);
 

@@ -128,6 +128,7 @@ class NormActBwdArgs(C.Structure):
         ("gx", Tensor),
         ("gres", Tensor),
         ("sums", C.c_void_p),
+        ("g_down", C.c_int32),
     ]
 
 

@@ -217,12 +217,19 @@ struct NormActF {
   }
 };
 
-// backward: shared recompute of (ga, gn, pre)
-template <typename T, int V>
+template <int MAXC>
+__device__ __forceinline__ int down_bwd_taps(int i, int n_in, int n_out, float scale,
+                                             int (&js)[MAXC], float (&wj)[MAXC]);
+
+// backward: shared recompute of (ga, gn, pre).  DOWN is a compile-time switch so the common
+// instances do not pay the register cost of the stencil-transpose path.
+template <typename T, int V, bool DOWN>
 struct NormActBwdBase {
   View g, g2, x;
   const float* stats;
   int act, g_halo, C;
+  int g_down;       // 1: g is the gradient of DownSample(act(norm(x))) at half resolution and the
+  float sch, scw;   //    transposed blur+bilinear stencil is applied on load (no ga tensor)
   struct State { float mean[V], rstd[V], m1[V], m2[V]; };
   __device__ void prepare_stats(int n, int c, State& st) const {
     if (stats) {
@@ -233,7 +240,24 @@ struct NormActBwdBase {
   }
   __device__ void compute(int n, int h, int w, int c, float (&ga)[V], float (&gn)[V],
                           float (&pre)[V], const State& st) const {
-    load_fold<T, V>(g, g_halo, n, h, w, c, ga);
+    if constexpr (DOWN) {
+      int jh[8], jw[8];
+      float wh[8], ww[8];
+      const int nh = down_bwd_taps<8>(h, x.h, g.h, sch, jh, wh);
+      const int nw = down_bwd_taps<8>(w, x.w, g.w, scw, jw, ww);
+#pragma unroll
+      for (int i = 0; i < V; ++i) ga[i] = 0.f;
+      for (int a = 0; a < nh; ++a)
+        for (int b = 0; b < nw; ++b) {
+          float t[V];
+          load_fold<T, V>(g, g_halo, n, jh[a], jw[b], c, t);
+          const float wgt = wh[a] * ww[b];
+#pragma unroll
+          for (int i = 0; i < V; ++i) ga[i] += wgt * t[i];
+        }
+    } else {
+      load_fold<T, V>(g, g_halo, n, h, w, c, ga);
+    }
     if (g2.ptr) {
       float t[V];
       load_vec<T, V>(vptr<T>(g2, n, h, w, c), t);
@@ -256,10 +280,10 @@ struct NormActBwdBase {
   }
 };
 
-template <typename T, int V>
-struct NormActBwdReduceF : NormActBwdBase<T, V> {
+template <typename T, int V, bool DOWN>
+struct NormActBwdReduceF : NormActBwdBase<T, V, DOWN> {
   static constexpr int NQ = 2;
-  using State = typename NormActBwdBase<T, V>::State;
+  using State = typename NormActBwdBase<T, V, DOWN>::State;
   __device__ void prepare(int n, int c, State& st) const { this->prepare_stats(n, c, st); }
   __device__ void operator()(int n, int h, int w, int c, float (&acc)[2][V], const State& st) const {
     float ga[V], gn[V], pre[V];
@@ -273,12 +297,12 @@ struct NormActBwdReduceF : NormActBwdBase<T, V> {
   __device__ int out_index(int n, int c, int q) const { return (n * this->C + c) * 2 + q; }
 };
 
-template <typename T, int V>
-struct NormActBwdApplyF : NormActBwdBase<T, V> {
+template <typename T, int V, bool DOWN>
+struct NormActBwdApplyF : NormActBwdBase<T, V, DOWN> {
   View gx, gres;
   const float* sums;
   float inv_hw;
-  using State = typename NormActBwdBase<T, V>::State;
+  using State = typename NormActBwdBase<T, V, DOWN>::State;
   __device__ void prepare(int n, int c, State& st) const {
     this->prepare_stats(n, c, st);
     if (this->stats) {
@@ -743,8 +767,14 @@ int otm_norm_act_bwd(const otm_norm_act_bwd_args* a, otm_stream stream) {
   OTM_REQUIRE(a && a->g.ptr && a->gx.ptr, "norm_act_bwd: null tensor");
   // x (the forward input) may be omitted for a pure fold/add pass (no norm, no activation)
   OTM_REQUIRE(a->x.ptr || (a->act == OTM_ACT_NONE && !a->stats), "norm_act_bwd: x required");
-  OTM_REQUIRE(same_shape(a->g, a->gx) && (!a->x.ptr || same_shape(a->gx, a->x)),
-              "norm_act_bwd: shape mismatch");
+  if (a->g_down) {
+    OTM_REQUIRE(a->x.ptr && same_shape(a->gx, a->x) && a->g.n == a->x.n && a->g.c == a->x.c &&
+                    a->g.h == a->x.h / 2 && a->g.w == a->x.w / 2,
+                "norm_act_bwd: g_down needs g of shape [n, H/2, W/2, c]");
+  } else {
+    OTM_REQUIRE(same_shape(a->g, a->gx) && (!a->x.ptr || same_shape(a->gx, a->x)),
+                "norm_act_bwd: shape mismatch");
+  }
   OTM_REQUIRE(a->g.dtype == a->gx.dtype && (!a->x.ptr || a->gx.dtype == a->x.dtype),
               "norm_act_bwd: dtype");
   OTM_REQUIRE(!a->stats || a->sums, "norm_act_bwd: sums workspace required with stats");
@@ -753,24 +783,34 @@ int otm_norm_act_bwd(const otm_norm_act_bwd_args* a, otm_stream stream) {
   int rc = OTM_OK;
   const otm_tensor& sh = a->gx;
   const int C = sh.c;
+#define OTM_NAB_BODY(DOWN)                                                                       \
+  do {                                                                                           \
+    if (a->stats) {                                                                              \
+      NormActBwdReduceF<T, V, DOWN> r;                                                           \
+      r.g = make_view(a->g); r.g2 = a->g2.ptr ? make_view(a->g2) : null_view();                  \
+      r.x = make_view(a->x); r.stats = a->stats; r.act = a->act; r.g_halo = a->g_halo; r.C = C;  \
+      r.g_down = a->g_down; r.sch = sch; r.scw = scw;                                            \
+      rc = launch_nc_reduce<V>(r, sh.n, sh.h, sh.w, C, a->sums, st);                             \
+    }                                                                                            \
+    if (rc == OTM_OK) {                                                                          \
+      NormActBwdApplyF<T, V, DOWN> f;                                                            \
+      f.g = make_view(a->g); f.g2 = a->g2.ptr ? make_view(a->g2) : null_view();                  \
+      f.x = a->x.ptr ? make_view(a->x) : null_view();                                            \
+      f.stats = a->stats; f.act = a->act; f.g_halo = a->g_halo; f.C = C;                         \
+      f.g_down = a->g_down; f.sch = sch; f.scw = scw;                                            \
+      f.gx = make_view(a->gx); f.gres = a->gres.ptr ? make_view(a->gres) : null_view();          \
+      f.sums = a->sums; f.inv_hw = 1.f / (float)(sh.h * sh.w);                                   \
+      rc = launch_ew<V>(f, sh.n, sh.h, sh.w, C, st);                                             \
+    }                                                                                            \
+  } while (0)
+  const float sch = a->g_down ? (float)a->x.h / (float)a->g.h : 1.f;
+  const float scw = a->g_down ? (float)a->x.w / (float)a->g.w : 1.f;
+  if (a->stats) OTM_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * sh.n * C, st));
   OTM_DISPATCH_TV(sh.dtype, vok, {
-    if (a->stats) {
-      OTM_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * sh.n * C, st));
-      NormActBwdReduceF<T, V> r;
-      r.g = make_view(a->g); r.g2 = a->g2.ptr ? make_view(a->g2) : null_view();
-      r.x = make_view(a->x); r.stats = a->stats; r.act = a->act; r.g_halo = a->g_halo; r.C = C;
-      rc = launch_nc_reduce<V>(r, sh.n, sh.h, sh.w, C, a->sums, st);
-    }
-    if (rc == OTM_OK) {
-      NormActBwdApplyF<T, V> f;
-      f.g = make_view(a->g); f.g2 = a->g2.ptr ? make_view(a->g2) : null_view();
-      f.x = a->x.ptr ? make_view(a->x) : null_view();
-      f.stats = a->stats; f.act = a->act; f.g_halo = a->g_halo; f.C = C;
-      f.gx = make_view(a->gx); f.gres = a->gres.ptr ? make_view(a->gres) : null_view();
-      f.sums = a->sums; f.inv_hw = 1.f / (float)(sh.h * sh.w);
-      rc = launch_ew<V>(f, sh.n, sh.h, sh.w, C, st);
-    }
+    if (a->g_down) OTM_NAB_BODY(true);
+    else OTM_NAB_BODY(false);
   });
+#undef OTM_NAB_BODY
   return rc;
 }
 

@@ -169,10 +169,12 @@ def norm_act(x, stats=None, act=ACT_NONE, residual=None, y_halo=0, out=None):
     return out
 
 
-def norm_act_bwd(g, x, stats=None, act=ACT_NONE, *, g_halo=0, g2=None, want_gres=False):
+def norm_act_bwd(g, x, stats=None, act=ACT_NONE, *, g_halo=0, g2=None, want_gres=False,
+                 g_down=False):
     """g: gradient w.r.t. the forward output; if g_halo>0 it is the INTERIOR view of the
-    gradient w.r.t. the reflect-padded output."""
-    n, c, h, w = g.shape
+    gradient w.r.t. the reflect-padded output.  g_down: g is the half-resolution gradient of
+    DownSample(act(norm(x))); the stencil transpose is applied on load."""
+    n, c, h, w = x.shape if g_down else g.shape
     gx = alloc(n, c, h, w, g.dtype, g.device)
     gres = alloc(n, c, h, w, g.dtype, g.device) if want_gres else None
     sums = torch.empty((n, c, 2), dtype=torch.float32, device=g.device) if stats is not None else None
@@ -186,6 +188,7 @@ def norm_act_bwd(g, x, stats=None, act=ACT_NONE, *, g_halo=0, g2=None, want_gres
     a.gx = L.tdesc(gx)
     a.gres = L.tdesc(gres)
     a.sums = L.ptr(sums)
+    a.g_down = int(g_down)
     L.check(L.lib.otm_norm_act_bwd(_byref(a), L.stream_ptr()), "otm_norm_act_bwd")
     return (gx, gres) if want_gres else gx
 

@@ -309,13 +309,18 @@ def test_down_up(K, shape, dtype):
     t.retain_grad()
     y = rp.down_sample(t, kern)
     g = rnd(*y.shape, seed=22).to(dtype).float()
-    (gt_ref,) = torch.autograd.grad(y, t, g)
+    (gt_ref,) = torch.autograd.grad(y, t, g, retain_graph=True)
     xt = nhwc(x.detach(), dtype)
     stats = K.instnorm_stats(xt)
     out = K.down(xt, stats, K.ACT_LRELU)
     assert relerr(out.float(), y.detach()) < TOL[dtype], "down fwd"
     ga = K.down_bwd(nhwc(g, dtype), shape[2:])
     assert relerr(ga.float(), gt_ref) < TOL[dtype], "down bwd"
+    # fused: stencil transpose + activation + instance-norm backward in one call
+    if shape[2] * shape[3] > 4:
+        (gx_ref,) = torch.autograd.grad(y, x, g, retain_graph=True)
+        gx = K.norm_act_bwd(nhwc(g, dtype), xt, stats, K.ACT_LRELU, g_down=True)
+        assert relerr(gx.float(), gx_ref) < TOL[dtype] * 3, "fused down+norm bwd"
     # UpSample
     x2 = rnd(*shape, seed=23).to(dtype).float().requires_grad_(True)
     y2 = rp.up_sample(x2, kern)
