@@ -246,6 +246,14 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
   return v[0];
 }
 
+// Software prefetch into L2 for the streaming passes: a warp has only one or two 16-byte loads
+// in flight per tensor, far too few bytes to cover HBM latency; prefetching the rows a few
+// iterations ahead costs no registers.
+template <typename T>
+__device__ __forceinline__ void prefetch_l2(const View& v, int n, int h, int w, int c) {
+  if (v.ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(vptr<T>(v, n, h, w, c)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -2,6 +2,8 @@
 // blur/bilinear resampling stencils and the modulated-conv side reductions.
 // All kernels use channel-vector (8-wide, 128-bit for bf16) NHWC access when the
 // tensors allow it and fall back to scalar access for C==1 images.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace otm {
@@ -24,6 +26,9 @@ static inline int ew_grid(long long total, int threads) {
 // shift when C/V is a power of two -- the first version spent ~390 instructions per 16-byte
 // vector on 64-bit div/mod and reached only 0.4-1.4 TB/s (profiles/r1_ew_kernels.md).
 // ---------------------------------------------------------------------------
+constexpr int PF_ROWS = 4;   // element-wise passes: prefetch this many image rows ahead
+constexpr int PF_ITERS = 4;  // reductions: prefetch this many loop iterations ahead
+
 template <int V, typename F>
 __global__ void __launch_bounds__(256) ew_kernel(F f, int N, int H, int W, int C, int cv_shift,
                                                  int rows) {
@@ -40,6 +45,11 @@ __global__ void __launch_bounds__(256) ew_kernel(F f, int N, int H, int W, int C
     int cur_n = -1;
     for (int r = r0; r < r1; ++r) {
       const int n = r / H, h = r - n * H;
+      if (r + PF_ROWS < r1) {
+        const int rp = r + PF_ROWS;
+        const int np = rp / H;
+        f.prefetch(np, rp - np * H, w, cv * V);
+      }
       if (n != cur_n) { f.prepare(n, cv * V, st); cur_n = n; }  // per-(n, channel) constants
       f(n, h, w, cv * V, st);
     }
@@ -54,10 +64,12 @@ static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
   int cv_shift = -1;
   if ((CV & (CV - 1)) == 0) { cv_shift = 0; while ((1 << cv_shift) < CV) ++cv_shift; }
   const int nrows = N * H;
-  // enough CTAs for ~8 per SM; at most 4 rows per CTA
-  int rows = nrows / (num_sms() * 8);
+  // enough CTAs for ~8 per SM; a bounded number of rows per CTA
+  static const int rows_cap = [] { const char* e = getenv("OTM_EW_ROWS"); return e ? atoi(e) : 8; }();
+  static const int ctas_per_sm = [] { const char* e = getenv("OTM_EW_CTAS"); return e ? atoi(e) : 8; }();
+  int rows = nrows / (num_sms() * ctas_per_sm);
   if (rows < 1) rows = 1;
-  if (rows > 8) rows = 8;
+  if (rows > rows_cap) rows = rows_cap;
   const int grid = (nrows + rows - 1) / rows;
   ew_kernel<V, F><<<grid, 256, 0, st>>>(f, N, H, W, C, cv_shift, rows);
   OTM_LAUNCH_CHECK();
@@ -95,6 +107,11 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(F f, int H, int W, int C
       f.prepare(n, cv * V, st);
       for (int p = p0 + row; p < p1; p += rows) {
         int h = p / W, w = p - h * W;
+        const int pp = p + PF_ITERS * rows;
+        if (pp < p1) {
+          const int hp = pp / W;
+          f.prefetch(n, hp, pp - hp * W, cv * V);
+        }
         f(n, h, w, cv * V, acc, st);
       }
     }
@@ -151,6 +168,7 @@ static int launch_nc_reduce(F f, int N, int H, int W, int C, float* out, cudaStr
 // needs ~1e-7 relative statistics: a 4e-6 error flips LeakyReLU masks in the 2x4-pixel layers).
 template <typename T, int V>
 struct StatsF {
+  __device__ void prefetch(int, int, int, int) const {}  // pure read reduction: measured slower with prefetch
   static constexpr int NQ = 2;
   View x;
   int C;
@@ -188,6 +206,10 @@ __global__ void stats_finalize_kernel(const float* ws, float* stats, View x, int
 // ---------------------------------------------------------------------------
 template <typename T, int V>
 struct NormActF {
+  __device__ void prefetch(int n, int h, int w, int c) const {
+    prefetch_l2<T>(x, n, h, w, c);
+    prefetch_l2<T>(res, n, h, w, c);
+  }
   View x, res, y;
   const float* stats;
   int act, halo, C;
@@ -225,6 +247,11 @@ __device__ __forceinline__ int down_bwd_taps(int i, int n_in, int n_out, float s
 // instances do not pay the register cost of the stencil-transpose path.
 template <typename T, int V, bool DOWN>
 struct NormActBwdBase {
+  __device__ void prefetch(int n, int h, int w, int c) const {
+    if constexpr (!DOWN) prefetch_l2<T>(g, n, h, w, c);
+    prefetch_l2<T>(g2, n, h, w, c);
+    prefetch_l2<T>(x, n, h, w, c);
+  }
   View g, g2, x;
   const float* stats;
   int act, g_halo, C;
@@ -380,6 +407,7 @@ __device__ __forceinline__ void up_taps(int j, int n_in, int (&pos)[4], float (&
 
 template <typename T, int V>
 struct DownF {
+  __device__ void prefetch(int, int, int, int) const {}
   View x, y;
   const float* stats;
   int act, halo, C;
@@ -478,6 +506,7 @@ __device__ __forceinline__ int up_bwd_taps(int i, int n_in, int (&js)[MAXC], flo
 
 template <typename T, int V>
 struct DownBwdF {
+  __device__ void prefetch(int, int, int, int) const {}
   View g, ga;
   int g_halo;
   float sch, scw;
@@ -505,6 +534,7 @@ struct DownBwdF {
 
 template <typename T, int V>
 struct UpF {
+  __device__ void prefetch(int, int, int, int) const {}
   View x, y;
   int halo;
   struct State {};
@@ -536,6 +566,7 @@ struct UpF {
 
 template <typename T, int V>
 struct UpBwdF {
+  __device__ void prefetch(int, int, int, int) const {}
   View g, gx;
   int g_halo;
   struct State {};
@@ -565,6 +596,12 @@ struct UpBwdF {
 // ---------------------------------------------------------------------------
 template <typename T, int V>
 struct ModOutF {
+  __device__ void prefetch(int n, int h, int w, int c) const {
+    prefetch_l2<T>(g, n, h, w, c);
+    prefetch_l2<T>(g2, n, h, w, c);
+    prefetch_l2<T>(out, n, h, w, c);
+    prefetch_l2<T>(res, n, h, w, c);
+  }
   static constexpr int NQ = 1;
   View g, g2, out, res, gy;
   int g_halo, act, C;
@@ -599,6 +636,11 @@ struct ModOutF {
 
 template <typename T, int V>
 struct ModInF {
+  __device__ void prefetch(int n, int h, int w, int c) const {
+    prefetch_l2<T>(g, n, h, w, c);
+    prefetch_l2<T>(x, n, h, w, c);
+    prefetch_l2<T>(gadd, n, h, w, c);
+  }
   static constexpr int NQ = 1;
   View g, x, gadd, gx;
   const float* s;
@@ -634,6 +676,7 @@ struct ModInF {
 
 template <typename T, int V>
 struct ChannelSumF {
+  __device__ void prefetch(int, int, int, int) const {}
   static constexpr int NQ = 1;
   View g;
   float scale;
@@ -651,6 +694,7 @@ struct ChannelSumF {
 
 template <typename T, int V>
 struct AvgPoolBwdF {
+  __device__ void prefetch(int, int, int, int) const {}
   View gx;
   const float* g;
   float inv_hw;
@@ -667,6 +711,7 @@ struct AvgPoolBwdF {
 
 template <typename TX, typename TY>
 struct CastF {
+  __device__ void prefetch(int, int, int, int) const {}
   View x, y;
   struct State {};
   __device__ void prepare(int, int, State&) const {}
@@ -677,6 +722,7 @@ struct CastF {
 
 template <typename T, int V>
 struct AddF {
+  __device__ void prefetch(int, int, int, int) const {}
   View dst, src;
   struct State {};
   __device__ void prepare(int, int, State&) const {}
