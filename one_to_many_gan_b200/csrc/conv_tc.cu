@@ -141,6 +141,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 columns per instruction: halves the number of (serialising) TMEM round trips of the epilogue
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
                                               uint32_t sbo_bytes) {
@@ -780,6 +798,229 @@ conv_tc_fwd_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------
+// Pair variant of the row-reuse kernel: one CTA works on TWO vertically adjacent 16x8 pixel
+// tiles at once (two fp32 accumulators in TMEM, double-buffered: 4*BN columns), so every B
+// (weight) tile fetched from L2 feeds two MMAs.  Operand traffic per 2 tiles and 64-channel
+// chunk: 6 A boxes (108 KB) + 9 B tiles (144 KB) instead of 2 x (54 + 144) KB.
+// ---------------------------------------------------------------------------
+template <int BN, int KS, int NA, int NB>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmY, TcFwdPP pp) {
+  const TcFwdP& p = pp.p;
+  constexpr int TW = 8, TH = 16;
+  constexpr int A_BOX = (TH + KS - 1) * TW * 128;  // bytes, one pixel tile
+  constexpr int A_SLOT = 2 * A_BOX;                // the pair of vertically adjacent tiles
+  constexpr int B_SLOT = BN * 128;
+  constexpr int SUB_BYTES = 128 * 128;
+  constexpr int TILE_BYTES = (BN / 64) * SUB_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* ringA = smem;
+  uint8_t* ringB = ringA + NA * A_SLOT;
+  uint8_t* stage_out = ringB + NB * B_SLOT;
+  uint64_t* bars = (uint64_t*)(stage_out + TILE_BYTES);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + NA;
+  uint64_t* fullB = emptyA + NA;
+  uint64_t* emptyB = fullB + NB;
+  uint64_t* tmem_full = emptyB + NB;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+  float* s_scale = (float*)(((uintptr_t)(tmem_ptr + 2) + 15) & ~(uintptr_t)15);
+  float* s_bias = s_scale + BN;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int cin_chunks = p.cin / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(smem_u32(&fullA[i]), 1); mbar_init(smem_u32(&emptyA[i]), 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&fullB[i]), 1); mbar_init(smem_u32(&emptyB[i]), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<4 * BN>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  auto decode = [&](int t, int& n, int& h0, int& w0, int& o0) {
+    const int ct = t % pp.cout_tiles;
+    const int rest = t / pp.cout_tiles;
+    const int pt = rest % pp.tiles_per_img;
+    n = rest / pp.tiles_per_img;
+    h0 = (pt / p.tiles_w) * (2 * TH);  // pt indexes PAIRS of tile rows
+    w0 = (pt % p.tiles_w) * TW;
+    o0 = ct * BN;
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    int ga = 0, gb = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int wrow = n * p.w_rows_per_sample + o0;
+      for (int cc = 0; cc < cin_chunks; ++cc) {
+        for (int s = 0; s < KS; ++s, ++ga) {
+          const int sa = ga % NA;
+          mbar_wait(smem_u32(&emptyA[sa]), ((ga / NA) & 1) ^ 1);
+          if (lane == 0) {
+            const uint32_t bar = smem_u32(&fullA[sa]);
+            mbar_expect_tx(bar, A_SLOT);
+            tma_load_4d(smem_u32(ringA + sa * A_SLOT), &tmA, bar, cc * 64, w0 + s + p.coord_off,
+                        h0 + p.coord_off, n);
+            tma_load_4d(smem_u32(ringA + sa * A_SLOT + A_BOX), &tmA, bar, cc * 64,
+                        w0 + s + p.coord_off, h0 + TH + p.coord_off, n);
+          }
+          __syncwarp();
+          for (int r = 0; r < KS; ++r, ++gb) {
+            const int sb = gb % NB;
+            mbar_wait(smem_u32(&emptyB[sb]), ((gb / NB) & 1) ^ 1);
+            if (lane == 0) {
+              const uint32_t bar = smem_u32(&fullB[sb]);
+              mbar_expect_tx(bar, B_SLOT);
+              tma_load_2d(smem_u32(ringB + sb * B_SLOT), &tmB, bar, (r * KS + s) * p.cin + cc * 64, wrow);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    int ga = 0, gb = 0, lt = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(smem_u32(&tmem_empty[buf]), ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * 2 * BN);  // [tile0 | tile1]
+      uint32_t first = 1;
+      for (int cc = 0; cc < cin_chunks; ++cc) {
+        for (int s = 0; s < KS; ++s, ++ga) {
+          const int sa = ga % NA;
+          mbar_wait(smem_u32(&fullA[sa]), (ga / NA) & 1);
+          for (int r = 0; r < KS; ++r, ++gb) {
+            const int sb = gb % NB;
+            mbar_wait(smem_u32(&fullB[sb]), (gb / NB) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t da0 = make_desc(smem_u32(ringA + sa * A_SLOT + r * (TW * 128)), 16, 1024);
+              const uint64_t da1 =
+                  make_desc(smem_u32(ringA + sa * A_SLOT + A_BOX + r * (TW * 128)), 16, 1024);
+              const uint64_t db = make_desc(smem_u32(ringB + sb * B_SLOT), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // the B tile is read once for both pixel tiles
+                umma_bf16(tacc, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                umma_bf16(tacc + BN, da1 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                          first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(smem_u32(&emptyB[sb]));
+              if (r == KS - 1) umma_commit(smem_u32(&emptyA[sa]));
+              if (r == KS - 1 && s == KS - 1 && cc == cin_chunks - 1)
+                umma_commit(smem_u32(&tmem_full[buf]));
+            }
+            first = 0;
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int wq = warp - 4;
+    const int te = threadIdx.x - 128;
+    const int m = wq * 32 + lane;
+    int lt = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int buf = lt & 1;
+      for (int c = te; c < BN; c += 128) {
+        s_scale[c] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + c] : 1.f);
+        s_bias[c] = p.bias ? p.bias[o0 + c] : 0.f;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // s_scale / s_bias visible
+      mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
+      tc_fence_after();
+      uint8_t* myrow = stage_out + m * 128;
+      const int sw = m & 7;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int hh0 = h0 + half * TH;
+        const int oh = hh0 + m / TW, ow = w0 + m % TW;
+        const bool valid = (oh < p.y.h) && (ow < p.y.w);
+        const uint32_t tacc =
+            tmem_base + (uint32_t)(buf * 2 * BN + half * BN) + ((uint32_t)(wq * 32) << 16);
+        // the previous TMA store must have finished reading the staging tile
+        if (te == 0) tma_store_wait_read();
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+#pragma unroll 1
+        for (int j2 = 0; j2 < BN / 32; ++j2) {
+          float v32[32];
+          tmem_ld32(tacc + (uint32_t)(j2 * 32), v32);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int j = j2 * 2 + q;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v32[q * 16 + i];
+            uint8_t* sub = myrow + (j >> 2) * SUB_BYTES;
+            const int c = (j & 3) * 2;
+            epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, sub + ((c ^ sw) << 4),
+                                s_scale + j * 16, s_bias + j * 16, sub + (((c + 1) ^ sw) << 4));
+          }
+        }
+        tc_fence_before();
+        if (half == 1) mbar_arrive(smem_u32(&tmem_empty[buf]));  // both accumulators drained
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (te == 0 && hh0 < p.y.h) {
+#pragma unroll
+          for (int sb = 0; sb < BN / 64; ++sb)
+            tma_store_4d(&tmY, smem_u32(stage_out + sb * SUB_BYTES), o0 + sb * 64, w0, hh0, n);
+          tma_store_commit();
+        }
+        if (p.y_halo > 0 && valid) {
+          int hs[3], ws[3];
+          const int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
+          const int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
+          if (nh * nw > 1) {
+            for (int piece = 0; piece < BN / 8; ++piece) {
+              const uint4 val = *reinterpret_cast<const uint4*>(
+                  myrow + (piece >> 3) * SUB_BYTES + (((piece & 7) ^ sw) << 4));
+              for (int a = 0; a < nh; ++a)
+                for (int b = 0; b < nw; ++b)
+                  if (a + b > 0)
+                    *reinterpret_cast<uint4*>(
+                        vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + piece * 8)) = val;
+            }
+          }
+        }
+      }
+    }
+    if (te == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<4 * BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // wgrad kernel
 // ---------------------------------------------------------------------------
 struct TcWgP {
@@ -1080,6 +1321,24 @@ static int launch_fwd_rr(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   return OTM_OK;
 }
 
+template <int BN, int KS, int NA, int NB>
+static int launch_fwd_rr2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                          const TcFwdPP& pp, int ctas, cudaStream_t st) {
+  constexpr int smem = NA * 2 * (16 + KS - 1) * 8 * 128 + NB * BN * 128 + (BN / 64) * 128 * 128 +
+                       1024 + 512 + 2 * BN * 4;
+  static_assert(smem <= 227 * 1024, "pair conv kernel exceeds shared memory");
+  static_assert(4 * BN <= 512, "pair conv kernel exceeds TMEM");
+  auto kern = conv_tc_fwd_rr2_kernel<BN, KS, NA, NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
 int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   const int Ho = a->y.h, Wo = a->y.w, cout = a->y.c, cin = a->x.c;
   // pixel tile shape: 128 = TW x TH, minimise the number of tiles (ties -> squarer)
@@ -1143,6 +1402,20 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
     CUtensorMap tmY;  // interior of y only: the TMA store clips tile tails at the image edge
     rc = make_act_map(&tmY, a->y, 0, TW, TH);
     if (rc) return rc;
+    // pair kernel: two tile rows per CTA when there are enough pairs to fill the SMs
+    const int tile_rows = (Ho + 15) / 16, tiles_w8 = (Wo + 7) / 8;
+    const long long pairs = (long long)((tile_rows + 1) / 2) * tiles_w8 * pp.cout_tiles * a->y.n;
+    if (rr && variant == 0 && BN <= 128 && pairs >= 2LL * num_sms()) {
+      pp.tiles_per_img = ((tile_rows + 1) / 2) * tiles_w8;
+      pp.total_tiles = (int)pairs;
+      int c2 = num_sms();
+      if (a->kh == 3) {
+        if (BN == 64) return launch_fwd_rr2<64, 3, 3, 8>(tmA, tmB, tmY, pp, c2, st);
+        return launch_fwd_rr2<128, 3, 2, 6>(tmA, tmB, tmY, pp, c2, st);
+      }
+      if (BN == 64) return launch_fwd_rr2<64, 4, 3, 8>(tmA, tmB, tmY, pp, c2, st);
+      return launch_fwd_rr2<128, 4, 2, 6>(tmA, tmB, tmY, pp, c2, st);
+    }
     if (rr) {
       if (a->kh == 3) {
         if (BN == 64) return launch_fwd_rr<64, 3, 4, 12>(tmA, tmB, tmY, pp, ctas, st);

@@ -22,3 +22,11 @@ def run(fn):
 t1 = run(lambda: K.conv_fwd(x, wp, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, act=K.ACT_RELU, per_sample=True, out=y))
 t2 = run(lambda: K.conv_fwd(x, wp1, c, 3, 3, 1, x_halo=1, y_halo=0, out=y))
 print(f"modulated+halo: {t1*1e3:.1f} us {flops/t1/1e9:.0f} TF/s | shared plain: {t2*1e3:.1f} us {flops/t2/1e9:.0f} TF/s")
+for name, kw, wpk in [
+    ("per-sample only", dict(per_sample=True), wp),
+    ("per-sample+scale", dict(per_sample=True, row_scale=sig), wp),
+    ("per-sample+scale+relu", dict(per_sample=True, row_scale=sig, act=K.ACT_RELU), wp),
+    ("shared+halo", dict(y_halo=1), wp1),
+]:
+    t = run(lambda: K.conv_fwd(x, wpk, c, 3, 3, 1, x_halo=1, out=y, **kw))
+    print(f"  {name}: {t*1e3:.1f} us {flops/t/1e9:.0f} TF/s")
