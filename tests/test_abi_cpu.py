@@ -14,7 +14,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def _declared():
     text = (ROOT / "include" / "otm_b200.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(otm_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(otm_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
