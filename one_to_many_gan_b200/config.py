@@ -11,7 +11,8 @@ import torch
 
 # new, optional keys (default = reference behaviour)
 DEFAULTS = {
-    "training": {"backend": "b200", "precision": "fp32", "synthetic_data": False},
+    "training": {"backend": "b200", "precision": "fp32", "synthetic_data": False,
+                 "styles_per_input": 1},
     "architecture": {"start_filters": 64},
 }
 

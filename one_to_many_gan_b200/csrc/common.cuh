@@ -210,6 +210,15 @@ __device__ __forceinline__ void load_fold(const View& g, int halo, int n, int h,
 // Activations are applied to whole register vectors with ONE (warp-uniform) branch per vector:
 // a per-element `switch` inlines tanhf() at every call site, which bloated the tcgen05 epilogue
 // past the instruction cache and cost ~100 us per launch (profiles/r1_epilogue_ablation.md).
+// tanh as two MUFU ops (ex2 + rcp), fully unrollable: tanhf() is ~40 instructions with branches,
+// and keeping it in a rolled loop indexes the value array dynamically, which moved the array of
+// EVERY activation path to local memory (STL/LDL round trips in the tcgen05 epilogue).
+// |error| <= ~2e-7 absolute.
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float ax = fabsf(x);
+  const float e = __expf(-2.f * ax);
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
 template <int V>
 __device__ __forceinline__ void act_fwd_vec(float (&v)[V], int act) {
   if (act == OTM_ACT_RELU) {
@@ -219,8 +228,8 @@ __device__ __forceinline__ void act_fwd_vec(float (&v)[V], int act) {
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
   } else if (act == OTM_ACT_TANH) {
-#pragma unroll 1
-    for (int i = 0; i < V; ++i) v[i] = tanhf(v[i]);
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = tanh_fast(v[i]);
   }
 }
 // g[i] *= act'(pre[i])  (derivative given the PRE-activation value)
@@ -233,9 +242,9 @@ __device__ __forceinline__ void act_bwd_vec(float (&g)[V], const float (&pre)[V]
 #pragma unroll
     for (int i = 0; i < V; ++i) g[i] = pre[i] > 0.f ? g[i] : 0.2f * g[i];
   } else if (act == OTM_ACT_TANH) {
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < V; ++i) {
-      float t = tanhf(pre[i]);
+      float t = tanh_fast(pre[i]);
       g[i] *= 1.f - t * t;
     }
   }

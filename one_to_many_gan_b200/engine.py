@@ -80,10 +80,17 @@ class TrainIteration:
         size = config["data"]["image_size"]
         ch = config["data"].get("image_channels", 1)
         B, wd = self.B, self.wd
+        # styles per input (BASELINE config 4): the G step's sampled-style passes run at B*K
+        self.K = training.styles_per_input(config)
+        BK = B * self.K
         # static inputs: [d_prints, d_marks, g_prints, g_marks]
         self.x = torch.zeros(4, B, ch, size[0], size[1], device=self.dev)
-        # host-drawn randomness: 3 style draws x (z1, z2) + theta (+ optional injected h)
-        self.n_rng = 3 * 2 * B * wd + 2 * B
+        # host-drawn randomness: 3 style draws x (z1, z2) -- slot 0 (D step) at batch B, slots
+        # 1-2 (G step) at batch B*K -- then theta and the optional injected h (B*K each)
+        self.style_batch = (B, BK, BK)
+        self.style_base = (0, 2 * B * wd, 2 * B * wd + 2 * BK * wd)
+        self.theta_base = 2 * B * wd + 4 * BK * wd
+        self.n_rng = self.theta_base + 2 * BK
         self.rng_host = torch.zeros(self.n_rng, dtype=torch.float32).pin_memory()
         self.rng_dev = torch.zeros(self.n_rng, dtype=torch.float32, device=self.dev)
         # integer controls: 3 crossovers, B pool sources, B pool destinations, B stored images
@@ -106,8 +113,8 @@ class TrainIteration:
     # ---------------------------------------------------------------- host part
     def _draw_style(self, slot: int):
         """builder.py:106-132 draw order: rand(()), [randint, randn, randn] | [randn]."""
-        B, wd = self.B, self.wd
-        base = slot * 2 * B * wd
+        B, wd = self.style_batch[slot], self.wd
+        base = self.style_base[slot]
         if torch.rand(()).lt(self.mix_p):
             cross = int(torch.randint(0, self.nb, ()))
             z1 = torch.randn(B, wd)
@@ -128,20 +135,20 @@ class TrainIteration:
         self.idx_host[o + 2 * B : o + 3 * B] = torch.tensor(sto)
 
     def _sample_host(self, h):
-        B, wd = self.B, self.wd
+        BK = self.B * self.K
         self._draw_style(0)              # D step: get_single_w(d=1)
         self._pool_decisions()           # ImageBuffer
         self._draw_style(1)              # G step: translation w
-        tbase = 3 * 2 * B * wd
-        self.rng_host[tbase : tbase + B] = torch.rand(B)  # theta
+        tbase = self.theta_base
+        self.rng_host[tbase : tbase + BK] = torch.rand(BK)  # theta
         if h is not None:
-            self.rng_host[tbase + B : tbase + 2 * B] = h.float().cpu()
+            self.rng_host[tbase + BK : tbase + 2 * BK] = h.float().cpu()
         self._draw_style(2)              # G step: get_two_w
 
     # ---------------------------------------------------------------- device part
     def _style(self, slot: int):
-        B, wd, nb = self.B, self.wd, self.nb
-        base = slot * 2 * B * wd
+        B, wd, nb = self.style_batch[slot], self.wd, self.nb
+        base = self.style_base[slot]
         z1 = self.rng_dev[base : base + B * wd].view(B, wd)
         z2 = self.rng_dev[base + B * wd : base + 2 * B * wd].view(B, wd)
         s1, s2 = self.M(z1), self.M(z2)
@@ -181,13 +188,14 @@ class TrainIteration:
         zero = self.M.shoeprint_style_vector
         reconstruct_w = zero.expand(self.nb, B, self.wd)
         translation_w = self._style(1)
-        tbase = 3 * 2 * B * self.wd
-        theta = self.rng_dev[tbase : tbase + B]
+        BK = B * self.K
+        tbase = self.theta_base
+        theta = self.rng_dev[tbase : tbase + BK]
         if self.inject_h:
-            h = self.rng_dev[tbase + B : tbase + 2 * B]
+            h = self.rng_dev[tbase + BK : tbase + 2 * BK]
         else:
             lo, hi = opt["path_loss_jacobian_granularity"]
-            h = torch.empty(B, device=self.dev).uniform_(lo, hi)
+            h = torch.empty(BK, device=self.dev).uniform_(lo, hi)
         d1 = (theta + h / 2).clamp(0, 1)
         d2 = (theta - h / 2).clamp(0, 1)
         s = self._style(2)

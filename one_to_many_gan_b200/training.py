@@ -134,13 +134,31 @@ def discriminator_losses(discriminator, fake, real):
     return real_loss + fake_loss, sign_real, -sign_fake
 
 
+def styles_per_input(config) -> int:
+    """`[training] styles_per_input = K` (not a reference key; default 1 = the reference):
+    BASELINE config 4, one input -> K sampled outputs per step."""
+    k = int(config["training"].get("styles_per_input", 1))
+    if k < 1:
+        raise ValueError("styles_per_input must be >= 1")
+    return k
+
+
 def generator_losses(config, generator, discriminator, style_extractor, prints, marks,
                      reconstruct_w, translation_w, w1, w2, cent_fin_diff_h, ada=None):
     """(reference training.py:158-243) all generator-side losses with their lambdas folded in.
-    Returns (total, gan, rec, idt, kl, path, style): WEIGHTED 1-element tensors."""
+    Returns (total, gan, rec, idt, kl, path, style): WEIGHTED 1-element tensors.
+
+    With K = translation_w.shape[1] / B > 1 styles per input, every sampled-style pass
+    (translation decode, D and S on the translations, both path-length extractions) runs on the
+    shoeprint latents broadcast to K styles (image (b, k) at index b*K + k, the
+    `latent.expand(K, ...)` of evaluation.py:172-177); the latent gradient is the sum over the
+    K decodes.  Reconstruction (w = 0) and identity stay at B."""
     opt = config["optimisation"]
     batch = prints.shape[0]
     nb = generator.n_style_blocks
+    n_sty = translation_w.shape[1] // batch
+    if translation_w.shape[1] != batch * n_sty or w1.shape[1] != batch * n_sty:
+        raise ValueError("style batch must be a multiple of the image batch")
     combined_latents = generator.encode(torch.cat([prints, marks], dim=0))
     kl_loss = ops.kl(combined_latents, opt["kl_loss_lambda"])
     if config["architecture"]["add_latent_noise"]:
@@ -151,7 +169,9 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     identity_w = real_shoemark_w.expand(nb, *real_shoemark_w.shape)
 
     # reconstruction / identity / translation as one 3B decode
-    dec_latents = torch.cat([shoeprint_latent, shoemark_latent, shoeprint_latent], dim=0)
+    shoeprint_latent_k = (shoeprint_latent if n_sty == 1
+                          else shoeprint_latent.repeat_interleave(n_sty, dim=0))
+    dec_latents = torch.cat([shoeprint_latent, shoemark_latent, shoeprint_latent_k], dim=0)
     dec_w = torch.cat([reconstruct_w, identity_w, translation_w], dim=1)
     images = generator.decode(dec_latents, dec_w)
     reconstruction_loss = ops.l1(images[:batch], prints, opt["reconstruction_loss_lambda"])
@@ -176,7 +196,7 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     ).reshape(1)
 
     # path length: two extractions of the same latent as one 2B batch
-    feats = generator.extract(torch.cat([shoeprint_latent, shoeprint_latent], dim=0),
+    feats = generator.extract(torch.cat([shoeprint_latent_k, shoeprint_latent_k], dim=0),
                               torch.cat([w1, w2], dim=1))
     path_loss = ops.path(feats, cent_fin_diff_h, opt["path_loss_lambda"])
 
@@ -276,10 +296,11 @@ def generator_step(
     reconstruct_w = mapping_network.get_single_w(
         batch_size=batch, n_gen_blocks=nb, device=device, domain_variable=0
     )
+    style_batch = batch * styles_per_input(config)
     translation_w = mapping_network.get_single_w(
-        batch_size=batch, n_gen_blocks=nb, device=device, domain_variable=1
+        batch_size=style_batch, n_gen_blocks=nb, device=device, domain_variable=1
     )
-    theta = torch.rand(batch).to(device)
+    theta = torch.rand(style_batch).to(device)
     if cent_fin_diff_h is None:
         lo, hi = opt["path_loss_jacobian_granularity"]
         cent_fin_diff_h = torch.ones_like(theta).uniform_(lo, hi)
@@ -288,7 +309,7 @@ def generator_step(
     d1 = (theta + cent_fin_diff_h / 2).clamp(0, 1)
     d2 = (theta - cent_fin_diff_h / 2).clamp(0, 1)
     w1, w2 = mapping_network.get_two_w(
-        batch_size=batch, n_gen_blocks=nb, device=device, domain_variables=(d1, d2)
+        batch_size=style_batch, n_gen_blocks=nb, device=device, domain_variables=(d1, d2)
     )
 
     losses = generator_losses(config, generator, discriminator, style_extractor,

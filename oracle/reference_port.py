@@ -616,9 +616,17 @@ class Trainer:
         return float(loss), (float(sign_real), float(sign_fake))
 
     # training.py:136-257
-    def generator_step(self, shoeprints: Tensor, shoemarks: Tensor, h_override: Tensor | None = None):
+    def generator_step(self, shoeprints: Tensor, shoemarks: Tensor, h_override: Tensor | None = None,
+                       n_styles: int = 1):
+        """n_styles = K > 1 is BASELINE config 4 (one input -> K sampled outputs): every
+        sampled-style pass (translation decode, D and S on the translations, both path-length
+        extractions) runs on the latent of each shoeprint broadcast to K styles, image (b, k)
+        at index b*K + k -- the `latent.expand(K, ...)` of evaluation.py:172-177 applied to the
+        training step; reconstruction (w = 0) and identity stay at B.  K = 1 is the reference."""
         a, hy = self.arch, self.hyper
         B, nb = hy.batch_size, a.n_style_blocks
+        K = int(n_styles)
+        BK = B * K
         G, M, S = _leaf(self.params["G"]), _leaf(self.params["M"]), _leaf(self.params["S"])
         D = self.params["D"]
         prints = shoeprints.to(self.dtype)
@@ -637,14 +645,15 @@ class Trainer:
         ident = generator_decode(G, mark_lat, mark_w.expand(nb, *mark_w.shape), a)
         idt_loss = F.l1_loss(ident, marks)
         # GAN (:193-204)
-        tw = get_single_w(M, B, nb, a, 1)
-        transl = generator_decode(G, print_lat, tw, a)
+        print_lat_k = print_lat if K == 1 else print_lat.repeat_interleave(K, dim=0)
+        tw = get_single_w(M, BK, nb, a, 1)
+        transl = generator_decode(G, print_lat_k, tw, a)
         scores = discriminator_forward(D, transl)
         gan_loss = F.mse_loss(scores, torch.ones_like(scores))
         # style cycle (:207-210)
         style_loss = style_cycle_loss(tw[-1], style_extractor_forward(S, transl))
         # path length (:214-234)
-        theta = torch.rand(B).to(self.dtype)
+        theta = torch.rand(BK).to(self.dtype)
         if h_override is None:
             hh = torch.ones_like(theta).uniform_(*hy.path_h_range)
         else:
@@ -652,9 +661,9 @@ class Trainer:
         self.last_h = hh
         d1 = (theta + hh / 2).clamp(0, 1)
         d2 = (theta - hh / 2).clamp(0, 1)
-        w1, w2 = get_two_w(M, B, nb, a, d1, d2)
-        f1 = generator_extract(G, print_lat, w1, a)
-        f2 = generator_extract(G, print_lat, w2, a)
+        w1, w2 = get_two_w(M, BK, nb, a, d1, d2)
+        f1 = generator_extract(G, print_lat_k, w1, a)
+        f2 = generator_extract(G, print_lat_k, w2, a)
         p_loss = path_loss(f1, f2, hh)
         total = (
             gan_loss

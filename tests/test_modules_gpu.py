@@ -108,7 +108,7 @@ def _cfg(case):
     }
 
 
-def _run_oracle(arch, P, dtype, batch, shape, h, iters):
+def _run_oracle(arch, P, dtype, batch, shape, h, iters, n_styles=1):
     torch.manual_seed(123)
     random.seed(123)
     tr = rp.Trainer(arch, rp.Hyper(batch_size=batch), P, dtype=dtype)
@@ -116,7 +116,8 @@ def _run_oracle(arch, P, dtype, batch, shape, h, iters):
     for it in range(iters):
         d = tr.discriminator_step(images(shape, 100 + it), images(shape, 200 + it))
         gd = {k: v.clone() for k, v in tr.last_grads["D"].items()}
-        g = tr.generator_step(images(shape, 300 + it), images(shape, 400 + it), h_override=h)
+        g = tr.generator_step(images(shape, 300 + it), images(shape, 400 + it), h_override=h,
+                              n_styles=n_styles)
         grads = {"D": gd, **{n: {k: v.clone() for k, v in tr.last_grads[n].items()} for n in "GMS"}}
         snap = {n: {k: v.clone() for k, v in tr.params[n].items()} for n in "DGMS"}
         out.append(([d[0], d[1][0], d[1][1], g[0], *g[1]], grads, snap))
@@ -229,3 +230,52 @@ def test_training_step_bf16_runs_and_tracks_oracle(case):
     for mod in (D, G, M, S):
         for p in mod.parameters():
             assert torch.isfinite(p).all()
+
+
+@pytest.mark.parametrize("use_engine", [False, True])
+def test_styles_per_input_matches_oracle_fp32(use_engine):
+    """BASELINE config 4 (one input -> K sampled outputs per step, here K = 3): the sampled-style
+    passes run at batch B*K on broadcast latents; losses at 2e-4 and every G/M/S gradient at the
+    oracle's fp32-vs-fp64 noise floor, through the step functions and through the graph engine."""
+    from one_to_many_gan_b200 import engine, training
+    from one_to_many_gan_b200.optim import FlatAdam
+
+    case, K = "down1", 3
+    arch, P, D, G, M, S = build(case, torch.float32)
+    b = CASES[case]["batch"]
+    shape = (b, 1, *arch.image_size)
+    h = torch.tensor([0.13, 0.17, 0.11, 0.19, 0.15, 0.12][: b * K])
+    ref64, _ = _run_oracle(arch, P, torch.float64, b, shape, h, 1, n_styles=K)
+    ref32, _ = _run_oracle(arch, P, torch.float32, b, shape, h, 1, n_styles=K)
+    dev = torch.device("cuda")
+    oD, oG, oS = (FlatAdam(m.parameters(), 2e-3, (0.5, 0.99)) for m in (D, G, S))
+    oM = FlatAdam(M.parameters(), 2e-5, (0.5, 0.99))
+    cfg = _cfg(case)
+    cfg["training"]["styles_per_input"] = K
+    cfg["data"] = {"image_size": list(arch.image_size)}
+    torch.manual_seed(123)
+    random.seed(123)
+    batches = [images(shape, s) for s in (100, 200, 300, 400)]
+    if use_engine:
+        it = engine.TrainIteration(cfg, dev, D, G, M, S, oD, oG, oM, oS, use_graph=False)
+        it.load_inputs(*[t.cuda() for t in batches])
+        out = it.run(h=h)
+        got = [out[k] for k in engine.TrainIteration.LOSS_NAMES]
+    else:
+        d = training.discriminator_step(cfg, dev, D, G, M, oD, iter([batches[0]]), iter([batches[1]]),
+                                        training.ImageBuffer(100), training.IdentityAugment(),
+                                        training.ADAp(256, 5.12e-4, b, 0.6))
+        g = training.generator_step(cfg, dev, G, D, M, S, oG, oM, oS, iter([batches[2]]),
+                                    iter([batches[3]]), training.IdentityAugment(), cent_fin_diff_h=h)
+        got = [d[0], d[1][0], d[1][1], g[0], *g[1]]
+    torch.testing.assert_close(torch.tensor(got, dtype=torch.float64),
+                               torch.tensor(ref64[0][0], dtype=torch.float64), rtol=2e-4, atol=1e-6)
+    mine = {"G": dict(G.named_parameters()), "M": dict(M.named_parameters()),
+            "S": dict(S.named_parameters())}
+    for net in "GMS":
+        live = [k for k in ref64[0][1][net] if (net, k) not in DEAD]
+        floors = {k: relerr(ref32[0][1][net][k], ref64[0][1][net][k]) for k in live}
+        net_floor = sorted(floors.values())[len(floors) // 2]
+        for k in live:
+            e = relerr(mine[net][k].grad, ref64[0][1][net][k])
+            assert e <= max(3 * floors[k], 3 * net_floor, 5e-3), (net, k, e, floors[k], net_floor)
