@@ -870,17 +870,19 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int n, h0, w0, o0;
       decode(t, n, h0, w0, o0);
       const int wrow = n * p.w_rows_per_sample + o0;
+      const bool two = (h0 + TH) < p.y.h;  // the lower tile of the pair has output rows
       for (int cc = 0; cc < cin_chunks; ++cc) {
         for (int s = 0; s < KS; ++s, ++ga) {
           const int sa = ga % NA;
           mbar_wait(smem_u32(&emptyA[sa]), ((ga / NA) & 1) ^ 1);
           if (lane == 0) {
             const uint32_t bar = smem_u32(&fullA[sa]);
-            mbar_expect_tx(bar, A_SLOT);
+            mbar_expect_tx(bar, two ? A_SLOT : A_BOX);
             tma_load_4d(smem_u32(ringA + sa * A_SLOT), &tmA, bar, cc * 64, w0 + s + p.coord_off,
                         h0 + p.coord_off, n);
-            tma_load_4d(smem_u32(ringA + sa * A_SLOT + A_BOX), &tmA, bar, cc * 64,
-                        w0 + s + p.coord_off, h0 + TH + p.coord_off, n);
+            if (two)
+              tma_load_4d(smem_u32(ringA + sa * A_SLOT + A_BOX), &tmA, bar, cc * 64,
+                          w0 + s + p.coord_off, h0 + TH + p.coord_off, n);
           }
           __syncwarp();
           for (int r = 0; r < KS; ++r, ++gb) {
@@ -906,6 +908,12 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * 2 * BN);  // [tile0 | tile1]
       uint32_t first = 1;
+      bool two;
+      {
+        int n, h0, w0, o0;
+        decode(t, n, h0, w0, o0);
+        two = (h0 + TH) < p.y.h;
+      }
       for (int cc = 0; cc < cin_chunks; ++cc) {
         for (int s = 0; s < KS; ++s, ++ga) {
           const int sa = ga % NA;
@@ -922,8 +930,9 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
               for (int k = 0; k < 4; ++k) {  // the B tile is read once for both pixel tiles
                 umma_bf16(tacc, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
-                umma_bf16(tacc + BN, da1 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                          first ? 0u : 1u);
+                if (two)
+                  umma_bf16(tacc + BN, da1 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                            first ? 0u : 1u);
                 first = 0;
               }
               umma_commit(smem_u32(&emptyB[sb]));
@@ -956,8 +965,9 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc_fence_after();
       uint8_t* myrow = stage_out + m * 128;
       const int sw = m & 7;
+      const int nhalf = (h0 + TH) < p.y.h ? 2 : 1;  // a fully out-of-range lower tile is skipped
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < nhalf; ++half) {
         const int hh0 = h0 + half * TH;
         const int oh = hh0 + m / TW, ow = w0 + m % TW;
         const bool valid = (oh < p.y.h) && (ow < p.y.w);
@@ -983,7 +993,7 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
         }
         tc_fence_before();
-        if (half == 1) mbar_arrive(smem_u32(&tmem_empty[buf]));  // both accumulators drained
+        if (half == nhalf - 1) mbar_arrive(smem_u32(&tmem_empty[buf]));  // accumulators drained
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (te == 0 && hh0 < p.y.h) {

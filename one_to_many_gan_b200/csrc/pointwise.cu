@@ -56,6 +56,45 @@ __global__ void __launch_bounds__(256) ew_kernel(F f, int N, int H, int W, int C
   }
 }
 
+// Persistent form: the work is cut into items of 256 channel-vectors (one image row = nblk
+// items) and every CTA owns a CONTIGUOUS range of items whose length differs by at most one
+// between CTAs.  grid = 4 CTAs per SM, all co-resident (64 registers/thread): no partial last
+// wave (the row-chunk form above ran 1.04-1.15 waves of 8 CTAs/SM-sized grids on 2-4 resident
+// CTAs/SM), and the per-(n, channel) constants are re-read only when the image changes.
+template <int V, typename F>
+__global__ void __launch_bounds__(256, 4) ew_persist_kernel(F f, int N, int H, int W, int C,
+                                                            int cv_shift, int nblk, int items) {
+  const int CV = C / V;
+  const int WC = W * CV;
+  const int nrows = N * H;
+  const int t0 = (int)((long long)items * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)items * (blockIdx.x + 1) / gridDim.x);
+  if (t0 >= t1) return;
+  int r = t0 / nblk, cb = t0 - r * nblk;
+  int n = r / H, h = r - n * H;
+  typename F::State st;
+  int cur_n = -1, cur_cv = -1;
+  for (int it = t0; it < t1; ++it) {
+    const int i = cb * 256 + threadIdx.x;
+    if (i < WC) {
+      int w, cv;
+      if (cv_shift >= 0) { w = i >> cv_shift; cv = i & (CV - 1); }
+      else { w = i / CV; cv = i - w * CV; }
+      if (r + PF_ROWS < nrows) {
+        int hp = h + PF_ROWS, np = n;
+        while (hp >= H) { hp -= H; ++np; }
+        f.prefetch(np, hp, w, cv * V);
+      }
+      if (n != cur_n || cv != cur_cv) { f.prepare(n, cv * V, st); cur_n = n; cur_cv = cv; }
+      f(n, h, w, cv * V, st);
+    }
+    if (++cb == nblk) {
+      cb = 0; ++r;
+      if (++h == H) { h = 0; ++n; }
+    }
+  }
+}
+
 template <int V, typename F>
 static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
   const long long total = (long long)N * H * W * (C / V);
@@ -64,6 +103,18 @@ static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
   int cv_shift = -1;
   if ((CV & (CV - 1)) == 0) { cv_shift = 0; while ((1 << cv_shift) < CV) ++cv_shift; }
   const int nrows = N * H;
+  static const int mode = [] { const char* e = getenv("OTM_EW_MODE"); return e ? atoi(e) : 1; }();
+  if (mode == 1) {
+    const int nblk = (W * CV + 255) / 256;
+    const long long items = (long long)nrows * nblk;
+    if (items < (1ll << 30)) {
+      long long grid = (long long)num_sms() * 4;
+      if (grid > items) grid = items;
+      ew_persist_kernel<V, F><<<(int)grid, 256, 0, st>>>(f, N, H, W, C, cv_shift, nblk, (int)items);
+      OTM_LAUNCH_CHECK();
+      return OTM_OK;
+    }
+  }
   // enough CTAs for ~8 per SM; a bounded number of rows per CTA
   static const int rows_cap = [] { const char* e = getenv("OTM_EW_ROWS"); return e ? atoi(e) : 8; }();
   static const int ctas_per_sm = [] { const char* e = getenv("OTM_EW_CTAS"); return e ? atoi(e) : 8; }();
@@ -83,7 +134,7 @@ static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
 // grid = (pixel chunks, 1, N), 256 threads = lanes (channel vectors) x rows (pixels).
 // ---------------------------------------------------------------------------
 template <int V, typename F>
-__global__ void __launch_bounds__(256) nc_reduce_kernel(F f, int H, int W, int C, int lanes,
+__global__ void __launch_bounds__(256, 4) nc_reduce_kernel(F f, int H, int W, int C, int lanes,
                                                         int pix_per_cta, float* out) {
   constexpr int NQ = F::NQ;
   __shared__ float red[256 * NQ * V];
@@ -148,8 +199,11 @@ static int launch_nc_reduce(F f, int N, int H, int W, int C, float* out, cudaStr
   while (lanes * 2 <= CV && lanes * 2 <= 256) lanes *= 2;
   int HW = H * W;
   int rows = 256 / lanes;
-  // aim for ~4 CTAs per SM overall, but at least `rows*4` pixels per CTA
-  int want_chunks = (num_sms() * 4 + N - 1) / N;
+  // all CTAs co-resident (4 per SM at 64 registers): chunks * N <= 4 * SMs, so there is no
+  // partial second wave; at least `rows*4` pixels per CTA
+  static const int mode = [] { const char* e = getenv("OTM_EW_MODE"); return e ? atoi(e) : 1; }();
+  int want_chunks = mode == 1 ? (num_sms() * 4) / N : (num_sms() * 4 + N - 1) / N;
+  if (want_chunks < 1) want_chunks = 1;
   int pix = (HW + want_chunks - 1) / want_chunks;
   int min_pix = rows * 4;
   if (pix < min_pix) pix = min_pix;

@@ -198,7 +198,9 @@ def _check_weights_after_one_step(case, mods, ref64, ref32):
             want = ref64[0][2][net][k]
             diff = (p.double() - want).abs()
             bad = ((diff > 2e-3 * want.abs() + 0.25 * lr[net]) & determined).double().mean().item()
-            assert bad <= 2e-3, (case, net, k, bad, determined.double().mean().item())
+            # (small tensors: allow a handful of elements -- 3 of the 1,024 weights of D's first
+            # conv flip in ~1 run out of 4, the fp32 atomics' summation order differs run to run)
+            assert bad <= max(2e-3, 8.0 / p.numel()), (case, net, k, bad, determined.double().mean().item())
 
 
 @pytest.mark.parametrize("case", ["down1"])
