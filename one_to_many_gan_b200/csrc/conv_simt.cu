@@ -427,6 +427,229 @@ wgrad_cin1_kernel(WgradP p, int tiles_w, int tiles_per_img, int total_tiles) {
 }
 
 // ---------------------------------------------------------------------------
+// Cin == 1 layers in bf16 mode on the warp-level tensor-core path (mma.sync m16n8k16, bf16 x
+// bf16 -> fp32).  K = 49 / 16 taps is below a tcgen05 tile and these layers are bound by the
+// 64-channel tensor they write (fwd) or read (wgrad), so the point of the MMA is only to take
+// the 64 x taps FMAs per pixel off the FFMA pipe: the FFMA kernels above ran at 19 TFLOP/s
+// (0.35 ms per 7x7 launch, 16x the time of the HBM traffic).
+//   forward : M = 16 pixels of one tile row, N = 64 couts (8 n-tiles), K = taps (padded to 16s).
+//             A fragments are gathered from the bf16 image patch in shared memory, the weight
+//             (B) fragments live in registers for the whole kernel.
+//   wgrad   : M = taps, N = 64 couts, K = pixels.  A gathered from the image patch, B =
+//             ldmatrix.trans of the [pixel][cout] dy tile (row pitch 144 B: conflict-free).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
+                                          const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+__device__ __forceinline__ uint32_t pack_bf16f(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256, 2)
+conv_cin1_mma_kernel(ConvP p, int tiles_w, int tiles_per_img, int total_tiles) {
+  constexpr int TT = 16, PW = TT + KS - 1, CO = 64, TAPS = KS * KS, KSTEPS = (TAPS + 15) / 16;
+  constexpr int SP = CO + 8;  // staging row pitch (elements): 144 B, conflict-free
+  __shared__ __nv_bfloat16 xs[(PW * PW + 7) & ~7];
+  __shared__ __align__(16) __nv_bfloat16 stage[8][16][SP];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int g = lane >> 2, q = lane & 3;
+  const int H = p.x.h, W = p.x.w, halo = p.x_halo;
+  // weight fragments: B[k = tap][n = cout] = w[cout][tap], zero for the padded taps
+  uint32_t bf[KSTEPS][8][2];
+  {
+    const float* wbase = (const float*)p.w;
+#pragma unroll
+    for (int kk = 0; kk < KSTEPS; ++kk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k0 = kk * 16 + q * 2 + h * 8, o = j * 8 + g;
+          const float lo = k0 < TAPS ? wbase[o * TAPS + k0] : 0.f;
+          const float hi = k0 + 1 < TAPS ? wbase[o * TAPS + k0 + 1] : 0.f;
+          bf[kk][j][h] = pack_bf16f(lo, hi);
+        }
+  }
+  // patch offsets of this lane's four k columns per k-step (padded taps read offset 0: their
+  // weights are zero and the patch holds finite values)
+  int aoff[KSTEPS][4];
+#pragma unroll
+  for (int kk = 0; kk < KSTEPS; ++kk)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = kk * 16 + q * 2 + (c & 1) + (c >> 1) * 8;
+      aoff[kk][c] = k < TAPS ? (k / KS) * PW + (k % KS) : 0;
+    }
+  __shared__ float s_bias[CO];
+  if (threadIdx.x < CO) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
+    __syncthreads();
+    for (int e = threadIdx.x; e < PW * PW; e += 256) {
+      const int pw = e % PW, ph = e / PW;
+      const int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+      float v = 0.f;
+      if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo)
+        v = *vptr<float>(p.x, n, ih, iw, 0);
+      xs[e] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const int ty = warp * 2 + mt;  // tile row = the 16 pixels (M) of this m-tile
+      float acc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+      const int b0 = ty * PW + g, b1 = b0 + 8;
+#pragma unroll
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        uint32_t a[4];
+        a[0] = pack_bf16(xs[b0 + aoff[kk][0]], xs[b0 + aoff[kk][1]]);
+        a[1] = pack_bf16(xs[b1 + aoff[kk][0]], xs[b1 + aoff[kk][1]]);
+        a[2] = pack_bf16(xs[b0 + aoff[kk][2]], xs[b0 + aoff[kk][3]]);
+        a[3] = pack_bf16(xs[b1 + aoff[kk][2]], xs[b1 + aoff[kk][3]]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mma_16816(acc[j], a, bf[kk][j]);
+      }
+      // epilogue: alpha, bias, activation -> bf16 -> per-warp staging tile [16 px][64 ch]
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = fmaf(acc[j][e], p.alpha, s_bias[j * 8 + q * 2 + (e & 1)]);
+        act_fwd_vec<4>(v, p.act);
+        *reinterpret_cast<uint32_t*>(&stage[warp][g][j * 8 + q * 2]) = pack_bf16f(v[0], v[1]);
+        *reinterpret_cast<uint32_t*>(&stage[warp][g + 8][j * 8 + q * 2]) = pack_bf16f(v[2], v[3]);
+      }
+      __syncwarp();
+      const int oh = oh0 + ty;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int chunk = lane + 32 * i;  // 16 px x 8 chunks of 8 channels
+        const int px = chunk >> 3, c8 = chunk & 7;
+        const int ow = ow0 + px;
+        if (oh < p.y.h && ow < p.y.w) {
+          const uint4 val = *reinterpret_cast<const uint4*>(&stage[warp][px][c8 * 8]);
+          if (p.y_halo == 0) {
+            *reinterpret_cast<uint4*>(vptr_mut<__nv_bfloat16>(p.y, n, oh, ow, c8 * 8)) = val;
+          } else {
+            float f[8];
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 ff = __bfloat1622float2(h2[e]);
+              f[2 * e] = ff.x; f[2 * e + 1] = ff.y;
+            }
+            store_halo<__nv_bfloat16, 8>(p.y, p.y_halo, n, oh, ow, c8 * 8, f);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256, 2)
+wgrad_cin1_mma_kernel(WgradP p, int tiles_w, int tiles_per_img, int total_tiles) {
+  constexpr int TT = 16, PW = TT + KS - 1, CO = 64, TAPS = KS * KS, MT = (TAPS + 15) / 16;
+  constexpr int KSL = MT == 4 ? 1 : 4;   // K slices (tile rows) across warps
+  constexpr int NG = 8 / (MT * KSL);     // n-groups of 4 n-tiles across warps
+  static_assert(MT * KSL * NG == 8 && NG == 2, "warp layout");
+  constexpr int DP = CO + 8;             // dy row pitch (elements): 144 B
+  extern __shared__ __align__(16) unsigned char wm_smem[];
+  __nv_bfloat16* dys = reinterpret_cast<__nv_bfloat16*>(wm_smem);  // [256 px][DP]
+  __nv_bfloat16* xs = dys + TT * TT * DP;                          // [PW*PW]
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int g = lane >> 2, q = lane & 3;
+  const int mi = warp % MT, ng = (warp / MT) % NG, ks = warp / (MT * NG);
+  const int H = p.x.h, W = p.x.w, halo = p.x_halo;
+  int toff[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int tap = mi * 16 + g + h * 8;
+    toff[h] = tap < TAPS ? (tap / KS) * PW + (tap % KS) : 0;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * TT, ow0 = (tile % tiles_w) * TT;
+    __syncthreads();
+    for (int e = threadIdx.x; e < PW * PW; e += 256) {
+      const int pw = e % PW, ph = e / PW;
+      const int ih = oh0 + ph - p.pad, iw = ow0 + pw - p.pad;
+      float v = 0.f;
+      if (ih >= -halo && ih < H + halo && iw >= -halo && iw < W + halo)
+        v = *vptr<float>(p.x, n, ih, iw, 0);
+      xs[e] = __float2bfloat16_rn(v);
+    }
+    for (int e = threadIdx.x; e < TT * TT * 8; e += 256) {
+      const int c8 = e & 7, px = e >> 3;
+      const int oh = oh0 + px / TT, ow = ow0 + px % TT;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (oh < p.dy.h && ow < p.dy.w)
+        val = *reinterpret_cast<const uint4*>(vptr<__nv_bfloat16>(p.dy, n, oh, ow, c8 * 8));
+      *reinterpret_cast<uint4*>(dys + px * DP + c8 * 8) = val;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kq = 0; kq < TT / KSL; ++kq) {
+      const int kk = ks * (TT / KSL) + kq;  // tile row = 16 pixels of K
+      uint32_t a[4];
+      const int xb = kk * PW + q * 2;
+      a[0] = pack_bf16(xs[xb + toff[0]], xs[xb + toff[0] + 1]);
+      a[1] = pack_bf16(xs[xb + toff[1]], xs[xb + toff[1] + 1]);
+      a[2] = pack_bf16(xs[xb + toff[0] + 8], xs[xb + toff[0] + 9]);
+      a[3] = pack_bf16(xs[xb + toff[1] + 8], xs[xb + toff[1] + 9]);
+#pragma unroll
+      for (int jp = 0; jp < 2; ++jp) {  // two n-tiles per ldmatrix.x4
+        uint32_t b[4];
+        const int krow = kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+        const int ncol = (ng * 4 + jp * 2 + (lane >> 4)) * 8;
+        ldmatrix_x4_trans(b, dys + krow * DP + ncol);
+        const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+        mma_16816(acc[jp * 2], a, b0);
+        mma_16816(acc[jp * 2 + 1], a, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int tap = mi * 16 + g + (e >> 1) * 8;
+      const int o = (ng * 4 + j) * 8 + q * 2 + (e & 1);
+      if (tap < TAPS) atomicAdd(p.dw + o * TAPS + tap, acc[j][e] * p.alpha);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // wgrad, generic tile: M = 64 couts, N = 64 flattened (r,s,i), K = pixels of one sample
 // chunk.  grid = (ceil(ktot/64), ceil(cout/64), n * splits); atomicAdd into dw.
 // ---------------------------------------------------------------------------
@@ -828,11 +1051,15 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
     const int per_img = tiles_w * tiles_h, total = per_img * a->y.n;
     int ctas = num_sms() * 2;
     if (ctas > total) ctas = total;
+    static const int thin_mma = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
+    const bool mma = thin_mma && out_bf && !a->row_scale && !a->residual.ptr;
     if (a->kh == 7) {
-      if (out_bf) conv_cin1_kernel<__nv_bfloat16, 7><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
+      if (mma) conv_cin1_mma_kernel<7><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
+      else if (out_bf) conv_cin1_kernel<__nv_bfloat16, 7><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
       else conv_cin1_kernel<float, 7><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
     } else {
-      if (out_bf) conv_cin1_kernel<__nv_bfloat16, 4><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
+      if (mma) conv_cin1_mma_kernel<4><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
+      else if (out_bf) conv_cin1_kernel<__nv_bfloat16, 4><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
       else conv_cin1_kernel<float, 4><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
     }
     OTM_LAUNCH_CHECK();
@@ -907,6 +1134,25 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
     }                                                                                             \
     kern<<<ctas, NT, smem, st>>>(p, tiles_w, per_img, total);                                     \
   } while (0)
+    static const int thin_mma = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
+    if (thin_mma && yb) {
+#define OTM_WM1(KS)                                                                              \
+  do {                                                                                            \
+    const size_t smem = sizeof(__nv_bfloat16) * (TT * TT * 72 + (TT + KS - 1) * (TT + KS - 1) + 8); \
+    auto kern = wgrad_cin1_mma_kernel<KS>;                                                        \
+    static bool set_ = false;                                                                     \
+    if (!set_) {                                                                                  \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                          (int)smem));                                            \
+      set_ = true;                                                                                \
+    }                                                                                             \
+    kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);                                    \
+  } while (0)
+      if (a->kh == 7) OTM_WM1(7); else OTM_WM1(4);
+#undef OTM_WM1
+      OTM_LAUNCH_CHECK();
+      return OTM_OK;
+    }
     if (a->kh == 7) {
       if (yb) OTM_WC1(__nv_bfloat16, 7, 416); else OTM_WC1(float, 7, 416);
     } else {

@@ -1206,6 +1206,178 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
 }
 
 // ---------------------------------------------------------------------------
+// Row-reuse wgrad: one CTA owns a filter COLUMN s and all KS filter rows of it.  Per K stage
+// (an 8 x 8 pixel tile of one sample) it loads the dy tile once and ONE x box of (8 + KS - 1)
+// rows; the operand of tap (r, s) is that box read through a descriptor offset by r pixel rows
+// (1024 B), exactly like the forward row-reuse kernel.  KS accumulators live in TMEM
+// (KS * BN columns).  L2 -> shared traffic per MMA drops from 8 KB (the per-tap kernel above
+// re-fetches both tiles for each of the kh*kw taps and measured ~9 TB/s of L2 reads at
+// 600 TFLOP/s, i.e. L2-bound) to 3 KB.
+//   XCH / DCH = 64-channel chunks of the x / dy operand (the M side always has 2 = 128 rows).
+// ---------------------------------------------------------------------------
+template <int XCH, int DCH, int KS, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_wgrad_rr_kernel(const __grid_constant__ CUtensorMap tmX,
+                        const __grid_constant__ CUtensorMap tmDy, TcWgP p) {
+  constexpr int TH = 8;
+  constexpr int X_BOX = (TH + KS - 1) * 1024;  // (8 + KS - 1) rows x 8 pixels x 128 B
+  constexpr int D_BOX = TH * 1024;
+  constexpr int X_BYTES = XCH * X_BOX, D_BYTES = DCH * D_BOX;
+  constexpr int STAGE_BYTES = X_BYTES + D_BYTES;
+  constexpr int BN = 64 * (XCH + DCH - 2);  // the side that is not the 128-row M side
+  constexpr int TCOLS = KS * BN <= 256 ? 256 : 512;
+  static_assert(KS * BN <= 512, "accumulators exceed TMEM");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* accum_full = bars + 2 * STAGES;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int s = blockIdx.x;  // filter column
+  const int mt = blockIdx.y / p.n_tiles_n, nt = blockIdx.y % p.n_tiles_n;
+  const int m0 = mt * 128, n0 = nt * BN;
+  const int n = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int t_beg = (int)((long long)p.tiles_total * split / p.splits);
+  const int t_end = (int)((long long)p.tiles_total * (split + 1) / p.splits);
+  const int num_k = t_end - t_beg;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDy);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int st = 0; st < STAGES; ++st) {
+      mbar_init(smem_u32(&full[st]), 1);
+      mbar_init(smem_u32(&empty[st]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TCOLS>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      const int xc0 = p.a_is_x ? m0 : n0, dc0 = p.a_is_x ? n0 : m0;
+      for (int it = 0; it < num_k; ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(smem_u32(&empty[stage]), ((it / STAGES) & 1) ^ 1);
+        if (lane == 0) {
+          const int t = t_beg + it;
+          const int h0 = (t / p.tiles_w) * TH, w0 = (t % p.tiles_w) * 8;
+          const uint32_t bar = smem_u32(&full[stage]);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+          for (int c = 0; c < XCH; ++c)
+            tma_load_4d(sa + c * X_BOX, &tmX, bar, xc0 + c * 64, w0 + s + p.x_coord_off,
+                        h0 + p.x_coord_off, n);
+#pragma unroll
+          for (int c = 0; c < DCH; ++c)
+            tma_load_4d(sa + X_BYTES + c * D_BOX, &tmDy, bar, dc0 + c * 64, w0, h0, n);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+      for (int it = 0; it < num_k; ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(smem_u32(&full[stage]), (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          // MN-major SW128: LBO = stride between 64-channel chunks, SBO = 8 pixels (1024 B)
+          const uint64_t dd = make_desc(sa + X_BYTES, D_BOX, 1024);
+#pragma unroll
+          for (int r = 0; r < KS; ++r) {
+            const uint64_t dx = make_desc(sa + r * 1024, X_BOX, 1024);
+            const uint64_t da = p.a_is_x ? dx : dd, db = p.a_is_x ? dd : dx;
+#pragma unroll
+            for (int k = 0; k < TH / 2; ++k)  // 16 pixels (K) = 2 pixel rows = 2048 B per step
+              umma_bf16(tmem_base + (uint32_t)(r * BN), da + (uint64_t)(k * 128),
+                        db + (uint64_t)(k * 128), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty[stage]));
+          if (it == num_k - 1) umma_commit(smem_u32(accum_full));
+        }
+        __syncwarp();
+      }
+    } else if (warp >= 4) {
+      const int wq = warp - 4;
+      mbar_wait(smem_u32(accum_full), 0);
+      tc_fence_after();
+      const int m = m0 + wq * 32 + lane;
+      const int taps = p.kh * p.kw;
+      float rowf = p.alpha;
+      if (p.a_is_x) { if (p.cs) rowf *= p.cs[(long long)n * p.cin + m]; }
+      else { if (p.rs) rowf *= p.rs[(long long)n * p.cout + m]; }
+      const int Mtot = p.a_is_x ? p.cin : p.cout, Ntot = p.a_is_x ? p.cout : p.cin;
+      const float* colv = p.a_is_x ? p.rs : p.cs;
+      float pacc = 0.f;
+#pragma unroll 1
+      for (int r = 0; r < KS; ++r) {
+        const int tap = r * p.kw + s;
+        const __nv_bfloat16* wrow =
+            p.P ? p.wfwd + (((long long)n * p.cout + m) * taps + tap) * p.cin : nullptr;
+#pragma unroll 1
+        for (int j = 0; j < BN / 16; ++j) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(r * BN + j * 16), v);
+          const int nn0 = n0 + j * 16;
+          if (wrow) {
+            float w0[8], w1[8];
+            load_vec<__nv_bfloat16, 8>(wrow + nn0, w0);
+            load_vec<__nv_bfloat16, 8>(wrow + nn0 + 8, w1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pacc = fmaf(v[i], w0[i], fmaf(v[8 + i], w1[i], pacc));
+          }
+          if (colv) {
+            const float4* cp = reinterpret_cast<const float4*>(colv + (long long)n * Ntot + nn0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 t = cp[q];
+              v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= rowf;
+          if (p.debug) continue;
+          if (p.ws) {
+            float4* dst = reinterpret_cast<float4*>(p.ws + ((long long)tap * Mtot + m) * Ntot + nn0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              atomicAdd(dst + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int nn = nn0 + i;
+              const int o = p.a_is_x ? nn : m, ci = p.a_is_x ? m : nn;
+              atomicAdd(p.dw + ((long long)o * p.cin + ci) * taps + tap, v[i]);
+            }
+          }
+        }
+      }
+      if (p.P && p.debug == 0) {
+        const float rsv = p.rs ? p.rs[(long long)n * p.cout + m] : 1.f;
+        atomicAdd(p.P + (long long)n * p.cout + m, pacc * rsv);
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TCOLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1483,6 +1655,22 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
   return OTM_OK;
 }
 
+template <int XCH, int DCH, int KS, int STAGES>
+static int launch_wgrad_rr(const CUtensorMap& tmX, const CUtensorMap& tmDy, const TcWgP& p, dim3 grid,
+                           cudaStream_t st) {
+  constexpr int smem = STAGES * (XCH * (8 + KS - 1) * 1024 + DCH * 8 * 1024) + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "wgrad rr ring exceeds shared memory");
+  auto kern = conv_tc_wgrad_rr_kernel<XCH, DCH, KS, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<grid, 256, smem, st>>>(tmX, tmDy, p);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
 int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const int cin = a->x.c, cout = a->dy.c;
   TcWgP p;
@@ -1508,20 +1696,71 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   static const int dbg = [] { const char* e = getenv("OTM_WG_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
 
+  static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
+  // OTM_WG_RR=1 selects the row-reuse wgrad kernel.  Measured (tools/bench_wgrad.py, B200): 959 vs
+  // 928 TFLOP/s at n=96 128->128, but 656 vs 733 at n=64 and 689-706 vs 799-896 on the 64-wide
+  // layers (1 CTA/SM: coarser waves, epilogue not overlapped); with the reduction skipped both
+  // kernels run at 1.0-1.1 PFLOP/s = the shared-memory operand bandwidth of a 128x128 MMA, so
+  // L2 re-fetches were not the limiter.  Default: the per-tap kernel.
+  static const int wg_rr = [] { const char* e = getenv("OTM_WG_RR"); return e ? atoi(e) : 0; }();
+  p.ws = a->ws;
+  p.wfwd = (const __nv_bfloat16*)a->wfwd;
+  p.P = a->P;
+  if (p.P) OTM_REQUIRE(!p.a_is_x && p.wfwd, "conv_wgrad: fused P needs Cout %% 128 == 0 and wfwd");
   CUtensorMap tmX, tmDy;
-  int rc = make_act_map(&tmX, a->x, a->x_halo, 8, 8);
+  int rc;
+  if (wg_rr && variant == 0 && a->kh == a->kw && (a->kh == 3 || a->kh == 4)) {
+    // row-reuse kernel: one CTA per (filter column, 128 x BN block, sample, K split), 1 CTA/SM
+    const int KS = a->kh;
+    const int bn = (N % 128 == 0) ? 128 : 64;
+    p.n_tiles_n = N / bn;
+    const long long base_rr = (long long)KS * m_tiles * p.n_tiles_n * a->dy.n;
+    // K splits: minimise waves x (main loop + epilogue) in units of one MMA-stage
+    const double t_stage = KS * 4.0, t_epi = KS * (bn / 16) * 1.2 + 6.0;
+    int best = 1;
+    double best_cost = 1e30;
+    const int smax = p.tiles_total < 64 ? (p.tiles_total + 7) / 8 : 8;
+    for (int sp = 1; sp <= smax; ++sp) {
+      if ((long long)a->dy.n * sp > 65535) break;
+      const double waves = (double)((base_rr * sp + num_sms() - 1) / num_sms());
+      const double cost = waves * (((p.tiles_total + sp - 1) / sp) * t_stage + t_epi);
+      if (cost < best_cost) { best_cost = cost; best = sp; }
+    }
+    p.splits = best;
+    rc = make_act_map(&tmX, a->x, a->x_halo, 8, 8 + KS - 1);
+    if (rc) return rc;
+    rc = make_act_map(&tmDy, a->dy, 0, 8, 8);
+    if (rc) return rc;
+    dim3 grid_rr(KS, m_tiles * p.n_tiles_n, a->dy.n * p.splits);
+    if (p.ws) OTM_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, sizeof(float) * (size_t)taps * cin * cout, st));
+    if (bn == 128) {
+      rc = KS == 3 ? launch_wgrad_rr<2, 2, 3, 5>(tmX, tmDy, p, grid_rr, st)
+                   : launch_wgrad_rr<2, 2, 4, 5>(tmX, tmDy, p, grid_rr, st);
+    } else if (p.a_is_x) {
+      rc = KS == 3 ? launch_wgrad_rr<2, 1, 3, 6>(tmX, tmDy, p, grid_rr, st)
+                   : launch_wgrad_rr<2, 1, 4, 6>(tmX, tmDy, p, grid_rr, st);
+    } else {
+      rc = KS == 3 ? launch_wgrad_rr<1, 2, 3, 6>(tmX, tmDy, p, grid_rr, st)
+                   : launch_wgrad_rr<1, 2, 4, 6>(tmX, tmDy, p, grid_rr, st);
+    }
+    if (rc) return rc;
+    if (p.ws) {
+      const long long total = (long long)taps * cin * cout;
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+      wgrad_fold_kernel<<<blocks, 256, 0, st>>>(p.ws, p.dw, cout, cin, taps, p.a_is_x);
+      OTM_LAUNCH_CHECK();
+    }
+    return OTM_OK;
+  }
+  rc = make_act_map(&tmX, a->x, a->x_halo, 8, 8);
   if (rc) return rc;
   rc = make_act_map(&tmDy, a->dy, 0, 8, 8);
   if (rc) return rc;
   const CUtensorMap& tmA = p.a_is_x ? tmX : tmDy;
   const CUtensorMap& tmB = p.a_is_x ? tmDy : tmX;
   dim3 grid(taps, m_tiles * p.n_tiles_n, a->dy.n * splits);
-  p.ws = a->ws;
-  p.wfwd = (const __nv_bfloat16*)a->wfwd;
-  p.P = a->P;
-  if (p.P) OTM_REQUIRE(!p.a_is_x && p.wfwd, "conv_wgrad: fused P needs Cout %% 128 == 0 and wfwd");
   if (p.ws) OTM_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, sizeof(float) * (size_t)taps * cin * cout, st));
-  static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
   if (variant == 1) {
     if (BN == 64) rc = launch_wgrad<64, 6, 1>(tmA, tmB, p, grid, st);
     else if (BN == 128) rc = launch_wgrad<128, 6, 1>(tmA, tmB, p, grid, st);

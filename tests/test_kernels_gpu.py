@@ -176,7 +176,9 @@ def test_image_side_convs_mixed_dtype(K, k, pad, halo, H, W):
         dw = torch.zeros_like(w)
         K.conv_wgrad(nhwc(x, torch.float32, halo), nhwc(dy.float(), dt), dw, k, k, pad, x_halo=halo,
                      alpha=alpha)
-        assert relerr(dw, gw_ref) < 2e-4, (k, dt)
+        # bf16 mode runs on mma.sync with the image patch rounded to bf16 (like every other
+        # layer's input in that mode); fp32 mode is the FFMA kernel
+        assert relerr(dw, gw_ref) < (2e-4 if dt == torch.float32 else 5e-3), (k, dt)
 
 
 @pytest.mark.parametrize("case", [(128, 128, 16, 16, 3), (64, 128, 16, 24, 2), (128, 64, 16, 16, 2),
