@@ -144,10 +144,10 @@ def mod_bwd(w, alpha, s, sigma_inv, q, P, Q, dw):
     return ds
 
 
-def instnorm_stats(x, eps=1e-5):
+def instnorm_stats(x, eps=1e-5, out=None):
     n, c = x.shape[:2]
     ws = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
-    stats = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+    stats = out if out is not None else torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
     d = L.tdesc(x)
     L.check(L.lib.otm_instnorm_stats(_byref(d), eps, L.ptr(ws), L.ptr(stats), L.stream_ptr()),
             "otm_instnorm_stats")
@@ -193,9 +193,10 @@ def norm_act_bwd(g, x, stats=None, act=ACT_NONE, *, g_halo=0, g2=None, want_gres
     return (gx, gres) if want_gres else gx
 
 
-def down(x, stats=None, act=ACT_NONE, y_halo=0):
+def down(x, stats=None, act=ACT_NONE, y_halo=0, out=None):
     n, c, h, w = x.shape
-    out = alloc(n, c, h // 2, w // 2, x.dtype, x.device, y_halo)
+    if out is None:
+        out = alloc(n, c, h // 2, w // 2, x.dtype, x.device, y_halo)
     a = L.DownArgs()
     a.x = L.tdesc(x)
     a.stats = L.ptr(stats)
