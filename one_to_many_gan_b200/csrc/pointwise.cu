@@ -3,6 +3,7 @@
 // All kernels use channel-vector (8-wide, 128-bit for bf16) NHWC access when the
 // tensors allow it and fall back to scalar access for C==1 images.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -61,9 +62,16 @@ __global__ void __launch_bounds__(256) ew_kernel(F f, int N, int H, int W, int C
 // between CTAs.  grid = 4 CTAs per SM, all co-resident (64 registers/thread): no partial last
 // wave (the row-chunk form above ran 1.04-1.15 waves of 8 CTAs/SM-sized grids on 2-4 resident
 // CTAs/SM), and the per-(n, channel) constants are re-read only when the image changes.
+// resident CTAs per SM of a functor's persistent kernel (register budget 65536 / (256 * OCC));
+// functors that hold a block of outputs per thread declare `static constexpr int OCC = 2`
+template <typename F, typename = void>
+struct ew_occ { static constexpr int value = 4; };
+template <typename F>
+struct ew_occ<F, std::void_t<decltype(F::OCC)>> { static constexpr int value = F::OCC; };
+
 template <int V, typename F>
-__global__ void __launch_bounds__(256, 4) ew_persist_kernel(F f, int N, int H, int W, int C,
-                                                            int cv_shift, int nblk, int items) {
+__global__ void __launch_bounds__(256, ew_occ<F>::value)
+ew_persist_kernel(F f, int N, int H, int W, int C, int cv_shift, int nblk, int items) {
   const int CV = C / V;
   const int WC = W * CV;
   const int nrows = N * H;
@@ -108,7 +116,7 @@ static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
     const int nblk = (W * CV + 255) / 256;
     const long long items = (long long)nrows * nblk;
     if (items < (1ll << 30)) {
-      long long grid = (long long)num_sms() * 4;
+      long long grid = (long long)num_sms() * ew_occ<F>::value;
       if (grid > items) grid = items;
       ew_persist_kernel<V, F><<<(int)grid, 256, 0, st>>>(f, N, H, W, C, cv_shift, nblk, (int)items);
       OTM_LAUNCH_CHECK();
@@ -645,6 +653,210 @@ struct UpBwdF {
   }
 };
 
+// Block forms of the x2 up-sampling stencils.  The per-output functors above spend ~200
+// instructions per 16-byte vector on tap generation and issue 9 (forward) / 36 (backward) loads
+// per output vector; they ran at 0.8-1.2 TB/s.  Here one thread produces a 2x2 block:
+//   forward : the four outputs of input pixel (h, w) from its 3x3 neighbourhood, separable,
+//             constant weights (even j=2m: .3125,.625,.0625 on m-1..m+1; odd: mirrored);
+//   backward: the input gradients of the 2x2 pixel block (2h..2h+1, 2w..2w+1) from the 8x8
+//             output-gradient window (rows 4h-2 .. 4h+5), horizontal pass first.
+// Blocks that touch the clamped image border take the general tap path of the functors above.
+template <typename T, int V>
+struct Up2x2F {
+  static constexpr int OCC = 2;
+  __device__ void prefetch(int, int, int, int) const {}
+  View x, y;
+  int halo;
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  __device__ void operator()(int n, int h, int w, int c, const State& st) const {
+    if (h >= 1 && h < x.h - 1 && w >= 1 && w < x.w - 1) {
+      float he[3][V], ho[3][V];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        float a[V], b[V], d[V];
+        load_vec<T, V>(vptr<T>(x, n, h - 1 + r, w - 1, c), a);
+        load_vec<T, V>(vptr<T>(x, n, h - 1 + r, w, c), b);
+        load_vec<T, V>(vptr<T>(x, n, h - 1 + r, w + 1, c), d);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          he[r][i] = 0.3125f * a[i] + 0.625f * b[i] + 0.0625f * d[i];
+          ho[r][i] = 0.0625f * a[i] + 0.625f * b[i] + 0.3125f * d[i];
+        }
+      }
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.3125f * he[0][i] + 0.625f * he[1][i] + 0.0625f * he[2][i];
+      store_halo<T, V>(y, halo, n, 2 * h, 2 * w, c, o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.3125f * ho[0][i] + 0.625f * ho[1][i] + 0.0625f * ho[2][i];
+      store_halo<T, V>(y, halo, n, 2 * h, 2 * w + 1, c, o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.0625f * he[0][i] + 0.625f * he[1][i] + 0.3125f * he[2][i];
+      store_halo<T, V>(y, halo, n, 2 * h + 1, 2 * w, c, o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.0625f * ho[0][i] + 0.625f * ho[1][i] + 0.3125f * ho[2][i];
+      store_halo<T, V>(y, halo, n, 2 * h + 1, 2 * w + 1, c, o);
+      return;
+    }
+    // border block: same separable 3x3 -> 2x2 scheme with per-axis weights from the general
+    // tap generator (window clamped into the image)
+    (void)st;
+    const int hs = min(max(h - 1, 0), x.h - 3), ws = min(max(w - 1, 0), x.w - 3);
+    float wr[2][3], wc[2][3];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      int pos[4];
+      float wt[4];
+      up_taps(2 * h + a, x.h, pos, wt);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += (pos[k] == hs + t) ? wt[k] : 0.f;
+        wr[a][t] = acc;
+      }
+      up_taps(2 * w + a, x.w, pos, wt);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += (pos[k] == ws + t) ? wt[k] : 0.f;
+        wc[a][t] = acc;
+      }
+    }
+    float hv[2][3][V];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float a[V], b[V], d[V];
+      load_vec<T, V>(vptr<T>(x, n, hs + r, ws, c), a);
+      load_vec<T, V>(vptr<T>(x, n, hs + r, ws + 1, c), b);
+      load_vec<T, V>(vptr<T>(x, n, hs + r, ws + 2, c), d);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < V; ++i) hv[q][r][i] = wc[q][0] * a[i] + wc[q][1] * b[i] + wc[q][2] * d[i];
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float o[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          o[i] = wr[a][0] * hv[q][0][i] + wr[a][1] * hv[q][1][i] + wr[a][2] * hv[q][2][i];
+        store_halo<T, V>(y, halo, n, 2 * h + a, 2 * w + q, c, o);
+      }
+  }
+};
+
+template <typename T, int V>
+struct UpBwd2x2F {
+  static constexpr int OCC = 2;
+  __device__ void prefetch(int, int, int, int) const {}
+  View g, gx;  // g: [n, 2H, 2W, c] output gradient (g_halo == 0 only), gx: [n, H, W, c]
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  // (h2, w2) index 2x2 blocks of gx
+  __device__ void operator()(int n, int h2, int w2, int c, const State& st) const {
+    const int h = 2 * h2, w = 2 * w2;
+    if (h >= 2 && h + 1 <= gx.h - 3 && w >= 2 && w + 1 <= gx.w - 3) {
+      // horizontal pass: window columns 2w-2 .. 2w+5; input col w uses 0..5, col w+1 uses 2..7
+      const float k6[6] = {0.0625f, 0.3125f, 0.625f, 0.625f, 0.3125f, 0.0625f};
+      float acc[2][2][V];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[a][b][i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float h0[V], h1[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) { h0[i] = 0.f; h1[i] = 0.f; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float v[V];
+          load_vec<T, V>(vptr<T>(g, n, 2 * h - 2 + r, 2 * w - 2 + q, c), v);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            if (q < 6) h0[i] = fmaf(k6[q], v[i], h0[i]);
+            if (q >= 2) h1[i] = fmaf(k6[q - 2], v[i], h1[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          if (r < 6) { acc[0][0][i] = fmaf(k6[r], h0[i], acc[0][0][i]); acc[0][1][i] = fmaf(k6[r], h1[i], acc[0][1][i]); }
+          if (r >= 2) { acc[1][0][i] = fmaf(k6[r - 2], h0[i], acc[1][0][i]); acc[1][1][i] = fmaf(k6[r - 2], h1[i], acc[1][1][i]); }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) store_vec<T, V>(vptr_mut<T>(gx, n, h + a, w + b, c), acc[a][b]);
+      return;
+    }
+    // border block: the same 8x8 -> 2x2 separable scheme with per-axis weights derived from
+    // the forward tap generator (window clamped into the image; an odd trailing row/column of gx
+    // gets zero weights and is not stored)
+    (void)st;
+    const int hs = min(max(2 * h - 2, 0), g.h - 8), ws = min(max(2 * w - 2, 0), g.w - 8);
+    float wr[2][8], wc[2][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int pos[4];
+      float wt[4];
+      up_taps(hs + r, gx.h, pos, wt);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += (pos[k] == h + a) ? wt[k] : 0.f;
+        wr[a][r] = acc;
+      }
+      up_taps(ws + r, gx.w, pos, wt);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += (pos[k] == w + a) ? wt[k] : 0.f;
+        wc[a][r] = acc;
+      }
+    }
+    float acc[2][2][V];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[a][b][i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float h0[V], h1[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { h0[i] = 0.f; h1[i] = 0.f; }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float v[V];
+        load_vec<T, V>(vptr<T>(g, n, hs + r, ws + q, c), v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { h0[i] = fmaf(wc[0][q], v[i], h0[i]); h1[i] = fmaf(wc[1][q], v[i], h1[i]); }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        acc[0][0][i] = fmaf(wr[0][r], h0[i], acc[0][0][i]); acc[0][1][i] = fmaf(wr[0][r], h1[i], acc[0][1][i]);
+        acc[1][0][i] = fmaf(wr[1][r], h0[i], acc[1][0][i]); acc[1][1][i] = fmaf(wr[1][r], h1[i], acc[1][1][i]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+        if (h + a < gx.h && w + b < gx.w) store_vec<T, V>(vptr_mut<T>(gx, n, h + a, w + b, c), acc[a][b]);
+  }
+};
+
 // ---------------------------------------------------------------------------
 // modulated-conv side passes
 // ---------------------------------------------------------------------------
@@ -1005,9 +1217,15 @@ int otm_up(const otm_tensor* x, const otm_tensor* y, int32_t y_halo, otm_stream 
   OTM_REQUIRE(x->dtype == y->dtype, "up: dtype mismatch");
   bool vok = vec_ok(*x, 8) && vec_ok(*y, 8);
   int rc = OTM_OK;
+  static const int blk = [] { const char* e = getenv("OTM_UP_BLOCK"); return e ? atoi(e) : 1; }();
   OTM_DISPATCH_TV(x->dtype, vok, {
-    UpF<T, V> f{make_view(*x), make_view(*y), y_halo};
-    rc = launch_ew<V>(f, y->n, y->h, y->w, y->c, st);
+    if (blk && V == 8 && x->h >= 4 && x->w >= 4) {
+      Up2x2F<T, V> f{make_view(*x), make_view(*y), y_halo};
+      rc = launch_ew<V>(f, x->n, x->h, x->w, x->c, st);
+    } else {
+      UpF<T, V> f{make_view(*x), make_view(*y), y_halo};
+      rc = launch_ew<V>(f, y->n, y->h, y->w, y->c, st);
+    }
   });
   return rc;
 }
@@ -1020,9 +1238,15 @@ int otm_up_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* gx, otm_st
   OTM_REQUIRE(g->dtype == gx->dtype, "up_bwd: dtype mismatch");
   bool vok = vec_ok(*g, 8) && vec_ok(*gx, 8);
   int rc = OTM_OK;
+  static const int blk = [] { const char* e = getenv("OTM_UP_BLOCK"); return e ? atoi(e) : 1; }();
   OTM_DISPATCH_TV(g->dtype, vok, {
-    UpBwdF<T, V> f{make_view(*g), make_view(*gx), g_halo};
-    rc = launch_ew<V>(f, gx->n, gx->h, gx->w, gx->c, st);
+    if (blk && V == 8 && g_halo == 0 && gx->h >= 8 && gx->w >= 8) {
+      UpBwd2x2F<T, V> f{make_view(*g), make_view(*gx)};
+      rc = launch_ew<V>(f, gx->n, (gx->h + 1) / 2, (gx->w + 1) / 2, gx->c, st);
+    } else {
+      UpBwdF<T, V> f{make_view(*g), make_view(*gx), g_halo};
+      rc = launch_ew<V>(f, gx->n, gx->h, gx->w, gx->c, st);
+    }
   });
   return rc;
 }

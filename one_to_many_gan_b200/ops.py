@@ -63,6 +63,23 @@ def _sqsum(weight: torch.Tensor):
     return _cached(key, weight, lambda: K.weight_sqsum(weight.detach(), eq_scale(weight)))
 
 
+# Training fast path (training.backward_unit): the wgrad kernels ACCUMULATE, so they can add
+# straight into `weight.grad` -- a view of the optimiser's flat gradient arena that zero_grad()
+# cleared with one memset -- instead of a fresh zero-filled buffer that autograd then adds to
+# .grad (that was ~100 fill + ~150 add launches per iteration).  The Function returns None for
+# that weight.  Off by default so the stages stay ordinary autograd Functions.
+DIRECT_WEIGHT_GRADS = False
+
+
+def _wgrad_buffer(weight: torch.Tensor):
+    """(buffer the wgrad kernels accumulate into, value to hand back to autograd)."""
+    g = weight.grad
+    if DIRECT_WEIGHT_GRADS and g is not None and g.dtype == torch.float32 and g.is_contiguous():
+        return g, None
+    buf = torch.zeros_like(weight)
+    return buf, buf
+
+
 def nhwc(t: torch.Tensor, dtype=None) -> torch.Tensor:
     """API-boundary normalisation (plumbing): channel-stride-1 storage in `dtype`."""
     if dtype is not None and t.dtype != dtype:
@@ -123,8 +140,8 @@ class ConvFn(torch.autograd.Function):
             g = K.norm_act_bwd(g, y, None, act)
         gw = gb = gx = None
         if ctx.needs_input_grad[1]:
-            gw = torch.zeros_like(weight)
-            K.conv_wgrad(x, g, gw, k, k, pad, x_halo=x_halo, alpha=eq_scale(weight))
+            buf, gw = _wgrad_buffer(weight)
+            K.conv_wgrad(x, g, buf, k, k, pad, x_halo=x_halo, alpha=eq_scale(weight))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = K.channel_sum(g)
         if ctx.needs_input_grad[0]:
@@ -241,13 +258,13 @@ class ResBlockFn(torch.autograd.Function):
         g_raw2 = K.norm_act_bwd(g, raw2, st2, ACT_NONE)
         gw1 = gw2 = None
         if ctx.needs_input_grad[2]:
-            gw2 = torch.zeros_like(w2)
-            K.conv_wgrad(t, g_raw2, gw2, 3, 3, 1, x_halo=1, alpha=eq_scale(w2))
+            buf, gw2 = _wgrad_buffer(w2)
+            K.conv_wgrad(t, g_raw2, buf, 3, 3, 1, x_halo=1, alpha=eq_scale(w2))
         gt_p = K.conv_fwd(g_raw2, _pack(w2, g.dtype, True), f, 3, 3, 2)
         g_raw1 = K.norm_act_bwd(gt_p[:, :, 1 : 1 + h, 1 : 1 + w], raw1, st1, ACT_RELU, g_halo=1)
         if ctx.needs_input_grad[1]:
-            gw1 = torch.zeros_like(w1)
-            K.conv_wgrad(x, g_raw1, gw1, 3, 3, 1, x_halo=1, alpha=eq_scale(w1))
+            buf, gw1 = _wgrad_buffer(w1)
+            K.conv_wgrad(x, g_raw1, buf, 3, 3, 1, x_halo=1, alpha=eq_scale(w1))
         gx = None
         if ctx.needs_input_grad[0]:
             gx_p = K.conv_fwd(g_raw1, _pack(w1, g.dtype, True), f, 3, 3, 2)
@@ -284,7 +301,7 @@ def _modconv_bwd(gy, P, x, s, sig, weight, pad, x_halo, gadd, need_x, *, wfwd=No
     Returns (gx, ds, dw)."""
     n, cin, h, w = x.shape
     c = eq_scale(weight)
-    dw = torch.zeros_like(weight)
+    dw, dw_ret = _wgrad_buffer(weight)
     if P is None:
         P = torch.zeros((n, weight.shape[0]), dtype=torch.float32, device=x.device)
         K.conv_wgrad(x, gy, dw, 3, 3, pad, x_halo=x_halo, alpha=c, rs=sig, cs=s, wfwd=wfwd, P=P)
@@ -296,7 +313,7 @@ def _modconv_bwd(gy, P, x, s, sig, weight, pad, x_halo, gadd, need_x, *, wfwd=No
     gint = gxt_p[:, :, x_halo : x_halo + h, x_halo : x_halo + w] if x_halo else gxt_p
     gx, Q = K.mod_in(gint, x, s, g_halo=x_halo, gadd=gadd, relu_mask=relu_mask)
     ds = K.mod_bwd(weight.detach(), c, s, sig, _sqsum(weight), P, Q, dw)
-    return (gx if need_x else None), ds, dw
+    return (gx if need_x else None), ds, dw_ret
 
 
 class ModConvFn(torch.autograd.Function):

@@ -216,10 +216,12 @@ def unweighted(config, values):
 def backward_unit(loss):
     """loss.backward() with the loss-seed fast path (each term's lambda is already folded in)."""
     ops.UNIT_LOSS_GRADS = True
+    ops.DIRECT_WEIGHT_GRADS = True  # wgrad kernels accumulate straight into the gradient arenas
     try:
         loss.backward()
     finally:
         ops.UNIT_LOSS_GRADS = False
+        ops.DIRECT_WEIGHT_GRADS = False
 
 
 def discriminator_step(
