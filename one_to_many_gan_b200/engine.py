@@ -172,7 +172,8 @@ class TrainIteration:
             fake = sources.index_select(0, self.idx_dev[o : o + B])
             self.pool.index_copy_(0, self.idx_dev[o + B : o + 2 * B],
                                   generated.index_select(0, self.idx_dev[o + 2 * B : o + 3 * B]))
-        disc_loss, sign_real, sign_fake = training.discriminator_losses(self.D, fake, self.x[1])
+        disc_loss, sign_real, sign_fake = training.discriminator_losses(
+            self.D, fake, self.x[1], training.r1_gamma(self.cfg))
         training.backward_unit(disc_loss)
         self.losses[0:3].copy_(torch.cat([v.detach().reshape(1).float()
                                           for v in (disc_loss, sign_real, sign_fake)]))

@@ -122,16 +122,28 @@ def _floats(*tensors) -> list[float]:
 # device-side cores shared by the reference-signature step functions below and by the
 # CUDA-graph engine (engine.py).  No host synchronisation, no host RNG in here.
 # ---------------------------------------------------------------------------
-def discriminator_losses(discriminator, fake, real):
+def r1_gamma(config) -> float:
+    """`[optimisation] r1_gamma` (not a reference key; default 0 = the reference): weight of the
+    R1 gradient penalty on real images, BASELINE config 5."""
+    return float(config.get("optimisation", {}).get("r1_gamma", 0.0))
+
+
+def discriminator_losses(discriminator, fake, real, r1_gamma: float = 0.0):
     """(reference training.py:107-117) one 2B discriminator pass; returns
-    (disc_loss, sign_real, sign_fake) as 1-element tensors."""
+    (disc_loss, sign_real, sign_fake) as 1-element tensors.  r1_gamma > 0 adds
+    gamma/2 * E||grad_x D(real)||^2 (r1.py) to disc_loss."""
     batch = real.shape[0]
     scores = discriminator(torch.cat([fake, real], dim=0))
     fake_scores, real_scores = scores[:batch], scores[batch:]
     # disc_loss = (mse(real, 1) + mse(fake, 0)) / 2
     real_loss, sign_real = ops.lsgan(real_scores, 1.0, 0.5)
     fake_loss, sign_fake = ops.lsgan(fake_scores, 0.0, 0.5)
-    return real_loss + fake_loss, sign_real, -sign_fake
+    loss = real_loss + fake_loss
+    if r1_gamma > 0:
+        from . import r1
+
+        loss = loss + r1.r1_penalty(discriminator, real, r1_gamma)
+    return loss, sign_real, -sign_fake
 
 
 def styles_per_input(config) -> int:
@@ -252,7 +264,8 @@ def discriminator_step(
     real_shoemarks = next(shoemark_iter).to(device)
     augmented_real = ada(real_shoemarks)
 
-    disc_loss, sign_real, sign_fake = discriminator_losses(discriminator, augmented_fake, augmented_real)
+    disc_loss, sign_real, sign_fake = discriminator_losses(discriminator, augmented_fake, augmented_real,
+                                                           r1_gamma(config))
 
     ada_p.update_p(sign_real.reshape(()))
 

@@ -367,6 +367,15 @@ def discriminator_forward(P, x):
     return eq_conv2d(x, P["model.14.weight.weight"], P["model.14.bias"], padding=1)
 
 
+def r1_penalty(P, real, gamma):
+    """gamma/2 * mean_b ||grad_x sum D(x_b)||^2 on the reference Discriminator (BASELINE config
+    5; not in the reference's training step: plain autograd double backward is the oracle)."""
+    x = real.detach().clone().requires_grad_(True)
+    scores = discriminator_forward(P, x)
+    (gx,) = torch.autograd.grad(scores.sum(), x, create_graph=True)
+    return gx.square().sum(dim=(1, 2, 3)).mean() * (0.5 * gamma)
+
+
 def style_extractor_forward(P, x):
     x = _patch_trunk(P, x)
     x = x.mean(dim=(2, 3))  # AdaptiveAvgPool2d(1) + Flatten, builder.py:314-315
@@ -555,6 +564,7 @@ class Hyper:
     mapping_network_learning_rate: float = 2e-5
     adam_betas: tuple[float, float] = (0.5, 0.99)
     add_latent_noise: bool = False
+    r1_gamma: float = 0.0  # extension (BASELINE config 5); 0 = the reference
     ada_target: float = 0.6
     ada_e: int = 256
     ada_adjustment_size: float = 5.12e-4
@@ -605,6 +615,8 @@ class Trainer:
         real_loss = F.mse_loss(real_scores, torch.ones_like(real_scores))
         fake_loss = F.mse_loss(fake_scores, torch.zeros_like(fake_scores))
         loss = (real_loss + fake_loss) / 2
+        if h.r1_gamma > 0:
+            loss = loss + r1_penalty(D, real, h.r1_gamma)
         sign_real = torch.sign(real_scores.detach() * 2 - 1).mean()
         sign_fake = -torch.sign(fake_scores.detach() * 2 - 1).mean()
         self.ada_p.update_p(float(sign_real))

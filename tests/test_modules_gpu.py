@@ -281,3 +281,54 @@ def test_styles_per_input_matches_oracle_fp32(use_engine):
         for k in live:
             e = relerr(mine[net][k].grad, ref64[0][1][net][k])
             assert e <= max(3 * floors[k], 3 * net_floor, 5e-3), (net, k, e, floors[k], net_floor)
+
+
+def test_r1_penalty_matches_oracle_fp32():
+    """BASELINE config 5: R1 gradient penalty on real images (double backward through D).
+    Penalty value and every D parameter gradient of (LSGAN + R1) against the fp64 oracle
+    (autograd double backward on the reference Discriminator)."""
+    from one_to_many_gan_b200 import r1, training
+    from one_to_many_gan_b200.optim import FlatAdam
+
+    case, gamma = "down1", 10.0
+    arch, P, D, G, M, S = build(case, torch.float32)
+    b = CASES[case]["batch"]
+    shape = (b, 1, *arch.image_size)
+    real = images(shape, 200)
+    P64 = {k: v.double() for k, v in P["D"].items()}
+    leaf = {k: (v.clone().requires_grad_(True) if not rp.is_buffer(k) else v) for k, v in P64.items()}
+    pen_ref = rp.r1_penalty(leaf, real.double(), gamma)
+    names = [k for k in leaf if not rp.is_buffer(k)]
+    g_ref = dict(zip(names, torch.autograd.grad(pen_ref, [leaf[k] for k in names], allow_unused=True)))
+    pen = r1.r1_penalty(D, real.cuda(), gamma)
+    assert abs(pen.item() - pen_ref.item()) <= 2e-4 * abs(pen_ref.item()), (pen.item(), pen_ref.item())
+    for p in D.parameters():
+        p.grad = None
+    pen.backward()
+    for k, p in D.named_parameters():
+        want = g_ref[k]
+        if want is None or want.abs().max() == 0:  # the output bias does not enter grad_x D
+            assert p.grad is None or p.grad.abs().max().item() <= 1e-6 * max(1.0, pen_ref.item()), k
+            continue
+        if ("D", k) in DEAD:
+            continue
+        assert relerr(p.grad, want) < 2e-3, (k, relerr(p.grad, want))
+
+    # the full D step with the penalty: logged loss and gradients vs the oracle step
+    torch.manual_seed(123)
+    random.seed(123)
+    tr = rp.Trainer(arch, rp.Hyper(batch_size=b, r1_gamma=gamma), P, dtype=torch.float64)
+    d_ref = tr.discriminator_step(images(shape, 100), images(shape, 200))
+    cfg = _cfg(case)
+    cfg["optimisation"]["r1_gamma"] = gamma
+    oD = FlatAdam(D.parameters(), 2e-3, (0.5, 0.99))
+    torch.manual_seed(123)
+    random.seed(123)
+    d = training.discriminator_step(cfg, torch.device("cuda"), D, G, M, oD, iter([images(shape, 100)]),
+                                    iter([images(shape, 200)]), training.ImageBuffer(100),
+                                    training.IdentityAugment(), training.ADAp(256, 5.12e-4, b, 0.6))
+    assert abs(d[0] - d_ref[0]) <= 5e-4 * abs(d_ref[0]), (d, d_ref)
+    for k, p in D.named_parameters():
+        if ("D", k) in DEAD:
+            continue
+        assert relerr(p.grad, tr.last_grads["D"][k]) < 5e-3, k
