@@ -106,3 +106,27 @@ def test_engine_bf16_graph_runs():
         assert all(map(lambda v: v == v and abs(v) < 1e6, out.values())), out
         assert out != prev
         prev = out
+
+
+def test_engine_bf16_graph_runs_configs_4_and_5():
+    """BASELINE configs 4 + 5 through the captured graph in bf16 mode: K = 4 styles per input
+    and the R1 penalty (double backward through D) every step; finite, changing losses."""
+    from one_to_many_gan_b200.engine import TrainIteration
+
+    size, batch = (32, 32), 2
+    cfg = _cfg(batch, size, 100)
+    cfg["training"]["styles_per_input"] = 4
+    cfg["optimisation"]["r1_gamma"] = 10.0
+    D, G, M, S, (oD, oG, oM, oS) = _build(size, 16, 3, torch.bfloat16)
+    eng = TrainIteration(cfg, torch.device("cuda"), D, G, M, S, oD, oG, oM, oS, warmup=1)
+    torch.manual_seed(3)
+    random.seed(3)
+    shape = (batch, 1, *size)
+    prev = None
+    for it in range(4):
+        eng.load_inputs(*[_images(shape, 50 + 4 * it + j) for j in range(4)])
+        out = eng.run()
+        assert all(map(lambda v: v == v and abs(v) < 1e6, out.values())), out
+        assert out != prev
+        prev = out
+    assert eng.graph is not None
