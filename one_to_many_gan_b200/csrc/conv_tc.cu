@@ -1031,6 +1031,256 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ---------------------------------------------------------------------------
+// Transposed pair kernel ("weights as the M operand") for BN = 128 output channels.
+// The pair kernel above issues two 128x128x16 MMAs per weight tile; each reads 4 KB + 4 KB of
+// operands from shared memory per 64 tensor-pipe cycles = 128 B/clk, which IS the SM's
+// shared-memory bandwidth: its main loop saturates at ~1.1 PFLOP/s (the 256-channel layers, N =
+// 256, reach 1.2-1.4).  Here D^T = W * X^T: M = 128 output channels (the weight tile, K-major),
+// N = 256 pixels = the two vertically adjacent 16x8 tiles loaded as ONE (32 + KS - 1)-row box,
+// so one 128x256x16 MMA reads 4 KB + 8 KB per 128 cycles = 96 B/clk.
+// The accumulator is transposed (TMEM lane = output channel, column = pixel): the epilogue
+// applies the per-channel scale/bias as per-thread scalars and transposes through the
+// SWIZZLE_128B staging tile with 2-byte stores; residual add, TMA store and the reflect halo
+// then work on staged pixel rows.
+// ---------------------------------------------------------------------------
+template <int KS, int NA, int NB>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmY, TcFwdPP pp) {
+  const TcFwdP& p = pp.p;
+  constexpr int BN = 128;  // output channels per tile (the MMA's M)
+  constexpr int TW = 8, TH = 16;
+  constexpr int A_SLOT = (2 * TH + KS - 1) * TW * 128;  // bytes: the pair's pixel rows, one box
+  constexpr int B_SLOT = BN * 128;
+  constexpr int SUB_BYTES = 128 * 128;
+  constexpr int TILE_BYTES = (BN / 64) * SUB_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* ringA = smem;
+  uint8_t* ringB = ringA + NA * A_SLOT;
+  uint8_t* stage_out = ringB + NB * B_SLOT;
+  uint64_t* bars = (uint64_t*)(stage_out + TILE_BYTES);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + NA;
+  uint64_t* fullB = emptyA + NA;
+  uint64_t* emptyB = fullB + NB;
+  uint64_t* tmem_full = emptyB + NB;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int cin_chunks = p.cin / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(smem_u32(&fullA[i]), 1); mbar_init(smem_u32(&emptyA[i]), 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&fullB[i]), 1); mbar_init(smem_u32(&emptyB[i]), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  auto decode = [&](int t, int& n, int& h0, int& w0, int& o0) {
+    const int ct = t % pp.cout_tiles;
+    const int rest = t / pp.cout_tiles;
+    const int pt = rest % pp.tiles_per_img;
+    n = rest / pp.tiles_per_img;
+    h0 = (pt / p.tiles_w) * (2 * TH);  // pt indexes PAIRS of tile rows
+    w0 = (pt % p.tiles_w) * TW;
+    o0 = ct * BN;
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    int ga = 0, gb = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int wrow = n * p.w_rows_per_sample + o0;
+      for (int cc = 0; cc < cin_chunks; ++cc) {
+        for (int s = 0; s < KS; ++s, ++ga) {
+          const int sa = ga % NA;
+          mbar_wait(smem_u32(&emptyA[sa]), ((ga / NA) & 1) ^ 1);
+          if (lane == 0) {
+            const uint32_t bar = smem_u32(&fullA[sa]);
+            mbar_expect_tx(bar, A_SLOT);
+            tma_load_4d(smem_u32(ringA + sa * A_SLOT), &tmA, bar, cc * 64, w0 + s + p.coord_off,
+                        h0 + p.coord_off, n);
+          }
+          __syncwarp();
+          for (int r = 0; r < KS; ++r, ++gb) {
+            const int sb = gb % NB;
+            mbar_wait(smem_u32(&emptyB[sb]), ((gb / NB) & 1) ^ 1);
+            if (lane == 0) {
+              const uint32_t bar = smem_u32(&fullB[sb]);
+              mbar_expect_tx(bar, B_SLOT);
+              tma_load_2d(smem_u32(ringB + sb * B_SLOT), &tmB, bar, (r * KS + s) * p.cin + cc * 64, wrow);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc2 = make_idesc(128, 256, 0, 0);  // both 16x8 tiles
+    constexpr uint32_t idesc1 = make_idesc(128, 128, 0, 0);  // lower tile out of range
+    int ga = 0, gb = 0, lt = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      uint32_t idesc;
+      {
+        int n, h0, w0, o0;
+        decode(t, n, h0, w0, o0);
+        idesc = (h0 + TH) < p.y.h ? idesc2 : idesc1;
+      }
+      mbar_wait(smem_u32(&tmem_empty[buf]), ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * 256);
+      uint32_t first = 1;
+      for (int cc = 0; cc < cin_chunks; ++cc) {
+        for (int s = 0; s < KS; ++s, ++ga) {
+          const int sa = ga % NA;
+          mbar_wait(smem_u32(&fullA[sa]), (ga / NA) & 1);
+          for (int r = 0; r < KS; ++r, ++gb) {
+            const int sb = gb % NB;
+            mbar_wait(smem_u32(&fullB[sb]), (gb / NB) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t dpx = make_desc(smem_u32(ringA + sa * A_SLOT + r * (TW * 128)), 16, 1024);
+              const uint64_t dw = make_desc(smem_u32(ringB + sb * B_SLOT), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(tacc, dw + (uint64_t)(k * 2), dpx + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(smem_u32(&emptyB[sb]));
+              if (r == KS - 1) umma_commit(smem_u32(&emptyA[sa]));
+              if (r == KS - 1 && s == KS - 1 && cc == cin_chunks - 1)
+                umma_commit(smem_u32(&tmem_full[buf]));
+            }
+            first = 0;
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int wq = warp - 4;
+    const int te = threadIdx.x - 128;
+    const int m = wq * 32 + lane;  // output channel (TMEM lane) in phase 1, pixel in phase 2
+    int lt = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int buf = lt & 1;
+      const float scale = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + m] : 1.f);
+      const float bias = p.bias ? p.bias[o0 + m] : 0.f;
+      mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
+      tc_fence_after();
+      const int nhalf = (h0 + TH) < p.y.h ? 2 : 1;
+      // staging address pieces of this thread's channel: [sub-tile of 64 ch][pixel][128 B]
+      uint8_t* const chan_base = stage_out + (m >> 6) * SUB_BYTES + (m & 7) * 2;
+      const int chunk = (m & 63) >> 3;
+#pragma unroll 1
+      for (int half = 0; half < nhalf; ++half) {
+        const int hh0 = h0 + half * TH;
+        const uint32_t tacc =
+            tmem_base + (uint32_t)(buf * 256 + half * 128) + ((uint32_t)(wq * 32) << 16);
+        // the previous TMA store must have finished reading the staging tile
+        if (te == 0) tma_store_wait_read();
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+#pragma unroll 1
+        for (int j2 = 0; j2 < 4; ++j2) {
+          float v[32];
+          tmem_ld32(tacc + (uint32_t)(j2 * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], scale, bias);
+          act_fwd_vec<32>(v, p.act);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int q = j2 * 32 + i;  // pixel of this half-tile
+            *reinterpret_cast<__nv_bfloat16*>(chan_base + q * 128 + ((chunk ^ (q & 7)) << 4)) =
+                __float2bfloat16_rn(v[i]);
+          }
+        }
+        tc_fence_before();
+        if (half == nhalf - 1) mbar_arrive(smem_u32(&tmem_empty[buf]));  // accumulator drained
+        // phase 2: thread = pixel row of the staged tile
+        const int oh = hh0 + m / TW, ow = w0 + m % TW;
+        const bool valid = (oh < p.y.h) && (ow < p.y.w);
+        uint8_t* myrow = stage_out + m * 128;
+        const int sw = m & 7;
+        if (p.res.ptr) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");  // staged tile complete
+          if (valid) {
+#pragma unroll 4
+            for (int piece = 0; piece < BN / 8; ++piece) {
+              uint4* sp = reinterpret_cast<uint4*>(myrow + (piece >> 3) * SUB_BYTES +
+                                                   (((piece & 7) ^ sw) << 4));
+              uint4 a = *sp;
+              const uint4 b = *reinterpret_cast<const uint4*>(
+                  vptr<__nv_bfloat16>(p.res, n, oh, ow, o0 + piece * 8));
+              __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a);
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+                a2[e] = __floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y);
+              }
+              *sp = a;
+            }
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (te == 0 && hh0 < p.y.h) {
+#pragma unroll
+          for (int sb = 0; sb < BN / 64; ++sb)
+            tma_store_4d(&tmY, smem_u32(stage_out + sb * SUB_BYTES), o0 + sb * 64, w0, hh0, n);
+          tma_store_commit();
+        }
+        if (p.y_halo > 0 && valid) {
+          int hs[3], ws[3];
+          const int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
+          const int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
+          if (nh * nw > 1) {
+            for (int piece = 0; piece < BN / 8; ++piece) {
+              const uint4 val = *reinterpret_cast<const uint4*>(
+                  myrow + (piece >> 3) * SUB_BYTES + (((piece & 7) ^ sw) << 4));
+              for (int a = 0; a < nh; ++a)
+                for (int b = 0; b < nw; ++b)
+                  if (a + b > 0)
+                    *reinterpret_cast<uint4*>(
+                        vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + piece * 8)) = val;
+            }
+          }
+        }
+      }
+    }
+    if (te == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // wgrad kernel
 // ---------------------------------------------------------------------------
 struct TcWgP {
@@ -1521,6 +1771,22 @@ static int launch_fwd_rr2(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   return OTM_OK;
 }
 
+template <int KS, int NA, int NB>
+static int launch_fwd_rr2t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                           const TcFwdPP& pp, int ctas, cudaStream_t st) {
+  constexpr int smem = NA * (32 + KS - 1) * 8 * 128 + NB * 128 * 128 + 2 * 128 * 128 + 1024 + 512;
+  static_assert(smem <= 227 * 1024, "transposed pair conv kernel exceeds shared memory");
+  auto kern = conv_tc_fwd_rr2t_kernel<KS, NA, NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
 int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   const int Ho = a->y.h, Wo = a->y.w, cout = a->y.c, cin = a->x.c;
   // pixel tile shape: 128 = TW x TH, minimise the number of tiles (ties -> squarer)
@@ -1591,6 +1857,14 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
       pp.tiles_per_img = ((tile_rows + 1) / 2) * tiles_w8;
       pp.total_tiles = (int)pairs;
       int c2 = num_sms();
+      static const int rr2t = [] { const char* e = getenv("OTM_RR2T"); return e ? atoi(e) : 1; }();
+      if (rr2t && BN == 128) {  // weights as the M operand, 256-pixel N operand
+        CUtensorMap tmA2;       // one box for both tiles of the pair
+        rc = make_act_map(&tmA2, a->x, a->x_halo, 8, 32 + a->kh - 1);
+        if (rc) return rc;
+        if (a->kh == 3) return launch_fwd_rr2t<3, 2, 6>(tmA2, tmB, tmY, pp, c2, st);
+        return launch_fwd_rr2t<4, 2, 6>(tmA2, tmB, tmY, pp, c2, st);
+      }
       if (a->kh == 3) {
         if (BN == 64) return launch_fwd_rr2<64, 3, 3, 8>(tmA, tmB, tmY, pp, c2, st);
         return launch_fwd_rr2<128, 3, 2, 6>(tmA, tmB, tmY, pp, c2, st);

@@ -111,6 +111,42 @@ def test_conv_tc_matches_simt(K, case):
     assert relerr(a.float(), b.float()) < 4e-3, case
 
 
+PAIR_CASES = [
+    # cin, cout, k, pad, x_halo, H, W, n : large enough (>= 2 x 148 tile pairs) for the persistent
+    # PAIR kernels the bench-size layers run on (two 16x8 pixel tiles per CTA step)
+    (128, 128, 3, 1, 1, 64, 64, 20),   # res-block / modulated res-block conv
+    (128, 128, 3, 2, 0, 64, 64, 20),   # its dgrad: 66x66 output, odd number of tile rows
+    (64, 128, 4, 1, 0, 63, 63, 24),    # discriminator 4x4
+    (128, 64, 3, 1, 0, 64, 64, 20),    # BN = 64 pair kernel
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_tc_pair_kernels(K, case):
+    """tcgen05 pair kernels (incl. the transposed 256-pixel-operand kernel) vs the FFMA path on
+    identical bf16 operands: plain, and with per-sample weights + demodulation scale + bias +
+    ReLU + residual + reflect halo."""
+    cin, cout, k, pad, halo, H, W, n = case
+    x = nhwc(rnd(n, cin, H, W, seed=21), torch.bfloat16, halo)
+    w = rnd(cout, cin, k, k, seed=22)
+    alpha = 1 / math.sqrt(cin * k * k)
+    wp = K.weight_pack(w, alpha, torch.bfloat16)
+    a = K.conv_fwd(x, wp, cout, k, k, pad, x_halo=halo, path=K.PATH_TC)
+    b = K.conv_fwd(x, wp, cout, k, k, pad, x_halo=halo, path=K.PATH_SIMT)
+    assert relerr(a.float(), b.float()) < 4e-3, ("plain", case)
+    s = torch.rand(n, cin, device="cuda") + 0.5
+    rs = torch.rand(n, cout, device="cuda") + 0.5
+    bias = rnd(cout, seed=23)
+    res = nhwc(rnd(*a.shape, seed=24), torch.bfloat16)
+    wps = K.weight_pack(w, alpha, torch.bfloat16, cs=s, nb=n)
+    kw = dict(x_halo=halo, row_scale=rs, bias=bias, act=K.ACT_RELU, residual=res, y_halo=1,
+              per_sample=True)
+    a = K.conv_fwd(x, wps, cout, k, k, pad, path=K.PATH_TC, **kw)
+    b = K.conv_fwd(x, wps, cout, k, k, pad, path=K.PATH_SIMT, **kw)
+    assert relerr(a.float(), b.float()) < 4e-3, ("epilogue", case)
+    assert torch.equal(K.padded_view(a, 1).float(), F.pad(a.float(), (1,) * 4, mode="reflect")), case
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("per_sample", [False, True])
 def test_conv_per_sample_weights(K, dtype, per_sample):
