@@ -215,11 +215,11 @@ def dominant_kernel_roofline(device):
     pk, how = peaks()
     ach = flops / ms / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from `ncu --set full`
-    # (profiles/r1_ncu_conv_tc_fwd_rr2.md); algorithmic bytes = x (107 MB) + per-sample weights
-    # (28 MB) + y (107 MB) = 242 MB, part of y stays in the 126 MB L2.
-    traffic = 201.7e6
+    # (profiles/r1_ncu_conv_tc_fwd_rr2t.md: 135.7 MB read + 65.8 MB written); algorithmic bytes =
+    # x (107 MB) + per-sample weights (28 MB) + y (107 MB) = 242 MB, part of y stays in the L2.
+    traffic = 201.6e6
     return {"bound": "tensor",
-            "kernel": "conv_tc_fwd_rr2_kernel<128,3,2,6>: modulated 3x3 128->128 @64x64, n=96 "
+            "kernel": "conv_tc_fwd_rr2t_kernel<3,2,6>: modulated 3x3 128->128 @64x64, n=96 "
                       "(+demodulation scale, ReLU, reflect halo)",
             "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "peak_source": how + " burst",
             "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4), "traffic": traffic,
