@@ -650,6 +650,201 @@ wgrad_cin1_mma_kernel(WgradP p, int tiles_w, int tiles_per_img, int total_tiles)
 }
 
 // ---------------------------------------------------------------------------
+// Cout == 1, Cin == 64 layers (the generator's 7x7 output conv, the dgrad of the 4x4 image-side
+// convs) in bf16 mode on mma.sync.  A single output channel leaves N = 1, so the filter's
+// HORIZONTAL taps become the N dimension:
+//     z[q][s] = sum_{r, ch} X[row + r][q][ch] * w[r][s][ch]      (M = 16 patch columns q,
+//     y[px]   = sum_s z[px + s][s]                                 N = 8 >= KS, K = KS * 64)
+// A fragments = ldmatrix of the [pixel][channel] bf16 patch (row pitch 144 B, conflict-free),
+// each patch-row fragment is reused by up to KS output rows; the weight fragments stay in
+// registers.  wgrad is the transpose: D[ch][s] += sum_q X[row + r][q][ch] * dy[row][q - s]
+// (A = ldmatrix.trans of the same patch, B gathered from a zero-padded dy row).
+// Tile: 16 output rows x (16*MW - KS + 1) output columns, patch (16 + KS - 1) x 16*MW pixels.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+template <int KS, int MW>
+struct Cout1Geom {
+  static constexpr int TH = 16, PH = TH + KS - 1, PWC = 16 * MW, TWO = PWC - KS + 1, CP = 72;
+  static constexpr int PATCH_ELEMS = (PH * PWC + 16) * CP;  // + 16 zero rows: ldmatrix overrun
+};
+
+// stage the (PH x PWC) x 64-channel patch of tile (oh0, ow0) into shared memory (zero outside)
+template <int KS, int MW>
+__device__ __forceinline__ void cout1_load_patch(const View& x, int x_halo, int pad, int n, int oh0,
+                                                 int ow0, __nv_bfloat16* xs) {
+  using G = Cout1Geom<KS, MW>;
+  const int H = x.h, W = x.w;
+  for (int e = threadIdx.x; e < G::PH * G::PWC * 8; e += 256) {
+    const int c8 = e & 7, q = e >> 3;
+    const int pw = q % G::PWC, ph = q / G::PWC;
+    const int ih = oh0 + ph - pad, iw = ow0 + pw - pad;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ih >= -x_halo && ih < H + x_halo && iw >= -x_halo && iw < W + x_halo)
+      val = *reinterpret_cast<const uint4*>(vptr<__nv_bfloat16>(x, n, ih, iw, c8 * 8));
+    *reinterpret_cast<uint4*>(xs + q * G::CP + c8 * 8) = val;
+  }
+}
+
+template <typename TO, int KS, int MW>
+__global__ void __launch_bounds__(256, MW == 1 ? 3 : 1)
+conv_cout1_mma_kernel(ConvP p, int tiles_w, int tiles_per_img, int total_tiles) {
+  using G = Cout1Geom<KS, MW>;
+  extern __shared__ __align__(16) unsigned char c1m_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(c1m_smem);
+  float* zs = reinterpret_cast<float*>(xs + G::PATCH_ELEMS);  // [8 warps][2 rows][PWC][8]
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int g = lane >> 2, q4 = lane & 3;
+  for (int e = threadIdx.x; e < 16 * G::CP; e += 256) xs[G::PH * G::PWC * G::CP + e] = __float2bfloat16_rn(0.f);
+  // weight fragments: B[k = (r, ch)][n = s] = w[(r, s)][ch]; columns s >= KS are zero
+  uint32_t bf[KS][4][2];
+  {
+    const __nv_bfloat16* wbase = (const __nv_bfloat16*)p.w;  // [tap][cin]
+#pragma unroll
+    for (int r = 0; r < KS; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = c * 16 + q4 * 2 + h * 8;
+          uint32_t v = 0;
+          if (g < KS) v = *reinterpret_cast<const uint32_t*>(wbase + (r * KS + g) * 64 + ch);
+          bf[r][c][h] = v;
+        }
+  }
+  float* zw = zs + warp * (2 * G::PWC * 8);
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * G::TH, ow0 = (tile % tiles_w) * G::TWO;
+    __syncthreads();
+    cout1_load_patch<KS, MW>(p.x, p.x_halo, p.pad, n, oh0, ow0, xs);
+    __syncthreads();
+    float acc[2][MW][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < MW; ++b)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
+    const int py0 = warp * 2;  // this warp's two output rows
+#pragma unroll
+    for (int rr = 0; rr < KS + 1; ++rr) {  // patch rows py0 .. py0 + KS
+      const int R = py0 + rr;
+#pragma unroll
+      for (int mt = 0; mt < MW; ++mt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t a[4];
+          const int row = R * G::PWC + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          ldmatrix_x4(a, xs + row * G::CP + c * 16 + (lane >> 4) * 8);
+          if (rr < KS) mma_16816(acc[0][mt], a, bf[rr < KS ? rr : 0][c]);          // row py0,   r = rr
+          if (rr >= 1) mma_16816(acc[1][mt], a, bf[rr >= 1 ? rr - 1 : 0][c]);      // row py0+1, r = rr-1
+        }
+    }
+    // z -> shared, then y[px] = sum_s z[px + s][s]
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int mt = 0; mt < MW; ++mt) {
+        float* zr = zw + (a * G::PWC + mt * 16) * 8;
+        *reinterpret_cast<float2*>(zr + g * 8 + q4 * 2) = make_float2(acc[a][mt][0], acc[a][mt][1]);
+        *reinterpret_cast<float2*>(zr + (g + 8) * 8 + q4 * 2) = make_float2(acc[a][mt][2], acc[a][mt][3]);
+      }
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int oh = oh0 + py0 + a;
+      for (int px = lane; px < G::TWO; px += 32) {
+        const int ow = ow0 + px;
+        if (oh < p.y.h && ow < p.y.w) {
+          float v = 0.f;
+#pragma unroll
+          for (int sx = 0; sx < KS; ++sx) v += zw[(a * G::PWC + px + sx) * 8 + sx];
+          v *= p.alpha;
+          if (p.row_scale) v *= p.row_scale[n];
+          if (p.bias) v += p.bias[0];
+          v = act_fwd(v, p.act);
+          if (p.res.ptr) v += to_f(*vptr<TO>(p.res, n, oh, ow, 0));
+          float vv[1] = {v};
+          store_halo<TO, 1>(p.y, p.y_halo, n, oh, ow, 0, vv);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <typename TDY, int KS, int MW>
+__global__ void __launch_bounds__(256, MW == 1 ? 3 : 1)
+wgrad_cout1_mma_kernel(WgradP p, int tiles_w, int tiles_per_img, int total_tiles) {
+  using G = Cout1Geom<KS, MW>;
+  constexpr int DYP = G::PWC + 16;  // dy row: 8 zeros | TWO values | zeros
+  constexpr int RH = (KS + 1) / 2;  // filter rows per warp half
+  extern __shared__ __align__(16) unsigned char w1m_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(w1m_smem);
+  __nv_bfloat16* dys = xs + G::PATCH_ELEMS;  // [16 rows][DYP]
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int ct = warp & 3;         // 16-channel tile (M)
+  const int r0 = (warp >> 2) * RH;  // this warp's filter rows r0 .. r0 + RH - 1
+  for (int e = threadIdx.x; e < 16 * G::CP; e += 256) xs[G::PH * G::PWC * G::CP + e] = __float2bfloat16_rn(0.f);
+  float acc[RH][4];
+#pragma unroll
+  for (int a = 0; a < RH; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[a][e] = 0.f;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tile = t - n * tiles_per_img;
+    const int oh0 = (tile / tiles_w) * G::TH, ow0 = (tile % tiles_w) * G::TWO;
+    __syncthreads();
+    cout1_load_patch<KS, MW>(p.x, p.x_halo, p.pad, n, oh0, ow0, xs);
+    for (int e = threadIdx.x; e < 16 * DYP; e += 256) {
+      const int py = e / DYP, c = e % DYP - 8;
+      float v = 0.f;
+      const int oh = oh0 + py, ow = ow0 + c;
+      if (c >= 0 && c < G::TWO && oh < p.dy.h && ow < p.dy.w) v = to_f(*vptr<TDY>(p.dy, n, oh, ow, 0));
+      dys[e] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int R = 0; R < G::PH; ++R) {
+#pragma unroll
+      for (int mt = 0; mt < MW; ++mt) {
+        // A[m = ch][k = q]: transposed load of patch rows q (k) x channels (m)
+        uint32_t a[4];
+        const int row = R * G::PWC + mt * 16 + (lane & 7) + (lane >> 4) * 8;
+        ldmatrix_x4_trans(a, xs + row * G::CP + ct * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+        for (int rl = 0; rl < RH; ++rl) {
+          const int r = r0 + rl, py = R - r;
+          if (r < KS && py >= 0 && py < G::TH) {
+            // B[k = q][n = s] = dy[py][q - s]
+            const __nv_bfloat16* d = dys + py * DYP + 8 + mt * 16 + q4 * 2 - g;
+            uint32_t b[2];
+            b[0] = pack_bf16(d[0], d[1]);
+            b[1] = pack_bf16(d[8], d[9]);
+            mma_16816(acc[rl], a, b);
+          }
+        }
+      }
+    }
+  }
+  const int taps = KS * KS;
+#pragma unroll
+  for (int rl = 0; rl < RH; ++rl)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = r0 + rl, sx = q4 * 2 + (e & 1), ch = ct * 16 + g + (e >> 1) * 8;
+      if (r < KS && sx < KS) atomicAdd(p.dw + ch * taps + r * KS + sx, acc[rl][e] * p.alpha);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // wgrad, generic tile: M = 64 couts, N = 64 flattened (r,s,i), K = pixels of one sample
 // chunk.  grid = (ceil(ktot/64), ceil(cout/64), n * splits); atomicAdd into dw.
 // ---------------------------------------------------------------------------
@@ -1088,6 +1283,35 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
     OTM_LAUNCH_CHECK();
     return OTM_OK;
   }
+  static const int thin_mma1 = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
+  if (thin_mma1 && p.cout == 1 && p.cin == 64 && in_bf && a->kh == a->kw && (a->kh == 4 || a->kh == 7) &&
+      a->w_batch_stride == 0 && vec_ok(a->x, 8) && a->y.h * a->y.w >= 256) {
+    static const int mw = [] { const char* e = getenv("OTM_COUT1_MW"); return e ? atoi(e) : 1; }();
+#define OTM_C1M(TO, KS, MW)                                                                      \
+  do {                                                                                            \
+    using G = Cout1Geom<KS, MW>;                                                                  \
+    const size_t smem = (size_t)G::PATCH_ELEMS * 2 + (size_t)8 * 2 * G::PWC * 8 * sizeof(float);  \
+    const int tiles_w = (a->y.w + G::TWO - 1) / G::TWO, tiles_h = (a->y.h + G::TH - 1) / G::TH;   \
+    const int per_img = tiles_w * tiles_h, total = per_img * a->y.n;                              \
+    auto kern = conv_cout1_mma_kernel<TO, KS, MW>;                                                \
+    static bool set_ = false;                                                                     \
+    if (!set_) {                                                                                  \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                          (int)smem));                                            \
+      set_ = true;                                                                                \
+    }                                                                                             \
+    int ctas = num_sms() * (MW == 1 ? 3 : 1);                                                     \
+    if (ctas > total) ctas = total;                                                               \
+    kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);                                    \
+  } while (0)
+#define OTM_C1M_KS(TO, MW) do { if (a->kh == 7) OTM_C1M(TO, 7, MW); else OTM_C1M(TO, 4, MW); } while (0)
+    if (out_bf) { if (mw == 1) OTM_C1M_KS(__nv_bfloat16, 1); else OTM_C1M_KS(__nv_bfloat16, 2); }
+    else { if (mw == 1) OTM_C1M_KS(float, 1); else OTM_C1M_KS(float, 2); }
+#undef OTM_C1M_KS
+#undef OTM_C1M
+    OTM_LAUNCH_CHECK();
+    return OTM_OK;
+  }
   if (p.cout == 1 && p.cin % 64 == 0 && a->kh == a->kw && (a->kh == 4 || a->kh == 7) &&
       vec_ok(a->x, 8) && a->y.h * a->y.w >= 256) {
 #define OTM_C1(TI, TO) \
@@ -1182,6 +1406,36 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
       if (yb) OTM_WC1(__nv_bfloat16, 4, 128); else OTM_WC1(float, 4, 128);
     }
 #undef OTM_WC1
+    OTM_LAUNCH_CHECK();
+    return OTM_OK;
+  }
+  // single output channel, 64 input channels, bf16 activations: mma.sync kernel
+  static const int thin_mma1 = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
+  if (thin_mma1 && p.cout == 1 && p.cin == 64 && a->x.dtype == OTM_BF16 && a->kh == a->kw &&
+      (a->kh == 4 || a->kh == 7) && !a->rs && !a->cs && vec_ok(a->x, 8) && a->dy.h * a->dy.w >= 256) {
+    static const int mw = [] { const char* e = getenv("OTM_COUT1_MW"); return e ? atoi(e) : 1; }();
+#define OTM_W1M(TDY, KS, MW)                                                                     \
+  do {                                                                                            \
+    using G = Cout1Geom<KS, MW>;                                                                  \
+    const size_t smem = (size_t)G::PATCH_ELEMS * 2 + (size_t)16 * (G::PWC + 16) * 2;              \
+    const int tiles_w = (a->dy.w + G::TWO - 1) / G::TWO, tiles_h = (a->dy.h + G::TH - 1) / G::TH; \
+    const int per_img = tiles_w * tiles_h, total = per_img * a->dy.n;                             \
+    auto kern = wgrad_cout1_mma_kernel<TDY, KS, MW>;                                              \
+    static bool set_ = false;                                                                     \
+    if (!set_) {                                                                                  \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                          (int)smem));                                            \
+      set_ = true;                                                                                \
+    }                                                                                             \
+    int ctas = num_sms() * (MW == 1 ? 3 : 1);                                                     \
+    if (ctas > total) ctas = total;                                                               \
+    kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);                                    \
+  } while (0)
+#define OTM_W1M_KS(TDY, MW) do { if (a->kh == 7) OTM_W1M(TDY, 7, MW); else OTM_W1M(TDY, 4, MW); } while (0)
+    if (a->dy.dtype == OTM_BF16) { if (mw == 1) OTM_W1M_KS(__nv_bfloat16, 1); else OTM_W1M_KS(__nv_bfloat16, 2); }
+    else { if (mw == 1) OTM_W1M_KS(float, 1); else OTM_W1M_KS(float, 2); }
+#undef OTM_W1M_KS
+#undef OTM_W1M
     OTM_LAUNCH_CHECK();
     return OTM_OK;
   }
