@@ -170,6 +170,52 @@ __global__ void __launch_bounds__(128) conv_small_cout_kernel(ConvP p) {
 }
 
 // ---------------------------------------------------------------------------
+// Cout == 1 with many input channels on a small grid (the discriminator head, 512 -> 1 4x4 at
+// 13x13): one WARP per output pixel, lanes across the channels (coalesced 512-byte rows of x and
+// of the [tap][cin] pack), shuffle reduction.  The pixel-per-thread kernel above walked K = 8192
+// serially with 1 KB-strided loads and took 0.24 ms per launch.
+// ---------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) conv_cout1_warp_kernel(ConvP p, int total_px) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (gw >= total_px) return;
+  const int HoWo = p.y.h * p.y.w;
+  const int n = gw / HoWo, pix = gw - n * HoWo;
+  const int oh = pix / p.y.w, ow = pix - oh * p.y.w;
+  const TI* wbase = (const TI*)p.w + (long long)n * p.w_bstride;
+  const int H = p.x.h, W = p.x.w, halo = p.x_halo;
+  float acc = 0.f;
+  for (int r = 0; r < p.kh; ++r) {
+    const int ih = oh + r - p.pad;
+    if (ih < -halo || ih >= H + halo) continue;
+    for (int s = 0; s < p.kw; ++s) {
+      const int iw = ow + s - p.pad;
+      if (iw < -halo || iw >= W + halo) continue;
+      const TI* xp = vptr<TI>(p.x, n, ih, iw, 0);
+      const TI* wp = wbase + (long long)(r * p.kw + s) * p.cin;
+      for (int c = lane * 8; c < p.cin; c += 256) {
+        float xv[8], wv[8];
+        load_vec<TI, 8>(xp + c, xv);
+        load_vec<TI, 8>(wp + c, wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(xv[i], wv[i], acc);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = acc * p.alpha;
+    if (p.row_scale) v *= p.row_scale[n];
+    if (p.bias) v += p.bias[0];
+    v = act_fwd(v, p.act);
+    if (p.res.ptr) v += to_f(*vptr<TO>(p.res, n, oh, ow, 0));
+    float vv[1] = {v};
+    store_halo<TO, 1>(p.y, p.y_halo, n, oh, ow, 0, vv);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Cout == 1, K x K (K = 4 or 7) with the input patch staged in shared memory:
 // persistent CTAs over 16x16 output tiles; a thread owns 8 channels x 4 consecutive pixels and
 // slides a 4-vector register window along the filter row, so each filter row costs K+3 patch
@@ -1321,6 +1367,17 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
     if (out_bf) return OTM_C1(float, __nv_bfloat16);
     return OTM_C1(float, float);
 #undef OTM_C1
+  }
+  if (p.cout == 1 && p.cin % 256 == 0 && vec_ok(a->x, 8) && ((uintptr_t)a->wpack % 16 == 0) &&
+      (a->w_batch_stride % 8 == 0)) {
+    const int total_px = a->y.n * a->y.h * a->y.w;
+    const int blocks = (total_px * 32 + 255) / 256;
+    if (in_bf && out_bf) conv_cout1_warp_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>(p, total_px);
+    else if (in_bf) conv_cout1_warp_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>(p, total_px);
+    else if (out_bf) conv_cout1_warp_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>(p, total_px);
+    else conv_cout1_warp_kernel<float, float><<<blocks, 256, 0, st>>>(p, total_px);
+    OTM_LAUNCH_CHECK();
+    return OTM_OK;
   }
   if (p.cout <= 4 && (size_t)p.cout * p.ktot * 4 <= 160 * 1024) {
     size_t smem = (size_t)p.cout * p.ktot * sizeof(float);
