@@ -653,6 +653,130 @@ struct UpBwdF {
   }
 };
 
+// Block forms of the exact-halving DownSample (n_in == 2 n_out: blur + bilinear collapses to the
+// separable taps (.125,.375,.375,.125) on x[2j-1 .. 2j+2]).  One thread produces a 2x2 output
+// block from a 6x6 input window (9 loads per output vector instead of 16; the norm + activation
+// in front of the stencil is applied 36 instead of 64 times), resp. the gradients of a 2x2 INPUT
+// block from the 3x3 output gradients that touch it (2.25 loads per vector instead of 4).
+// Blocks whose window leaves the image, and all odd sizes, take the per-pixel functors above.
+template <typename T, int V>
+struct Down2x2F {
+  static constexpr int OCC = 2;
+  __device__ void prefetch(int, int, int, int) const {}
+  View x, y;
+  const float* stats;
+  int act, halo, C;
+  struct State { float mean[V], rstd[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+    if (stats) {
+      const float* p = stats + ((long long)n * C + c) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { st.mean[i] = p[2 * i]; st.rstd[i] = p[2 * i + 1]; }
+    }
+  }
+  // (h2, w2) index 2x2 blocks of y
+  __device__ void operator()(int n, int h2, int w2, int c, const State& st) const {
+    const int ho = 2 * h2, wo = 2 * w2;
+    const int r0 = 2 * ho - 1, c0 = 2 * wo - 1;  // window origin in x
+    if (r0 >= 0 && r0 + 5 < x.h && c0 >= 0 && c0 + 5 < x.w && ho + 1 < y.h && wo + 1 < y.w) {
+      const float k4[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+      float acc[2][2][V];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[a][b][i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        float h0[V], h1[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) { h0[i] = 0.f; h1[i] = 0.f; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          float v[V];
+          load_vec<T, V>(vptr<T>(x, n, r0 + r, c0 + q, c), v);
+          if (stats) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[i] = (v[i] - st.mean[i]) * st.rstd[i];
+          }
+          act_fwd_vec<V>(v, act);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            if (q < 4) h0[i] = fmaf(k4[q], v[i], h0[i]);
+            if (q >= 2) h1[i] = fmaf(k4[q - 2], v[i], h1[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          if (r < 4) { acc[0][0][i] = fmaf(k4[r], h0[i], acc[0][0][i]); acc[0][1][i] = fmaf(k4[r], h1[i], acc[0][1][i]); }
+          if (r >= 2) { acc[1][0][i] = fmaf(k4[r - 2], h0[i], acc[1][0][i]); acc[1][1][i] = fmaf(k4[r - 2], h1[i], acc[1][1][i]); }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) store_halo<T, V>(y, halo, n, ho + a, wo + b, c, acc[a][b]);
+      return;
+    }
+    DownF<T, V> f{x, y, stats, act, halo, C, (float)x.h / (float)y.h, (float)x.w / (float)y.w};
+    typename DownF<T, V>::State fs;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { fs.mean[i] = st.mean[i]; fs.rstd[i] = st.rstd[i]; }
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        if (ho + a < y.h && wo + b < y.w) f(n, ho + a, wo + b, c, fs);
+  }
+};
+
+template <typename T, int V>
+struct DownBwd2x2F {
+  static constexpr int OCC = 3;
+  __device__ void prefetch(int, int, int, int) const {}
+  View g, ga;  // g: [n, H/2, W/2, c] (g_halo == 0 only), ga: [n, H, W, c]
+  struct State {};
+  __device__ void prepare(int, int, State&) const {}
+  // (h2, w2) index 2x2 blocks of ga: rows 2 h2, 2 h2 + 1 are touched by output rows h2-1 .. h2+1
+  __device__ void operator()(int n, int h2, int w2, int c, const State&) const {
+    const int h = 2 * h2, w = 2 * w2;
+    if (h >= 2 && h + 1 <= ga.h - 3 && w >= 2 && w + 1 <= ga.w - 3) {
+      // input row 2a   <- outputs a-1 (.125), a (.375);  row 2a+1 <- outputs a (.375), a+1 (.125)
+      float t[3][3][V];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) load_vec<T, V>(vptr<T>(g, n, h2 - 1 + r, w2 - 1 + q, c), t[r][q]);
+      float he[3][V], ho[3][V];  // horizontal pass: even / odd input column
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          he[r][i] = 0.125f * t[r][0][i] + 0.375f * t[r][1][i];
+          ho[r][i] = 0.375f * t[r][1][i] + 0.125f * t[r][2][i];
+        }
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.125f * he[0][i] + 0.375f * he[1][i];
+      store_vec<T, V>(vptr_mut<T>(ga, n, h, w, c), o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.125f * ho[0][i] + 0.375f * ho[1][i];
+      store_vec<T, V>(vptr_mut<T>(ga, n, h, w + 1, c), o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.375f * he[1][i] + 0.125f * he[2][i];
+      store_vec<T, V>(vptr_mut<T>(ga, n, h + 1, w, c), o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = 0.375f * ho[1][i] + 0.125f * ho[2][i];
+      store_vec<T, V>(vptr_mut<T>(ga, n, h + 1, w + 1, c), o);
+      return;
+    }
+    DownBwdF<T, V> f{g, ga, 0, (float)ga.h / (float)g.h, (float)ga.w / (float)g.w};
+    typename DownBwdF<T, V>::State fs;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        if (h + a < ga.h && w + b < ga.w) f(n, h + a, w + b, c, fs);
+  }
+};
+
 // Block forms of the x2 up-sampling stencils.  The per-output functors above spend ~200
 // instructions per 16-byte vector on tap generation and issue 9 (forward) / 36 (backward) loads
 // per output vector; they ran at 0.8-1.2 TB/s.  Here one thread produces a 2x2 block:
@@ -1185,10 +1309,20 @@ int otm_down(const otm_down_args* a, otm_stream stream) {
               "down: halo too large");
   bool vok = vec_ok(a->x, 8) && vec_ok(a->y, 8);
   int rc = OTM_OK;
+  // OTM_DOWN_FWD_BLOCK=1: 2x2 output blocks from a 6x6 window.  Measured SLOWER than the per-output
+  // functor (1.54 vs 1.02 ms per iteration at 128x128, 7.2 vs 5.3 ms at 256x256: 128 registers ->
+  // 2 CTAs/SM); off by default.  The backward block form (DownBwd2x2F) is faster and is on.
+  static const int blk = [] { const char* e = getenv("OTM_DOWN_FWD_BLOCK"); return e ? atoi(e) : 0; }();
+  const bool even = a->x.h == 2 * a->y.h && a->x.w == 2 * a->y.w && a->y.h >= 4 && a->y.w >= 4;
   OTM_DISPATCH_TV(a->x.dtype, vok, {
-    DownF<T, V> f{make_view(a->x), make_view(a->y), a->stats, a->act, a->y_halo, a->x.c,
-                  (float)a->x.h / (float)a->y.h, (float)a->x.w / (float)a->y.w};
-    rc = launch_ew<V>(f, a->y.n, a->y.h, a->y.w, a->y.c, st);
+    if (blk && V == 8 && even) {
+      Down2x2F<T, V> f{make_view(a->x), make_view(a->y), a->stats, a->act, a->y_halo, a->x.c};
+      rc = launch_ew<V>(f, a->y.n, (a->y.h + 1) / 2, (a->y.w + 1) / 2, a->y.c, st);
+    } else {
+      DownF<T, V> f{make_view(a->x), make_view(a->y), a->stats, a->act, a->y_halo, a->x.c,
+                    (float)a->x.h / (float)a->y.h, (float)a->x.w / (float)a->y.w};
+      rc = launch_ew<V>(f, a->y.n, a->y.h, a->y.w, a->y.c, st);
+    }
   });
   return rc;
 }
@@ -1201,10 +1335,17 @@ int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_
   OTM_REQUIRE(g->dtype == ga->dtype, "down_bwd: dtype mismatch");
   bool vok = vec_ok(*g, 8) && vec_ok(*ga, 8);
   int rc = OTM_OK;
+  static const int blk = [] { const char* e = getenv("OTM_DOWN_BLOCK"); return e ? atoi(e) : 1; }();
+  const bool even = ga->h == 2 * g->h && ga->w == 2 * g->w && g->h >= 4 && g->w >= 4;
   OTM_DISPATCH_TV(g->dtype, vok, {
-    DownBwdF<T, V> f{make_view(*g), make_view(*ga), g_halo, (float)ga->h / (float)g->h,
-                     (float)ga->w / (float)g->w};
-    rc = launch_ew<V>(f, ga->n, ga->h, ga->w, ga->c, st);
+    if (blk && V == 8 && even && g_halo == 0) {
+      DownBwd2x2F<T, V> f{make_view(*g), make_view(*ga)};
+      rc = launch_ew<V>(f, ga->n, ga->h / 2, ga->w / 2, ga->c, st);
+    } else {
+      DownBwdF<T, V> f{make_view(*g), make_view(*ga), g_halo, (float)ga->h / (float)g->h,
+                       (float)ga->w / (float)g->w};
+      rc = launch_ew<V>(f, ga->n, ga->h, ga->w, ga->c, st);
+    }
   });
   return rc;
 }

@@ -16,8 +16,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=bench.BATCH)
 ap.add_argument("--top", type=int, default=45)
 ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--size", type=int, default=0, help="square image size (default: the bench config)")
 args = ap.parse_args()
 bench.BATCH = args.batch
+if args.size:
+    bench.IMAGE = (args.size, args.size)
+    bench.CONFIG["data"]["image_size"] = [args.size, args.size]
 bench.CONFIG["training"]["batch_size"] = args.batch
 dev = torch.device("cuda", 0)
 step = bench.build_trainer(dev, 0, use_graph=False)
