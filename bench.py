@@ -226,6 +226,47 @@ def dominant_kernel_roofline(device):
             "launch_ms": round(ms, 4), "flops_per_launch": flops}
 
 
+def hbm_kernel_roofline(device):
+    """The heaviest HBM-bound stage of the iteration -- the InstanceNorm + ReLU backward of a
+    res-block conv, [64,128,64,64] bf16 (otm_norm_act_bwd: per-(n,c) reductions, then the apply)
+    -- timed alone (CUDA events, L2 flushed) against the measured copy bandwidth.  Algorithmic
+    bytes: reduction 2R + apply 2R + 1W of 67.1 MB each."""
+    import statistics
+
+    from one_to_many_gan_b200 import kernels as K
+
+    n, c, hw = 64, 128, 64
+    x = K.alloc(n, c, hw, hw, torch.bfloat16, device, 0, zero=True)
+    x.normal_()
+    g = torch.randn_like(x)
+    st = K.instnorm_stats(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    nbytes = 5.0 * x.numel() * 2
+
+    def launch():
+        K.norm_act_bwd(g, x, st, K.ACT_RELU)
+
+    launch()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        launch()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = statistics.mean(ts)
+    pk, how = peaks()
+    ach = nbytes / ms / 1e6
+    return {"bound": "hbm", "kernel": "otm_norm_act_bwd (NormActBwdReduceF + NormActBwdApplyF), "
+                                       "[64,128,64,64] bf16, InstanceNorm + ReLU backward",
+            "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_source": how, "unit": "GB/s",
+            "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None, "launch_ms": round(ms, 4),
+            "bytes_per_launch": nbytes}
+
+
 def cpu_baseline(sample_batch=2, iters=1, warm=0):
     """The oracle port (oracle/reference_port.py) of the same iteration on the host cores."""
     from oracle import reference_port as rp
@@ -372,6 +413,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches * args.steps),
             "roofline": roof,
+            "roofline_hbm": hbm_kernel_roofline(device),
             "conv_step_roofline": {
                 "achieved_tflops_per_gpu": round(conv_tflops, 1), "peak": pk["bf16_tflops_sustained"],
                 "peak_source": how + " sustained",

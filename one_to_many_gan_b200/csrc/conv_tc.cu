@@ -1204,8 +1204,10 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll 1
         for (int j2 = 0; j2 < 4; ++j2) {
+          if (p.debug & 2) break;  // timing experiment: no TMEM read-out
           float v[32];
           tmem_ld32(tacc + (uint32_t)(j2 * 32), v);
+          if (p.debug & 1) continue;  // timing experiment: no epilogue math / staging stores
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], scale, bias);
           act_fwd_vec<32>(v, p.act);
@@ -1246,7 +1248,7 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (te == 0 && hh0 < p.y.h) {
+        if (te == 0 && hh0 < p.y.h && !(p.debug & 4)) {  // debug 4: no TMA store
 #pragma unroll
           for (int sb = 0; sb < BN / 64; ++sb)
             tma_store_4d(&tmY, smem_u32(stage_out + sb * SUB_BYTES), o0 + sb * 64, w0, hh0, n);
