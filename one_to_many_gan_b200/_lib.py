@@ -6,12 +6,14 @@ every op raises when handed a non-CUDA tensor."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libotm_b200.so"
+# OTM_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = Path(os.environ["OTM_B200_LIB"]) if os.environ.get("OTM_B200_LIB") else _PKG / "libotm_b200.so"
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3

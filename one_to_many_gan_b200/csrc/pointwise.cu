@@ -64,24 +64,50 @@ __global__ void __launch_bounds__(256) ew_kernel(F f, int N, int H, int W, int C
 // CTAs/SM), and the per-(n, channel) constants are re-read only when the image changes.
 // resident CTAs per SM of a functor's persistent kernel (register budget 65536 / (256 * OCC));
 // functors that hold a block of outputs per thread declare `static constexpr int OCC = 2`
+#ifndef OTM_EW_OCC
+#define OTM_EW_OCC 4
+#endif
+#ifndef OTM_RED_OCC
+#define OTM_RED_OCC 4
+#endif
 template <typename F, typename = void>
-struct ew_occ { static constexpr int value = 4; };
+struct ew_occ { static constexpr int value = OTM_EW_OCC; };
 template <typename F>
 struct ew_occ<F, std::void_t<decltype(F::OCC)>> { static constexpr int value = F::OCC; };
 
 template <int V, typename F>
 __global__ void __launch_bounds__(256, ew_occ<F>::value)
-ew_persist_kernel(F f, int N, int H, int W, int C, int cv_shift, int nblk, int items) {
+ew_persist_kernel(F f, int N, int H, int W, int C, int cv_shift, int nblk, int items, int chunk) {
   const int CV = C / V;
   const int WC = W * CV;
   const int nrows = N * H;
+  typename F::State st;
+  int cur_n = -1, cur_cv = -1;
+  if (chunk > 0) {
+    // block-cyclic order: CTA b takes chunks b, b + G, ... of `chunk` consecutive items, so at any
+    // time the grid streams through one contiguous window of the tensors
+    for (int c0 = blockIdx.x * chunk; c0 < items; c0 += gridDim.x * chunk) {
+      const int c1 = min(c0 + chunk, items);
+      for (int it = c0; it < c1; ++it) {
+        const int r = it / nblk, cb = it - r * nblk;
+        const int n = r / H, h = r - n * H;
+        const int i = cb * 256 + threadIdx.x;
+        if (i < WC) {
+          int w, cv;
+          if (cv_shift >= 0) { w = i >> cv_shift; cv = i & (CV - 1); }
+          else { w = i / CV; cv = i - w * CV; }
+          if (n != cur_n || cv != cur_cv) { f.prepare(n, cv * V, st); cur_n = n; cur_cv = cv; }
+          f(n, h, w, cv * V, st);
+        }
+      }
+    }
+    return;
+  }
   const int t0 = (int)((long long)items * blockIdx.x / gridDim.x);
   const int t1 = (int)((long long)items * (blockIdx.x + 1) / gridDim.x);
   if (t0 >= t1) return;
   int r = t0 / nblk, cb = t0 - r * nblk;
   int n = r / H, h = r - n * H;
-  typename F::State st;
-  int cur_n = -1, cur_cv = -1;
   for (int it = t0; it < t1; ++it) {
     const int i = cb * 256 + threadIdx.x;
     if (i < WC) {
@@ -118,7 +144,9 @@ static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
     if (items < (1ll << 30)) {
       long long grid = (long long)num_sms() * ew_occ<F>::value;
       if (grid > items) grid = items;
-      ew_persist_kernel<V, F><<<(int)grid, 256, 0, st>>>(f, N, H, W, C, cv_shift, nblk, (int)items);
+      static const int chunk = [] { const char* e = getenv("OTM_EW_CHUNK"); return e ? atoi(e) : 0; }();
+      ew_persist_kernel<V, F><<<(int)grid, 256, 0, st>>>(f, N, H, W, C, cv_shift, nblk, (int)items,
+                                                         chunk);
       OTM_LAUNCH_CHECK();
       return OTM_OK;
     }
@@ -142,7 +170,7 @@ static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
 // grid = (pixel chunks, 1, N), 256 threads = lanes (channel vectors) x rows (pixels).
 // ---------------------------------------------------------------------------
 template <int V, typename F>
-__global__ void __launch_bounds__(256, 4) nc_reduce_kernel(F f, int H, int W, int C, int lanes,
+__global__ void __launch_bounds__(256, OTM_RED_OCC) nc_reduce_kernel(F f, int H, int W, int C, int lanes,
                                                         int pix_per_cta, float* out) {
   constexpr int NQ = F::NQ;
   __shared__ float red[256 * NQ * V];
@@ -210,7 +238,7 @@ static int launch_nc_reduce(F f, int N, int H, int W, int C, float* out, cudaStr
   // all CTAs co-resident (4 per SM at 64 registers): chunks * N <= 4 * SMs, so there is no
   // partial second wave; at least `rows*4` pixels per CTA
   static const int mode = [] { const char* e = getenv("OTM_EW_MODE"); return e ? atoi(e) : 1; }();
-  int want_chunks = mode == 1 ? (num_sms() * 4) / N : (num_sms() * 4 + N - 1) / N;
+  int want_chunks = mode == 1 ? (num_sms() * OTM_RED_OCC) / N : (num_sms() * 4 + N - 1) / N;
   if (want_chunks < 1) want_chunks = 1;
   int pix = (HW + want_chunks - 1) / want_chunks;
   int min_pix = rows * 4;

@@ -16,6 +16,9 @@ def mk(n, c, h, w, halo=0):
 for (n, c, h, w) in [(64, 128, 128, 128), (64, 128, 64, 64), (160, 128, 64, 64)]:
     x = mk(n, c, h, w); g = mk(n, c, h, w); gp = mk(n, c, h, w, 1)
     st = K.instnorm_stats(x); mb = n * c * h * w * 2 / 1e6
+    y = torch.empty_like(x)
+    t = run(lambda: y.copy_(x)); print(f"[{n},{c},{h},{w}] torch copy   {t*1e3:7.1f} us {2*mb/t/1e3:6.2f} TB/s (1R+1W, calibration)")
+    t = run(lambda: torch.add(x, g, out=y)); print(f"[{n},{c},{h},{w}] torch add    {t*1e3:7.1f} us {3*mb/t/1e3:6.2f} TB/s (2R+1W, calibration)")
     t = run(lambda: K.instnorm_stats(x)); print(f"[{n},{c},{h},{w}] stats        {t*1e3:7.1f} us {mb/t/1e3:6.2f} TB/s (1R)")
     t = run(lambda: K.norm_act(x, st, K.ACT_RELU, y_halo=1)); print(f"[{n},{c},{h},{w}] norm_act     {t*1e3:7.1f} us {2*mb/t/1e3:6.2f} TB/s (1R+1W)")
     t = run(lambda: K.norm_act_bwd(g, x, st, K.ACT_RELU)); print(f"[{n},{c},{h},{w}] norm_act_bwd {t*1e3:7.1f} us {5*mb/t/1e3:6.2f} TB/s (4R+1W, two kernels)")
