@@ -1154,6 +1154,209 @@ struct AddF {
   }
 };
 
+// ---------------------------------------------------------------------------
+// TMA-staged streaming form of the InstanceNorm / activation backward passes.
+// The register-file drivers above keep (threads x 1-3 x 16 B) in flight and plateau at 2.5-3
+// TB/s (torch's trivial add kernel: 5.2-6.5 TB/s on the same tensors, by running 2048 threads/SM
+// with 8 loads each -- impossible with 30+ registers of per-channel state per thread).  Here the
+// bytes in flight live in shared memory instead: one producer lane issues 1-D bulk copies
+// (cp.async.bulk -> mbarrier) of whole image rows of every input into a ring of stages, 8
+// consumer warps compute from shared memory and store straight to global.
+//   stage = [g row (W + 2p pixels) | g alias row (reflect fold of rows 1 / H-2) | x row | g2 row]
+// MODE 0: apply (writes gx / gres), MODE 1: the two per-(n,c) reductions.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sb_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sb_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void sb_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sb_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "SB_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra SB_DONE;\n"
+      "bra SB_WAIT_LOOP;\n"
+      "SB_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void sb_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(288, 1)
+nab_stream_kernel(NormActBwdApplyF<T, 8, false> f, int N, int H, int W, int C, int stages, float* red_out) {
+  constexpr int V = 8;
+  extern __shared__ __align__(128) unsigned char nab_smem[];
+  const int p = f.g_halo;
+  const int CV = C / V;
+  const uint32_t g_row_bytes = (uint32_t)(W + 2 * p) * C * sizeof(T);
+  const uint32_t x_row_bytes = (uint32_t)W * C * sizeof(T);
+  const bool has_x = f.x.ptr != nullptr, has_g2 = f.g2.ptr != nullptr;
+  const uint32_t off_alias = g_row_bytes, off_x = off_alias + (p ? g_row_bytes : 0);
+  const uint32_t off_g2 = off_x + (has_x ? x_row_bytes : 0);
+  const uint32_t stage_bytes = (off_g2 + (has_g2 ? x_row_bytes : 0) + 127u) & ~127u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nab_smem + (size_t)stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + stages;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    for (int s2 = 0; s2 < stages; ++s2) { sb_mbar_init(sb_smem(&full[s2]), 1); sb_mbar_init(sb_smem(&empty[s2]), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int rows = N * H;
+  const int r0 = (int)((long long)rows * blockIdx.x / gridDim.x);
+  const int r1 = (int)((long long)rows * (blockIdx.x + 1) / gridDim.x);
+  if (warp == 8) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      for (int r = r0, k = 0; r < r1; ++r, ++k) {
+        const int st = k % stages;
+        sb_mbar_wait(sb_smem(&empty[st]), ((k / stages) & 1) ^ 1);
+        const int n = r / H, h = r - n * H;
+        const int alias = p ? (h == 1 ? -1 : (h == H - 2 ? H : -2)) : -2;
+        const uint32_t bar = sb_smem(&full[st]);
+        const uint32_t base = sb_smem(nab_smem + (size_t)st * stage_bytes);
+        uint32_t bytes = g_row_bytes + (alias != -2 ? g_row_bytes : 0) + (has_x ? x_row_bytes : 0) +
+                         (has_g2 ? x_row_bytes : 0);
+        sb_mbar_expect_tx(bar, bytes);
+        sb_bulk_load(base, vptr<T>(f.g, n, h, -p, 0), g_row_bytes, bar);
+        if (alias != -2) sb_bulk_load(base + off_alias, vptr<T>(f.g, n, alias, -p, 0), g_row_bytes, bar);
+        if (has_x) sb_bulk_load(base + off_x, vptr<T>(f.x, n, h, 0, 0), x_row_bytes, bar);
+        if (has_g2) sb_bulk_load(base + off_g2, vptr<T>(f.g2, n, h, 0, 0), x_row_bytes, bar);
+      }
+    }
+    return;
+  }
+  // ---------------- consumers (8 warps) ----------------
+  const int tid = threadIdx.x;  // 0..255
+  const int cv = tid % CV;      // constant per thread: CV divides 256 (so it is a power of two)
+  const int cv_sh = 31 - __clz(CV);
+  using F = NormActBwdApplyF<T, 8, false>;
+  typename F::State st;
+  int cur_n = -1;
+  float acc[2][V];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+  auto flush = [&](int n) {
+    if (MODE == 1 && n >= 0) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          atomicAdd(red_out + ((long long)n * C + cv * V + i) * 2 + q, acc[q][i]);
+          acc[q][i] = 0.f;
+        }
+    }
+  };
+  for (int r = r0, k = 0; r < r1; ++r, ++k) {
+    const int stg = k % stages;
+    const int n = r / H, h = r - n * H;
+    if (n != cur_n) {
+      flush(cur_n);
+      if (MODE == 0) f.prepare(n, cv * V, st); else f.prepare_stats(n, cv * V, st);
+      cur_n = n;
+    }
+    sb_mbar_wait(sb_smem(&full[stg]), (k / stages) & 1);
+    const unsigned char* base = nab_smem + (size_t)stg * stage_bytes;
+    const T* grow = reinterpret_cast<const T*>(base);
+    const T* arow = reinterpret_cast<const T*>(base + off_alias);
+    const T* xrow = reinterpret_cast<const T*>(base + off_x);
+    const T* g2row = reinterpret_cast<const T*>(base + off_g2);
+    const bool row_alias = p && (h == 1 || h == H - 2);
+    for (int i = tid; i < W * CV; i += 256) {
+      const int w = i >> cv_sh;
+      float ga[V], gn[V], pre[V];
+      load_vec<T, V>(grow + (size_t)(w + p) * C + cv * V, ga);
+      if (p) {
+        const int wa = (w == 1) ? -1 : ((w == W - 2) ? W : -2);
+        if (wa != -2) {
+          float t[V];
+          load_vec<T, V>(grow + (size_t)(wa + p) * C + cv * V, t);
+#pragma unroll
+          for (int e = 0; e < V; ++e) ga[e] += t[e];
+        }
+        if (row_alias) {
+          float t[V];
+          load_vec<T, V>(arow + (size_t)(w + p) * C + cv * V, t);
+#pragma unroll
+          for (int e = 0; e < V; ++e) ga[e] += t[e];
+          if (wa != -2) {
+            load_vec<T, V>(arow + (size_t)(wa + p) * C + cv * V, t);
+#pragma unroll
+            for (int e = 0; e < V; ++e) ga[e] += t[e];
+          }
+        }
+      }
+      if (has_g2) {
+        float t[V];
+        load_vec<T, V>(g2row + (size_t)w * C + cv * V, t);
+#pragma unroll
+        for (int e = 0; e < V; ++e) ga[e] += t[e];
+      }
+      if (has_x) {
+        load_vec<T, V>(xrow + (size_t)w * C + cv * V, pre);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) pre[e] = 0.f;
+      }
+      if (f.stats) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) pre[e] = (pre[e] - st.mean[e]) * st.rstd[e];
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) gn[e] = ga[e];
+      act_bwd_vec<V>(gn, pre, f.act);
+      if (MODE == 1) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) { acc[0][e] += gn[e]; acc[1][e] += gn[e] * pre[e]; }
+      } else {
+        if (f.gres.ptr) store_vec<T, V>(vptr_mut<T>(f.gres, n, h, w, cv * V), ga);
+        if (f.stats) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) gn[e] = st.rstd[e] * (gn[e] - st.m1[e] - pre[e] * st.m2[e]);
+        }
+        store_vec<T, V>(vptr_mut<T>(f.gx, n, h, w, cv * V), gn);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) sb_mbar_arrive(sb_smem(&empty[stg]));
+  }
+  flush(cur_n);
+}
+
+// rows must be dense (pixel stride == C), 16-byte aligned, CV | 256, halo 0 or 1
+static bool nab_stream_ok(const otm_norm_act_bwd_args* a) {
+  if (a->g_down || a->g_halo > 1 || a->gx.c % 8 != 0) return false;
+  const int C = a->gx.c, CV = C / 8;
+  if (CV < 1 || 256 % CV != 0) return false;
+  if (a->gx.h < 4 || a->gx.w < 4) return false;
+  auto dense = [&](const otm_tensor& t) {
+    return !t.ptr || (t.sw == C && t.sh % 8 == 0 && t.sn % 8 == 0 && ((uintptr_t)t.ptr % 16 == 0));
+  };
+  if (!dense(a->g) || !dense(a->x) || !dense(a->g2) || !dense(a->gx) || !dense(a->gres)) return false;
+  const size_t es = dtype_size(a->gx.dtype);
+  const size_t grow = (size_t)(a->gx.w + 2 * a->g_halo) * C * es, xrow = (size_t)a->gx.w * C * es;
+  if (grow % 16 || xrow % 16) return false;
+  const size_t stage = grow * (a->g_halo ? 2 : 1) + (a->x.ptr ? xrow : 0) + (a->g2.ptr ? xrow : 0) + 128;
+  return 2 * stage + 256 <= 200 * 1024;
+}
+
 static bool same_shape(const otm_tensor& a, const otm_tensor& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }
@@ -1318,6 +1521,41 @@ static int norm_act_bwd_impl(const otm_norm_act_bwd_args* a, otm_stream stream) 
   const float sch = a->g_down ? (float)a->x.h / (float)a->g.h : 1.f;
   const float scw = a->g_down ? (float)a->x.w / (float)a->g.w : 1.f;
   if (a->stats) OTM_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * sh.n * C, st));
+  static const int use_stream = [] { const char* e = getenv("OTM_NAB_STREAM"); return e ? atoi(e) : 1; }();
+  if (use_stream && vok && nab_stream_ok(a)) {
+    const size_t es = dtype_size(sh.dtype);
+    const size_t grow = (size_t)(sh.w + 2 * a->g_halo) * C * es, xrow = (size_t)sh.w * C * es;
+    const size_t stage = (grow * (a->g_halo ? 2 : 1) + (a->x.ptr ? xrow : 0) + (a->g2.ptr ? xrow : 0) + 127) &
+                         ~(size_t)127;
+    int stages = (int)((200 * 1024 - 256) / stage);
+    if (stages > 8) stages = 8;
+    const size_t smem = stage * stages + 2 * 8 * stages + 64;
+    int grid = num_sms();
+    if (grid > sh.n * sh.h) grid = sh.n * sh.h;
+#define OTM_NAB_STREAM(T)                                                                          \
+  do {                                                                                              \
+    NormActBwdApplyF<T, 8, false> f;                                                                \
+    f.g = make_view(a->g); f.g2 = a->g2.ptr ? make_view(a->g2) : null_view();                       \
+    f.x = a->x.ptr ? make_view(a->x) : null_view();                                                 \
+    f.stats = a->stats; f.act = a->act; f.g_halo = a->g_halo; f.C = C;                              \
+    f.g_down = 0; f.sch = 1.f; f.scw = 1.f;                                                         \
+    f.gx = make_view(a->gx); f.gres = a->gres.ptr ? make_view(a->gres) : null_view();               \
+    f.sums = a->sums; f.inv_hw = 1.f / (float)(sh.h * sh.w);                                        \
+    static bool set0 = false, set1 = false;                                                         \
+    if (a->stats) {                                                                                 \
+      auto k1 = nab_stream_kernel<T, 1>;                                                            \
+      if (!set1) { OTM_CHECK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set1 = true; } \
+      k1<<<grid, 288, smem, st>>>(f, sh.n, sh.h, sh.w, C, stages, a->sums);                         \
+    }                                                                                               \
+    auto k0 = nab_stream_kernel<T, 0>;                                                              \
+    if (!set0) { OTM_CHECK_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set0 = true; } \
+    k0<<<grid, 288, smem, st>>>(f, sh.n, sh.h, sh.w, C, stages, nullptr);                           \
+  } while (0)
+    if (sh.dtype == OTM_BF16) OTM_NAB_STREAM(__nv_bfloat16); else OTM_NAB_STREAM(float);
+#undef OTM_NAB_STREAM
+    OTM_LAUNCH_CHECK();
+    return OTM_OK;
+  }
   OTM_DISPATCH_TV(sh.dtype, vok, {
     if (a->g_down) OTM_NAB_BODY(true);
     else OTM_NAB_BODY(false);
