@@ -80,6 +80,11 @@ inline View null_view() {
   v.ptr = nullptr;
   return v;
 }
+__host__ __device__ inline View null_view_dev() {
+  View v{};
+  v.ptr = nullptr;
+  return v;
+}
 inline size_t dtype_size(int dt) { return dt == OTM_BF16 ? 2 : 4; }
 
 // can the view be accessed with V-wide channel vectors?
