@@ -1259,15 +1259,27 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
   for (int q = 0; q < NA; ++q)
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+  // per-sample flush of the register accumulators: the 256 / CV threads that share a channel
+  // vector meet in shared memory first, so one atomic per (n, c, q) and CTA reaches L2
+  float* red_sm = reinterpret_cast<float*>(bars + 2 * stages);  // [NQ * V][256]
   auto flush = [&](int n) {
-    if (NQ > 0 && n >= 0) {
+    if (NQ > 0 && n >= 0) {  // n and the call sites are uniform over the consumer warps
 #pragma unroll
       for (int q = 0; q < NQ; ++q)
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          atomicAdd(red_out + op.out_index(n, cv * V + i, q), acc[q][i]);
+          red_sm[(q * V + i) * 256 + tid] = acc[q][i];
           acc[q][i] = 0.f;
         }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int groups = 256 / CV;  // threads tid, tid + CV, ... hold the same channel vector
+      for (int o = tid; o < NQ * V * CV; o += 256) {
+        const int c_v = o % CV, qi = o / CV;  // qi = q * V + i
+        float sum = 0.f;
+        for (int g2 = 0; g2 < groups; ++g2) sum += red_sm[qi * 256 + g2 * CV + c_v];
+        atomicAdd(red_out + op.out_index(n, c_v * V + qi % V, qi / V), sum);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   };
   for (int r = r0, k = 0; r < r1; ++r, ++k) {
@@ -1494,10 +1506,11 @@ static int row_stream_plan(const otm_tensor& A, int a_halo, const otm_tensor* B,
   if (arow % 16 || xrow % 16) return 0;
   const size_t stage = (arow * (a_halo ? 2 : 1) + ((B && B->ptr) ? xrow : 0) + ((Cc && Cc->ptr) ? xrow : 0) + 127) &
                        ~(size_t)127;
-  int stages = (int)((200 * 1024 - 256) / stage);
+  const size_t scratch = 2 * 8 * 256 * sizeof(float);  // reduction flush scratch [NQ * V][256]
+  int stages = (int)((200 * 1024 - 256 - scratch) / stage);
   if (stages < 2) return 0;
   if (stages > 8) stages = 8;
-  *smem_bytes = stage * stages + 2 * 8 * stages + 64;
+  *smem_bytes = stage * stages + 2 * 8 * stages + scratch + 64;
   return stages;
 }
 
