@@ -1567,9 +1567,10 @@ int otm_instnorm_stats(const otm_tensor* x, float eps, float* ws, float* stats,
   bool vok = vec_ok(*x, 8);
   int rc = OTM_OK;
   size_t rs_smem_bytes = 0;
-  // (pure read reductions measured no faster through the row-streaming kernel -- 39.9 vs 33.8 us on
-  // [64,128,64,64] -- and the whole iteration slower; OTM_STREAM_REDUCE=1 enables it)
-  static const int stream_red = [] { const char* e = getenv("OTM_STREAM_REDUCE"); return e ? atoi(e) : 0; }();
+  // pure read reductions through the row-streaming kernel: 31.7 vs 33.8 us on [64,128,64,64], 70.7
+  // vs 80.9 us on [64,128,128,128] once the flush goes through shared memory (with one atomic per
+  // thread it was slower); OTM_STREAM_REDUCE=0 selects the register-file reduction
+  static const int stream_red = [] { const char* e = getenv("OTM_STREAM_REDUCE"); return e ? atoi(e) : 1; }();
   const int rs_stages = (vok && stream_red)
                             ? row_stream_plan(*x, 0, nullptr, nullptr, nullptr, nullptr, &rs_smem_bytes) : 0;
   if (rs_stages) {
@@ -1920,7 +1921,7 @@ int otm_channel_sum(const otm_tensor* g, float* out, otm_stream stream) {
   int rc = OTM_OK;
   {
     size_t smem = 0;
-    static const int stream_red = [] { const char* e = getenv("OTM_STREAM_REDUCE"); return e ? atoi(e) : 0; }();
+    static const int stream_red = [] { const char* e = getenv("OTM_STREAM_REDUCE"); return e ? atoi(e) : 1; }();
     const int stages = (vok && stream_red) ? row_stream_plan(*g, 0, nullptr, nullptr, nullptr, nullptr, &smem) : 0;
     if (stages) {
       if (g->dtype == OTM_BF16) {
