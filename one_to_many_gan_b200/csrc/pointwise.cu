@@ -1530,6 +1530,167 @@ static int launch_row_stream(const OP& op, int N, int H, int W, int C, int stage
   return OTM_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Windowed row streaming for the DownSample stencil (blur + bilinear, 4 x 4 taps, stride ~2):
+// output row ho reads input rows i0-1 .. i0+2.  The producer lane bulk-copies every input row of
+// the CTA's range ONCE into a ring of S >= 6 row slots; the consumers wait for the rows a new
+// output row adds, release the rows it no longer needs, and gather their 16 taps from shared
+// memory (the register-file kernel gathered them through L1/L2 at ~1 TB/s).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void down_row_window(int ho, int n_in, float scale, int& lo, int& hi) {
+  const float src = fmaxf((ho + 0.5f) * scale - 0.5f, 0.f);
+  const int i0 = min((int)floorf(src), n_in - 1);
+  lo = max(i0 - 1, 0);
+  hi = min(i0 + 2, n_in - 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(288, 1)
+down_stream_kernel(DownF<T, 8> f, int N, int Ho, int Wo, int C, int S) {
+  constexpr int V = 8;
+  extern __shared__ __align__(128) unsigned char ds_smem[];
+  const int Hi = f.x.h, Wi = f.x.w;
+  const int CV = C / V;
+  const uint32_t row_bytes = (uint32_t)Wi * C * sizeof(T);
+  const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ds_smem + (size_t)S * slot_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    for (int s2 = 0; s2 < S; ++s2) { sb_mbar_init(sb_smem(&full[s2]), 1); sb_mbar_init(sb_smem(&empty[s2]), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int rows = N * Ho;
+  const int q0 = (int)((long long)rows * blockIdx.x / gridDim.x);
+  const int q1 = (int)((long long)rows * (blockIdx.x + 1) / gridDim.x);
+  if (warp == 8) {
+    // ---------------- producer: every needed input row once, in order ----------------
+    if (lane == 0) {
+      int k = 0, cur_n = -1, next_in = 0;
+      for (int q = q0; q < q1; ++q) {
+        const int n = q / Ho, ho = q - n * Ho;
+        int lo, hi;
+        down_row_window(ho, Hi, f.sch, lo, hi);
+        if (n != cur_n) { cur_n = n; next_in = lo; }
+        for (; next_in <= hi; ++next_in, ++k) {
+          const int st = k % S;
+          sb_mbar_wait(sb_smem(&empty[st]), ((k / S) & 1) ^ 1);
+          const uint32_t bar = sb_smem(&full[st]);
+          sb_mbar_expect_tx(bar, row_bytes);
+          sb_bulk_load(sb_smem(ds_smem + (size_t)st * slot_bytes), vptr<T>(f.x, n, next_in, 0, 0), row_bytes, bar);
+        }
+      }
+    }
+    return;
+  }
+  // ---------------- consumers ----------------
+  const int tid = threadIdx.x;
+  const int cv = tid % CV;
+  const int cv_sh = 31 - __clz(CV);
+  typename DownF<T, 8>::State st;
+  int cur_n = -1;
+  int first = 0, kbase = 0;   // input row `first` of the current image has load index kbase
+  int waited_hi = -1;         // highest input row of the current image already waited for
+  int released = 0;           // input rows [first, released) of the current image are released
+  int kcount = 0;             // rows loaded so far (mirrors the producer's k)
+  auto slot_of = [&](int r) { return (kbase + (r - first)) % S; };
+  auto release_upto = [&](int upto) {  // warp-level: one arrival per warp and row
+    // (the rows were rewritten in place through the generic proxy; order that before the bulk
+    // copy that will overwrite the slot)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+      for (int r = released; r < upto; ++r) sb_mbar_arrive(sb_smem(&empty[slot_of(r)]));
+    released = max(released, upto);
+  };
+  for (int q = q0; q < q1; ++q) {
+    const int n = q / Ho, ho = q - n * Ho;
+    int lo, hi;
+    down_row_window(ho, Hi, f.sch, lo, hi);
+    if (n != cur_n) {
+      if (cur_n >= 0) release_upto(waited_hi + 1);
+      cur_n = n;
+      first = lo; kbase = kcount; waited_hi = lo - 1; released = lo;
+      f.prepare(n, cv * V, st);
+    }
+    release_upto(lo);
+    // rows this output row adds: wait, then normalise + activate them ONCE, in place (each input
+    // element feeds up to 4 x 4 output taps; storing act(norm(x)) back at storage precision
+    // leaves the stencil a plain weighted gather)
+    const bool transform = f.stats != nullptr || f.act != OTM_ACT_NONE;
+    for (int r = waited_hi + 1; r <= hi; ++r) {
+      const int k = kbase + (r - first);
+      sb_mbar_wait(sb_smem(&full[k % S]), (k / S) & 1);
+      if (transform) {
+        T* row = reinterpret_cast<T*>(ds_smem + (size_t)(k % S) * slot_bytes);
+        for (int i = tid; i < Wi * CV; i += 256) {
+          float v[V];
+          load_vec<T, V>(row + (size_t)(i >> cv_sh) * C + cv * V, v);
+          if (f.stats) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[e] = (v[e] - st.mean[e]) * st.rstd[e];
+          }
+          act_fwd_vec<V>(v, f.act);
+          store_vec<T, V>(row + (size_t)(i >> cv_sh) * C + cv * V, v);
+        }
+      }
+    }
+    if (hi > waited_hi) {
+      kcount += hi - waited_hi;
+      waited_hi = hi;
+      if (transform) asm volatile("bar.sync 1, 256;" ::: "memory");  // transformed rows visible
+    }
+    int ph[4];
+    float wh[4];
+    down_taps(ho, Hi, f.sch, ph, wh);
+    const T* rp[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rp[a] = reinterpret_cast<const T*>(ds_smem + (size_t)slot_of(ph[a]) * slot_bytes);
+    for (int i = tid; i < Wo * CV; i += 256) {
+      const int wo = i >> cv_sh;
+      int pw[4];
+      float ww[4];
+      down_taps(wo, Wi, f.scw, pw, ww);
+      float acc[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float wgt = wh[a] * ww[b];
+          float v[V];
+          load_vec<T, V>(rp[a] + (size_t)pw[b] * C + cv * V, v);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] += wgt * v[e];
+        }
+      }
+      store_halo<T, V>(f.y, f.halo, n, ho, wo, cv * V, acc);
+    }
+  }
+  if (cur_n >= 0) release_upto(waited_hi + 1);
+}
+
+static int down_stream_slots(const otm_down_args* a, size_t* smem_bytes) {
+  static const int use_stream = [] { const char* e = getenv("OTM_DOWN_STREAM"); return e ? atoi(e) : 1; }();
+  const otm_tensor& x = a->x;
+  if (!use_stream || x.c % 8 != 0) return 0;
+  const int C = x.c, CV = C / 8;
+  if (CV < 1 || 256 % CV != 0 || a->y.h < 2 || a->y.w < 2) return 0;
+  if (x.sw != C || x.sh % 8 || x.sn % 8 || ((uintptr_t)x.ptr % 16)) return 0;
+  const size_t es = dtype_size(x.dtype);
+  if ((long long)x.n * x.h * x.w * C * (long long)es < (8ll << 20)) return 0;
+  const size_t row = ((size_t)x.w * C * es + 127) & ~(size_t)127;
+  if (((size_t)x.w * C * es) % 16) return 0;
+  int S = (int)((200 * 1024 - 256) / row);
+  if (S < 6) return 0;
+  if (S > 12) S = 12;
+  *smem_bytes = row * S + 2 * 8 * S + 64;
+  return S;
+}
+
 static bool same_shape(const otm_tensor& a, const otm_tensor& b) {
   return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
 }
@@ -1778,6 +1939,30 @@ int otm_down(const otm_down_args* a, otm_stream stream) {
   // OTM_DOWN_FWD_BLOCK=1: 2x2 output blocks from a 6x6 window.  Measured SLOWER than the per-output
   // functor (1.54 vs 1.02 ms per iteration at 128x128, 7.2 vs 5.3 ms at 256x256: 128 registers ->
   // 2 CTAs/SM); off by default.  The backward block form (DownBwd2x2F) is faster and is on.
+  {
+    size_t smem = 0;
+    const int S = vok ? down_stream_slots(a, &smem) : 0;
+    if (S) {
+      int grid = num_sms();
+      if (grid > a->y.n * a->y.h) grid = a->y.n * a->y.h;
+#define OTM_DOWN_STREAM(T)                                                                        \
+  do {                                                                                             \
+    DownF<T, 8> f{make_view(a->x), make_view(a->y), a->stats, a->act, a->y_halo, a->x.c,           \
+                  (float)a->x.h / (float)a->y.h, (float)a->x.w / (float)a->y.w};                   \
+    auto kern = down_stream_kernel<T>;                                                             \
+    static bool set_ = false;                                                                      \
+    if (!set_) {                                                                                   \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      set_ = true;                                                                                 \
+    }                                                                                              \
+    kern<<<grid, 288, smem, st>>>(f, a->y.n, a->y.h, a->y.w, a->y.c, S);                           \
+  } while (0)
+      if (a->x.dtype == OTM_BF16) OTM_DOWN_STREAM(__nv_bfloat16); else OTM_DOWN_STREAM(float);
+#undef OTM_DOWN_STREAM
+      OTM_LAUNCH_CHECK();
+      return OTM_OK;
+    }
+  }
   static const int blk = [] { const char* e = getenv("OTM_DOWN_FWD_BLOCK"); return e ? atoi(e) : 0; }();
   const bool even = a->x.h == 2 * a->y.h && a->x.w == 2 * a->y.w && a->y.h >= 4 && a->y.w >= 4;
   OTM_DISPATCH_TV(a->x.dtype, vok, {
