@@ -1195,8 +1195,19 @@ __device__ __forceinline__ void sb_bulk_load(uint32_t dst, const void* src, uint
       : "memory");
 }
 
+// position (in view coordinates) of the reflect-halo element that aliases interior index i of an
+// extent-n axis with a halo of width p (nn.ReflectionPad2d), or NO_ALIAS; at most one exists
+// when n >= 2p + 2
+constexpr int NO_ALIAS = -1000000;
+__device__ __forceinline__ int reflect_alias(int i, int n, int p) {
+  if (p == 0) return NO_ALIAS;
+  if (i >= 1 && i <= p) return -i;
+  if (i >= n - 1 - p && i <= n - 2) return 2 * (n - 1) - i;
+  return NO_ALIAS;
+}
+
 // Generic row-streaming kernel.  OP supplies up to three row inputs -- A (optionally the interior
-// view of a reflect-padded tensor with halo 1: its aliases are folded on the fly), B, C -- and
+// view of a reflect-padded tensor with halo <= 3: its aliases are folded on the fly), B, C -- and
 //   NQ, State, prepare(n, c, State&), run(n, h, w, c, a[8], b[8], c[8], acc[NQ|1][8], State),
 //   out_index(n, c, q) for the NQ per-(n,c) reductions (accumulated in registers per sample).
 template <typename T, typename OP>
@@ -1234,14 +1245,14 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
         const int st = k % stages;
         sb_mbar_wait(sb_smem(&empty[st]), ((k / stages) & 1) ^ 1);
         const int n = r / H, h = r - n * H;
-        const int alias = p ? (h == 1 ? -1 : (h == H - 2 ? H : -2)) : -2;
+        const int alias = reflect_alias(h, H, p);
         const uint32_t bar = sb_smem(&full[st]);
         const uint32_t base = sb_smem(rs_smem + (size_t)st * stage_bytes);
-        const uint32_t bytes = a_row_bytes + (alias != -2 ? a_row_bytes : 0) + (has_b ? x_row_bytes : 0) +
+        const uint32_t bytes = a_row_bytes + (alias != NO_ALIAS ? a_row_bytes : 0) + (has_b ? x_row_bytes : 0) +
                                (has_c ? x_row_bytes : 0);
         sb_mbar_expect_tx(bar, bytes);
         sb_bulk_load(base, vptr<T>(va, n, h, -p, 0), a_row_bytes, bar);
-        if (alias != -2) sb_bulk_load(base + off_alias, vptr<T>(va, n, alias, -p, 0), a_row_bytes, bar);
+        if (alias != NO_ALIAS) sb_bulk_load(base + off_alias, vptr<T>(va, n, alias, -p, 0), a_row_bytes, bar);
         if (has_b) sb_bulk_load(base + off_b, vptr<T>(vb, n, h, 0, 0), x_row_bytes, bar);
         if (has_c) sb_bulk_load(base + off_c, vptr<T>(vc, n, h, 0, 0), x_row_bytes, bar);
       }
@@ -1296,14 +1307,14 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
     const T* alrow = reinterpret_cast<const T*>(base + off_alias);
     const T* brow = reinterpret_cast<const T*>(base + off_b);
     const T* crow = reinterpret_cast<const T*>(base + off_c);
-    const bool row_alias = p && (h == 1 || h == H - 2);
+    const bool row_alias = reflect_alias(h, H, p) != NO_ALIAS;
     for (int i = tid; i < W * CV; i += 256) {
       const int w = i >> cv_sh;
       float a[V], b[V], c[V];
       load_vec<T, V>(arow + (size_t)(w + p) * C + cv * V, a);
       if (p) {
-        const int wa = (w == 1) ? -1 : ((w == W - 2) ? W : -2);
-        if (wa != -2) {
+        const int wa = reflect_alias(w, W, p);
+        if (wa != NO_ALIAS) {
           float t[V];
           load_vec<T, V>(arow + (size_t)(wa + p) * C + cv * V, t);
 #pragma unroll
@@ -1314,7 +1325,7 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
           load_vec<T, V>(alrow + (size_t)(w + p) * C + cv * V, t);
 #pragma unroll
           for (int e = 0; e < V; ++e) a[e] += t[e];
-          if (wa != -2) {
+          if (wa != NO_ALIAS) {
             load_vec<T, V>(alrow + (size_t)(wa + p) * C + cv * V, t);
 #pragma unroll
             for (int e = 0; e < V; ++e) a[e] += t[e];
@@ -1485,7 +1496,7 @@ struct ChannelSumRowOp {
 static int row_stream_plan(const otm_tensor& A, int a_halo, const otm_tensor* B, const otm_tensor* Cc,
                            const otm_tensor* o1, const otm_tensor* o2, size_t* smem_bytes) {
   static const int use_stream = [] { const char* e = getenv("OTM_ROW_STREAM"); return e ? atoi(e) : 1; }();
-  if (!use_stream || a_halo > 1 || A.c % 8 != 0) return 0;
+  if (!use_stream || a_halo > 3 || A.c % 8 != 0 || A.h < 2 * a_halo + 2 || A.w < 2 * a_halo + 2) return 0;
   // small tensors: the 148 x 288-thread persistent launch with its ring set-up costs more than
   // the register-file kernels
   static const long long min_bytes = [] {
@@ -1681,7 +1692,11 @@ static int down_stream_slots(const otm_down_args* a, size_t* smem_bytes) {
   if (CV < 1 || 256 % CV != 0 || a->y.h < 2 || a->y.w < 2) return 0;
   if (x.sw != C || x.sh % 8 || x.sn % 8 || ((uintptr_t)x.ptr % 16)) return 0;
   const size_t es = dtype_size(x.dtype);
-  if ((long long)x.n * x.h * x.w * C * (long long)es < (8ll << 20)) return 0;
+  static const long long min_bytes = [] {
+    const char* e = getenv("OTM_ROW_STREAM_MIN_MB");
+    return (long long)(e ? atoi(e) : 8) << 20;
+  }();
+  if ((long long)x.n * x.h * x.w * C * (long long)es < min_bytes) return 0;
   const size_t row = ((size_t)x.w * C * es + 127) & ~(size_t)127;
   if (((size_t)x.w * C * es) % 16) return 0;
   int S = (int)((200 * 1024 - 256) / row);
