@@ -1251,17 +1251,29 @@ __global__ void demod_kernel(const float* __restrict__ s, const float* __restric
 }
 
 // ds[b,i] = Q[b,i] + 2 s[b,i] sum_o dd[b,o] q[o,i],  dd = -0.5 sigma_inv^2 P
-__global__ void mod_bwd_ds_kernel(otm_mod_bwd_args a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.nb * a.cin) return;
-  int b = idx / a.cin, i = idx - b * a.cin;
+// A CTA (4 warps) owns 32 consecutive i of one sample: the warps split the o loop (a 128-term
+// dependent chain per thread took 20 us per launch), partial sums meet in shared memory.
+__global__ void __launch_bounds__(128) mod_bwd_ds_kernel(otm_mod_bwd_args a) {
+  __shared__ float part[4][32];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int blocks_per_b = (a.cin + 31) / 32;
+  const int b = blockIdx.x / blocks_per_b, i = (blockIdx.x % blocks_per_b) * 32 + lane;
   float acc = 0.f;
-  for (int o = 0; o < a.cout; ++o) {
-    float si = a.sigma_inv[b * a.cout + o];
-    float dd = -0.5f * si * si * a.P[b * a.cout + o];
-    acc = fmaf(dd, a.q[(long long)o * a.cin + i], acc);
+  if (i < a.cin) {
+    const int o0 = a.cout * wq / 4, o1 = a.cout * (wq + 1) / 4;
+#pragma unroll 4
+    for (int o = o0; o < o1; ++o) {
+      const float si = a.sigma_inv[b * a.cout + o];
+      const float dd = -0.5f * si * si * a.P[b * a.cout + o];
+      acc = fmaf(dd, a.q[(long long)o * a.cin + i], acc);
+    }
   }
-  a.ds[idx] = a.Q[idx] + 2.f * a.s[idx] * acc;
+  part[wq][lane] = acc;
+  __syncthreads();
+  if (wq == 0 && i < a.cin) {
+    const int idx = b * a.cin + i;
+    a.ds[idx] = a.Q[idx] + 2.f * a.s[idx] * (part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane]);
+  }
 }
 // dw[o,i,k] += 2 alpha^2 w[o,i,k] sum_b dd[b,o] s[b,i]^2
 // A CTA (4 warps) owns 32 consecutive (o,i) pairs: the warps split the sample loop, the partial
@@ -1658,7 +1670,7 @@ int otm_mod_bwd(const otm_mod_bwd_args* a, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OTM_REQUIRE(a && a->w && a->s && a->sigma_inv && a->q && a->P && a->Q && a->ds && a->dw,
               "mod_bwd: null");
-  mod_bwd_ds_kernel<<<(a->nb * a->cin + 127) / 128, 128, 0, st>>>(*a);
+  mod_bwd_ds_kernel<<<a->nb * ((a->cin + 31) / 32), 128, 0, st>>>(*a);
   OTM_LAUNCH_CHECK();
   long long cnt = (long long)a->cout * a->cin;
   mod_bwd_dw_kernel<<<(int)((cnt + 31) / 32), 128, 0, st>>>(*a);

@@ -1684,6 +1684,141 @@ down_stream_kernel(DownF<T, 8> f, int N, int Ho, int Wo, int C, int S) {
   if (cur_n >= 0) release_upto(waited_hi + 1);
 }
 
+// Transpose of the DownSample stencil in gather form with a FIXED candidate set: n_out = n_in / 2
+// (DownSample always halves), so floor(src_j) is 2j or 2j+1 and input i can only be touched by the
+// outputs j0 .. j0+2, j0 = max(0, (i-2) >> 1); each candidate's weight is the sum of its taps that
+// land on i (zero if none).
+__device__ __forceinline__ void down_bwd_taps3(int i, int n_in, int n_out, float scale,
+                                               int (&js)[3], float (&wj)[3]) {
+  const int j0 = max(0, (i - 2) >> 1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int j = j0 + c;
+    int pos[4];
+    float wt[4];
+    down_taps(min(j, n_out - 1), n_in, scale, pos, wt);
+    float w = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w += (pos[k] == i) ? wt[k] : 0.f;
+    js[c] = min(j, n_out - 1);
+    wj[c] = j < n_out ? w : 0.f;
+  }
+}
+
+// Windowed row streaming of the DownSample backward: output (full-resolution) row h gathers the
+// half-resolution gradient rows j0 .. j0+2, which the producer lane bulk-copies once each into a
+// ring; the horizontal candidates / weights of every output column are tabulated in shared memory
+// once per CTA.  The pass is then bound by writing ga.
+template <typename T>
+__global__ void __launch_bounds__(288, 1)
+down_bwd_stream_kernel(View g, View ga, float sch, float scw, int C, int S) {
+  constexpr int V = 8;
+  extern __shared__ __align__(128) unsigned char db_smem[];
+  const int N = ga.n, H = ga.h, W = ga.w, Ho = g.h, Wo = g.w;
+  const int CV = C / V;
+  const uint32_t row_bytes = (uint32_t)Wo * C * sizeof(T);
+  const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(db_smem + (size_t)S * slot_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  int* tab_j = reinterpret_cast<int*>(bars + 2 * S);       // [W][3]
+  float* tab_w = reinterpret_cast<float*>(tab_j + 3 * W);  // [W][3]
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    for (int s2 = 0; s2 < S; ++s2) { sb_mbar_init(sb_smem(&full[s2]), 1); sb_mbar_init(sb_smem(&empty[s2]), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int w = threadIdx.x; w < W; w += blockDim.x) {
+    int js[3];
+    float wj[3];
+    down_bwd_taps3(w, W, Wo, scw, js, wj);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { tab_j[3 * w + c] = js[c]; tab_w[3 * w + c] = wj[c]; }
+  }
+  __syncthreads();
+  const int rows = N * H;
+  const int q0 = (int)((long long)rows * blockIdx.x / gridDim.x);
+  const int q1 = (int)((long long)rows * (blockIdx.x + 1) / gridDim.x);
+  auto window = [&](int h, int& lo, int& hi) {
+    lo = min(max(0, (h - 2) >> 1), Ho - 1);
+    hi = min(max(0, (h - 2) >> 1) + 2, Ho - 1);
+  };
+  if (warp == 8) {
+    if (lane == 0) {
+      int k = 0, cur_n = -1, next_in = 0;
+      for (int q = q0; q < q1; ++q) {
+        const int n = q / H, h = q - n * H;
+        int lo, hi;
+        window(h, lo, hi);
+        if (n != cur_n) { cur_n = n; next_in = lo; }
+        for (; next_in <= hi; ++next_in, ++k) {
+          const int st = k % S;
+          sb_mbar_wait(sb_smem(&empty[st]), ((k / S) & 1) ^ 1);
+          const uint32_t bar = sb_smem(&full[st]);
+          sb_mbar_expect_tx(bar, row_bytes);
+          sb_bulk_load(sb_smem(db_smem + (size_t)st * slot_bytes), vptr<T>(g, n, next_in, 0, 0), row_bytes, bar);
+        }
+      }
+    }
+    return;
+  }
+  const int tid = threadIdx.x;
+  const int cv = tid % CV;
+  const int cv_sh = 31 - __clz(CV);
+  int cur_n = -1, first = 0, kbase = 0, waited_hi = -1, released = 0, kcount = 0;
+  auto slot_of = [&](int r) { return (kbase + (r - first)) % S; };
+  auto release_upto = [&](int upto) {
+    __syncwarp();
+    if (lane == 0)
+      for (int r = released; r < upto; ++r) sb_mbar_arrive(sb_smem(&empty[slot_of(r)]));
+    released = max(released, upto);
+  };
+  for (int q = q0; q < q1; ++q) {
+    const int n = q / H, h = q - n * H;
+    int lo, hi;
+    window(h, lo, hi);
+    if (n != cur_n) {
+      if (cur_n >= 0) release_upto(waited_hi + 1);
+      cur_n = n;
+      first = lo; kbase = kcount; waited_hi = lo - 1; released = lo;
+    }
+    release_upto(lo);
+    for (int r = waited_hi + 1; r <= hi; ++r) {
+      const int k = kbase + (r - first);
+      sb_mbar_wait(sb_smem(&full[k % S]), (k / S) & 1);
+    }
+    if (hi > waited_hi) { kcount += hi - waited_hi; waited_hi = hi; }
+    int jh[3];
+    float wh[3];
+    down_bwd_taps3(h, H, Ho, sch, jh, wh);
+    const T* rp[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      rp[a] = reinterpret_cast<const T*>(db_smem + (size_t)slot_of(min(max(jh[a], lo), hi)) * slot_bytes);
+    for (int i = tid; i < W * CV; i += 256) {
+      const int w = i >> cv_sh;
+      float acc[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int jw = tab_j[3 * w + b];
+        const float wwb = tab_w[3 * w + b];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          float v[V];
+          load_vec<T, V>(rp[a] + (size_t)jw * C + cv * V, v);
+          const float wgt = wh[a] * wwb;
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] += wgt * v[e];
+        }
+      }
+      store_vec<T, V>(vptr_mut<T>(ga, n, h, w, cv * V), acc);
+    }
+  }
+  if (cur_n >= 0) release_upto(waited_hi + 1);
+}
+
 static int down_stream_slots(const otm_down_args* a, size_t* smem_bytes) {
   static const int use_stream = [] { const char* e = getenv("OTM_DOWN_STREAM"); return e ? atoi(e) : 1; }();
   const otm_tensor& x = a->x;
@@ -2001,6 +2136,43 @@ int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_
   OTM_REQUIRE(g->dtype == ga->dtype, "down_bwd: dtype mismatch");
   bool vok = vec_ok(*g, 8) && vec_ok(*ga, 8);
   int rc = OTM_OK;
+  {
+    // windowed row streaming (odd and even sizes): g rows are small, the pass is write-bound
+    static const int use_stream = [] { const char* e = getenv("OTM_DOWN_BWD_STREAM"); return e ? atoi(e) : 1; }();
+    static const long long min_bytes = [] {
+      const char* e = getenv("OTM_ROW_STREAM_MIN_MB");
+      return (long long)(e ? atoi(e) : 8) << 20;
+    }();
+    const int C = g->c, CV = C / 8;
+    const size_t es = dtype_size(g->dtype);
+    const size_t row = ((size_t)g->w * C * es + 127) & ~(size_t)127;
+    const bool ok = use_stream && vok && g_halo == 0 && C % 8 == 0 && CV >= 1 && 256 % CV == 0 &&
+                    g->sw == C && g->sh % 8 == 0 && g->sn % 8 == 0 && ((uintptr_t)g->ptr % 16 == 0) &&
+                    ((size_t)g->w * C * es) % 16 == 0 && g->h >= 3 && g->w >= 3 && ga->w <= 1024 &&
+                    (long long)ga->n * ga->h * ga->w * C * (long long)es >= min_bytes;
+    int S = ok ? (int)((160 * 1024) / row) : 0;
+    if (S > 12) S = 12;
+    if (S >= 5) {
+      const size_t smem = row * S + 2 * 8 * S + (size_t)ga->w * 3 * 8 + 64;
+      int grid = num_sms();
+      if (grid > ga->n * ga->h) grid = ga->n * ga->h;
+#define OTM_DBS(T)                                                                                 \
+  do {                                                                                              \
+    auto kern = down_bwd_stream_kernel<T>;                                                          \
+    static bool set_ = false;                                                                       \
+    if (!set_) {                                                                                    \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      set_ = true;                                                                                  \
+    }                                                                                               \
+    kern<<<grid, 288, smem, st>>>(make_view(*g), make_view(*ga), (float)ga->h / (float)g->h,        \
+                                  (float)ga->w / (float)g->w, C, S);                                \
+  } while (0)
+      if (g->dtype == OTM_BF16) OTM_DBS(__nv_bfloat16); else OTM_DBS(float);
+#undef OTM_DBS
+      OTM_LAUNCH_CHECK();
+      return OTM_OK;
+    }
+  }
   static const int blk = [] { const char* e = getenv("OTM_DOWN_BLOCK"); return e ? atoi(e) : 1; }();
   const bool even = ga->h == 2 * g->h && ga->w == 2 * g->w && g->h >= 4 && g->w >= 4;
   OTM_DISPATCH_TV(g->dtype, vok, {

@@ -123,3 +123,16 @@ def test_stream_down(K, shape):
     assert torch.equal(K.padded_view(out, 1).float(), F.pad(out.float(), (1,) * 4, mode="reflect"))
     plain = K.down(xt)
     assert relerr(plain.float(), rp.down_sample(x, kern)) < TOL[torch.bfloat16], shape
+
+
+@pytest.mark.parametrize("shape", [(16, 64, 128, 128), (16, 64, 127, 127), (16, 128, 62, 62)])
+def test_stream_down_bwd(K, shape):
+    from oracle import reference_port as rp
+
+    kern = rp._smooth_kernel().cuda()
+    x = rnd(*shape, seed=12).requires_grad_(True)
+    y = rp.down_sample(x, kern)
+    g = rnd(*y.shape, seed=13).bfloat16().float()
+    (want,) = torch.autograd.grad(y, x, g)
+    ga = K.down_bwd(to_nhwc(K, g), shape[2:])
+    assert relerr(ga.float(), want) < TOL[torch.bfloat16], shape
