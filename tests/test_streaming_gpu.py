@@ -136,3 +136,14 @@ def test_stream_down_bwd(K, shape):
     (want,) = torch.autograd.grad(y, x, g)
     ga = K.down_bwd(to_nhwc(K, g), shape[2:])
     assert relerr(ga.float(), want) < TOL[torch.bfloat16], shape
+
+
+@pytest.mark.parametrize("shape", [(16, 128, 64, 64), (8, 64, 96, 80)])
+def test_stream_up(K, shape):
+    from oracle import reference_port as rp
+
+    kern = rp._smooth_kernel().cuda()
+    x = rnd(*shape, seed=14).bfloat16().float()
+    want = rp.up_sample(x, kern)
+    out = K.up(to_nhwc(K, x))
+    assert relerr(out.float(), want) < TOL[torch.bfloat16], shape
