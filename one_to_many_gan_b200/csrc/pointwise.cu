@@ -1210,8 +1210,15 @@ __device__ __forceinline__ int reflect_alias(int i, int n, int p) {
 // view of a reflect-padded tensor with halo <= 3: its aliases are folded on the fly), B, C -- and
 //   NQ, State, prepare(n, c, State&), run(n, h, w, c, a[8], b[8], c[8], acc[NQ|1][8], State),
 //   out_index(n, c, q) for the NQ per-(n,c) reductions (accumulated in registers per sample).
+// consumer threads per CTA of the row-streaming kernel (+ one producer warp).  8 warps left an
+// eligible warp in only 46 % of the cycles (profiles/r1_ncu_row_stream.md)
+#ifndef OTM_RS_THREADS
+#define OTM_RS_THREADS 512
+#endif
+constexpr int RS_THREADS = OTM_RS_THREADS;
+
 template <typename T, typename OP>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(RS_THREADS + 32, 1)
 row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out) {
   constexpr int V = 8;
   constexpr int NQ = OP::NQ;
@@ -1231,14 +1238,14 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
   uint64_t* empty = bars + stages;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (threadIdx.x == 0) {
-    for (int s2 = 0; s2 < stages; ++s2) { sb_mbar_init(sb_smem(&full[s2]), 1); sb_mbar_init(sb_smem(&empty[s2]), 8); }
+    for (int s2 = 0; s2 < stages; ++s2) { sb_mbar_init(sb_smem(&full[s2]), 1); sb_mbar_init(sb_smem(&empty[s2]), RS_THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int rows = N * H;
   const int r0 = (int)((long long)rows * blockIdx.x / gridDim.x);
   const int r1 = (int)((long long)rows * (blockIdx.x + 1) / gridDim.x);
-  if (warp == 8) {
+  if (warp == RS_THREADS / 32) {
     // ---------------- producer ----------------
     if (lane == 0) {
       for (int r = r0, k = 0; r < r1; ++r, ++k) {
@@ -1259,8 +1266,8 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
     }
     return;
   }
-  // ---------------- consumers (8 warps) ----------------
-  const int tid = threadIdx.x;  // 0..255
+  // ---------------- consumers (RS_THREADS / 32 warps) ----------------
+  const int tid = threadIdx.x;  // 0..RS_THREADS-1
   const int cv = tid % CV;      // constant per thread: CV divides 256 (so it is a power of two)
   const int cv_sh = 31 - __clz(CV);
   typename OP::State st;
@@ -1272,25 +1279,25 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
     for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
   // per-sample flush of the register accumulators: the 256 / CV threads that share a channel
   // vector meet in shared memory first, so one atomic per (n, c, q) and CTA reaches L2
-  float* red_sm = reinterpret_cast<float*>(bars + 2 * stages);  // [NQ * V][256]
+  float* red_sm = reinterpret_cast<float*>(bars + 2 * stages);  // [NQ * V][RS_THREADS]
   auto flush = [&](int n) {
     if (NQ > 0 && n >= 0) {  // n and the call sites are uniform over the consumer warps
 #pragma unroll
       for (int q = 0; q < NQ; ++q)
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          red_sm[(q * V + i) * 256 + tid] = acc[q][i];
+          red_sm[(q * V + i) * RS_THREADS + tid] = acc[q][i];
           acc[q][i] = 0.f;
         }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int groups = 256 / CV;  // threads tid, tid + CV, ... hold the same channel vector
-      for (int o = tid; o < NQ * V * CV; o += 256) {
+      asm volatile("bar.sync 1, %0;" ::"n"(RS_THREADS) : "memory");
+      const int groups = RS_THREADS / CV;  // threads tid, tid + CV, ... hold the same channel vector
+      for (int o = tid; o < NQ * V * CV; o += RS_THREADS) {
         const int c_v = o % CV, qi = o / CV;  // qi = q * V + i
         float sum = 0.f;
-        for (int g2 = 0; g2 < groups; ++g2) sum += red_sm[qi * 256 + g2 * CV + c_v];
+        for (int g2 = 0; g2 < groups; ++g2) sum += red_sm[qi * RS_THREADS + g2 * CV + c_v];
         atomicAdd(red_out + op.out_index(n, c_v * V + qi % V, qi / V), sum);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(RS_THREADS) : "memory");
     }
   };
   for (int r = r0, k = 0; r < r1; ++r, ++k) {
@@ -1308,7 +1315,7 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
     const T* brow = reinterpret_cast<const T*>(base + off_b);
     const T* crow = reinterpret_cast<const T*>(base + off_c);
     const bool row_alias = reflect_alias(h, H, p) != NO_ALIAS;
-    for (int i = tid; i < W * CV; i += 256) {
+    for (int i = tid; i < W * CV; i += RS_THREADS) {
       const int w = i >> cv_sh;
       float a[V], b[V], c[V];
       load_vec<T, V>(arow + (size_t)(w + p) * C + cv * V, a);
@@ -1517,7 +1524,7 @@ static int row_stream_plan(const otm_tensor& A, int a_halo, const otm_tensor* B,
   if (arow % 16 || xrow % 16) return 0;
   const size_t stage = (arow * (a_halo ? 2 : 1) + ((B && B->ptr) ? xrow : 0) + ((Cc && Cc->ptr) ? xrow : 0) + 127) &
                        ~(size_t)127;
-  const size_t scratch = 2 * 8 * 256 * sizeof(float);  // reduction flush scratch [NQ * V][256]
+  const size_t scratch = 2 * 8 * RS_THREADS * sizeof(float);  // reduction flush scratch [NQ * V][threads]
   int stages = (int)((200 * 1024 - 256 - scratch) / stage);
   if (stages < 2) return 0;
   if (stages > 8) stages = 8;
@@ -1536,7 +1543,7 @@ static int launch_row_stream(const OP& op, int N, int H, int W, int C, int stage
   }
   int grid = num_sms();
   if (grid > N * H) grid = N * H;
-  kern<<<grid, 288, smem, st>>>(op, N, H, W, C, stages, red_out);
+  kern<<<grid, RS_THREADS + 32, smem, st>>>(op, N, H, W, C, stages, red_out);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
 }
