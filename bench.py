@@ -42,6 +42,23 @@ CONFIG = {
     "data": {"image_size": list(IMAGE), "image_channels": 1},
 }
 WORKLOAD = "G+D train iteration, default arch, 128x128, batch 32/GPU, bf16 act / fp32 accum"
+# dense-conv algorithmic GFLOP per image per iteration for the extra configs
+GFLOP_256 = 1441.2
+
+
+def base_config(world):
+    """The `config` object both arms print (the driver compares them)."""
+    return {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+            "l2": "activations per step (>1 GB) exceed the 126 MB L2"}
+
+
+def make_config(image, batch):
+    import copy
+
+    cfg = copy.deepcopy(CONFIG)
+    cfg["training"]["batch_size"] = batch
+    cfg["data"]["image_size"] = list(image)
+    return cfg
 
 
 def peaks():
@@ -117,22 +134,24 @@ class HostBatches:
         return t
 
 
-def build_trainer(device, rank, use_graph=True):
+def build_trainer(device, rank, use_graph=True, config=None):
     """The four networks + optimisers + the CUDA-graph iteration engine (public API:
     one_to_many_gan_b200.engine.TrainIteration)."""
     from one_to_many_gan_b200 import builder
     from one_to_many_gan_b200.engine import TrainIteration
     from one_to_many_gan_b200.optim import FlatAdam
 
+    config = config or CONFIG
+    image = tuple(config["data"]["image_size"])
     torch.manual_seed(42)
-    arch = CONFIG["architecture"]
+    arch = config["architecture"]
     dt = torch.bfloat16
     D = builder.Discriminator(1, act_dtype=dt).to(device)
-    G = builder.Generator(1, arch["w_dim"], IMAGE, arch["min_latent_resolution"],
+    G = builder.Generator(1, arch["w_dim"], image, arch["min_latent_resolution"],
                           arch["n_resnet_blocks"], act_dtype=dt).to(device)
     M = builder.MappingNetwork(arch["w_dim"], arch["mapping_network_layers"], 0.9).to(device)
     S = builder.StyleExtractor(1, arch["w_dim"], act_dtype=dt).to(device)
-    o = CONFIG["optimisation"]
+    o = config["optimisation"]
     betas = tuple(o["adam_betas"])
     oD = FlatAdam(D.parameters(), o["learning_rate"], betas)
     oG = FlatAdam(G.parameters(), o["learning_rate"], betas)
@@ -142,7 +161,7 @@ def build_trainer(device, rank, use_graph=True):
     import random
 
     random.seed(1234 + rank)
-    eng = TrainIteration(CONFIG, device, D, G, M, S, oD, oG, oM, oS, use_graph=use_graph, warmup=2)
+    eng = TrainIteration(config, device, D, G, M, S, oD, oG, oM, oS, use_graph=use_graph, warmup=2)
 
     def step(prints, marks):
         # one iteration consumes two shoeprint and two shoemark batches (D step, then G step)
@@ -267,47 +286,109 @@ def hbm_kernel_roofline(device):
             "bytes_per_launch": nbytes}
 
 
-def cpu_baseline(sample_batch=2, iters=1, warm=0):
-    """The oracle port (oracle/reference_port.py) of the same iteration on the host cores."""
+def _oracle_trainer(batch, device="cpu"):
     from oracle import reference_port as rp
 
-    torch.set_num_threads(os.cpu_count() or 1)
     arch = rp.Arch(image_size=IMAGE)
-    tr = rp.Trainer(arch, rp.Hyper(batch_size=sample_batch), rp.init_all(arch, 42))
-    shape = (sample_batch, 1, *IMAGE)
+    tr = rp.Trainer(arch, rp.Hyper(batch_size=batch), rp.init_all(arch, 42), device=device)
 
     def one(i):
-        tr.discriminator_step(rp.synthetic_batch(sample_batch, arch, 10 + i), rp.synthetic_batch(sample_batch, arch, 20 + i))
-        tr.generator_step(rp.synthetic_batch(sample_batch, arch, 30 + i), rp.synthetic_batch(sample_batch, arch, 40 + i))
+        b = [rp.synthetic_batch(batch, arch, 10 * k + i).to(device) for k in range(1, 5)]
+        tr.discriminator_step(b[0], b[1])
+        tr.generator_step(b[2], b[3])
 
-    for i in range(warm):
-        one(i)
-    t0 = time.perf_counter()
-    for i in range(iters):
-        one(100 + i)
-    dt = time.perf_counter() - t0
-    del shape
-    return {"value": round(sample_batch * iters / dt, 4), "unit": "images/sec",
-            "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{iters} D+G iteration(s) at 128x128, batch {sample_batch} (workload batch is {BATCH}), fp32, torch CPU"}, dt
+    return one
+
+
+def cpu_baseline(batches=(2, 8, BATCH)):
+    """The oracle port (oracle/reference_port.py) of the same iteration on the host cores:
+    one warm-up iteration (batch 2: thread pools, MKL-DNN primitive caches), then ONE timed D+G
+    iteration per batch size -- the last one is the workload's own batch; the smaller ones show
+    how the CPU's per-image cost depends on the batch.  `value` is the workload-batch number."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    _oracle_trainer(2)(0)  # warm-up
+    by_batch = {}
+    for b in batches:
+        one = _oracle_trainer(b)
+        t0 = time.perf_counter()
+        one(100)
+        by_batch[str(b)] = round(b / (time.perf_counter() - t0), 4)
+    return {"value": by_batch[str(batches[-1])], "unit": "images/sec", "cores": torch.get_num_threads(),
+            "kind": "port", "by_batch": by_batch,
+            "sample": f"1 warm-up (batch 2) + 1 timed D+G iteration each at batch {list(batches)}, "
+                      f"128x128, fp32, torch CPU; value = batch {batches[-1]} (the workload's)"}
+
+
+def gpu_baseline(device, iters=10, warm=2):
+    """The 'existing Blackwell kernel' bar: the SAME iteration as eager
+    PyTorch on this B200 -- the oracle port's functional torch ops (cuDNN / cuBLAS / ATen of
+    torch 2.11) at the workload's batch 32, 128x128 -- in the two modes a user of the reference
+    would run: (i) fp32 with TF32 allowed, as reference train.py:67-68 sets it; (ii) bf16 autocast
+    with channels_last images and weights.  CUDA events, `warm` untimed + `iters` timed."""
+    out = {}
+    dev = str(device)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
+             torch.get_float32_matmul_precision(), torch.backends.cudnn.benchmark)
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.set_float32_matmul_precision("medium")
+        for mode in ("tf32", "bf16"):
+            from oracle import reference_port as rp
+
+            arch = rp.Arch(image_size=IMAGE)
+            tr = rp.Trainer(arch, rp.Hyper(batch_size=BATCH), rp.init_all(arch, 42), device=dev)
+            if mode == "bf16":
+                for net in tr.params.values():
+                    for k, v in net.items():
+                        if v.dim() == 4:
+                            net[k] = v.contiguous(memory_format=torch.channels_last)
+            bat = [rp.synthetic_batch(BATCH, arch, 7 + k).to(device) for k in range(4)]
+            if mode == "bf16":
+                bat = [b.contiguous(memory_format=torch.channels_last) for b in bat]
+
+            def one():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+                    tr.discriminator_step(bat[0], bat[1])
+                    tr.generator_step(bat[2], bat[3])
+
+            for _ in range(warm):
+                one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[mode] = {"value": round(BATCH / ms * 1e3, 2), "ms_per_step": round(ms, 2)}
+            del tr, bat
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved[0], saved[1]
+        torch.set_float32_matmul_precision(saved[2])
+    out.update({"unit": "images/sec", "kind": "port on cuda:0 (eager torch %s, cuDNN %s)" % (
+        torch.__version__, torch.backends.cudnn.version()),
+        "sample": f"{warm} warm-up + {iters} timed D+G iterations, 128x128, batch {BATCH}; tf32 = fp32 "
+                  "storage with TF32 convs/matmuls (reference train.py:67-68); bf16 = autocast + "
+                  "channels_last.  The port skips two things the reference wastes (the G autograd "
+                  "graph of the D step, D's weight gradients in the G step), so this bar is not "
+                  "lower than the reference's own eager run."})
+    return out
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the
-    reference itself is pure Python/PyTorch and is pinned to the port by tests/golden)."""
+    reference itself is pure Python/PyTorch and is pinned to the port by tests/golden) on all
+    host cores.  Each step is a bounded sample of the workload: one D+G iteration at batch 8
+    (the workload's batch is 32; the CPU's img/s at batch 2 / 8 / 32 is in the b200 arm's
+    `cpu_baseline.by_batch`)."""
     if rank != 0:
         return
-    sample_batch = 2
-    from oracle import reference_port as rp
-
+    sample_batch = 8
     torch.set_num_threads(os.cpu_count() or 1)
-    arch = rp.Arch(image_size=IMAGE)
-    tr = rp.Trainer(arch, rp.Hyper(batch_size=sample_batch), rp.init_all(arch, 42))
-
-    def one(i):
-        tr.discriminator_step(rp.synthetic_batch(sample_batch, arch, 10 + i), rp.synthetic_batch(sample_batch, arch, 20 + i))
-        tr.generator_step(rp.synthetic_batch(sample_batch, arch, 30 + i), rp.synthetic_batch(sample_batch, arch, 40 + i))
-
+    one = _oracle_trainer(sample_batch)
     for i in range(args.warmup):
         one(i)
     t0 = time.perf_counter()
@@ -316,19 +397,45 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     val = sample_batch * args.steps / dt
     sample = (f"each step = one D+G iteration at 128x128 on batch {sample_batch} (bounded sample of the "
-              f"batch-{BATCH} workload; per-image cost is batch-independent: per-sample norms)")
+              f"batch-{BATCH} workload), fp32, torch CPU, {torch.get_num_threads()} threads")
     line = {
         "impl": "reference", "metric": "G+D train-step images/sec", "value": round(val, 4),
         "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1000 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_arm": sample},
+        "config": base_config(world),
         "cpu_baseline": {"value": round(val, 4), "unit": "images/sec", "cores": torch.get_num_threads(),
                          "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "images/sec", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
+    if torch.cuda.is_available() and os.environ.get("OTM_REF_GPU", "1") == "1":
+        try:  # the eager-PyTorch-on-B200 bar, reported next to the CPU number
+            line["gpu_baseline"] = gpu_baseline(torch.device("cuda", 0), iters=5, warm=2)
+        except Exception as e:  # noqa: BLE001 - the CPU arm must still print its line
+            line["gpu_baseline"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
+
+
+def extra_config(device, rank, world, dist_on, image, batch, gflop, steps=5):
+    """Another BASELINE config through the same engine (device-resident inputs, CUDA events,
+    max over ranks): reported under `configs`, not the headline."""
+    from one_to_many_gan_b200.synthetic import SyntheticImages
+
+    cfg = make_config(image, batch)
+    step = build_trainer(device, rank, True, cfg)
+    prints = SyntheticImages(batch, 1, image, device, seed=42, rank=rank, stream_id=0)
+    marks = SyntheticImages(batch, 1, image, device, seed=42, rank=rank, stream_id=1)
+    ms, last = time_steps(step, prints, marks, steps, 4, dist_on, device)
+    value = world * batch * steps / (ms / 1e3)
+    pk, _ = peaks()
+    tf = gflop * value / world / 1e3
+    return {"workload": f"{image[0]}x{image[1]}, batch {batch}/GPU, bf16", "value": round(value, 2),
+            "unit": "images/sec", "ms_per_step": round(ms / steps, 3), "steps": steps,
+            "conv_tflops_per_gpu": round(tf, 1),
+            "conv_frac_of_sustained_peak": round(tf / pk["bf16_tflops_sustained"], 4),
+            "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2**30, 1),
+            "losses_finite": all(v == v for v in last.values())}
 
 
 def main():
@@ -338,6 +445,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -404,10 +513,9 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": BATCH * world,
-                       "parallelism": f"dp{world}", "l2": "activations per step (>1 GB) exceed the 126 MB L2",
-                       "execution": "one CUDA graph per iteration" if use_graph else "eager",
-                       "losses": {k: round(v, 5) for k, v in last.items()}},
+            "config": base_config(world),
+            "execution": "one CUDA graph per iteration" if use_graph else "eager",
+            "losses": {k: round(v, 5) for k, v in last.items()},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
@@ -421,8 +529,20 @@ def main():
                 "note": "algorithmic dense-conv FLOPs/image (SURVEY 8d) x images/s / sustained bf16 peak",
             },
         }
+    # ---- BASELINE config 3 (256x256, batch 32 per GPU) through the same engine, every N -------
+    del step
+    torch.cuda.empty_cache()
+    extra = None
+    if not args.no_extra_configs:
+        extra = [extra_config(device, rank, world, dist_on, (256, 256), 32, GFLOP_256)]
+        torch.cuda.empty_cache()
+    if rank == 0:
+        if extra:
+            line["configs"] = extra
+        if world == 1 and not args.no_gpu_baseline:
+            line["gpu_baseline"] = gpu_baseline(device)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if dist_on:
         dist.barrier()

@@ -96,6 +96,7 @@ class Generator(nn.Module):
             filters *= 2
         encoder += [ResnetBlock(filters) for _ in range(n_enc_res)]
         self.encoder = nn.Sequential(*encoder)
+        self.latent_channels = filters
 
         decoder: list[nn.Module] = [ModulatedResnetBlock(filters, w_dim=w_dim) for _ in range(n_dec_res)]
         for _ in range(n_down):
@@ -111,6 +112,13 @@ class Generator(nn.Module):
             [isinstance(m, ModulatedResnetBlock | Conv2dWeightModulate) for m in self.decoder]
         )
         self.latent_halo = 1 if n_dec_res > 0 else 0
+
+    def latent_shape(self, image_shape):
+        """Shape of encode(x) for an image batch of shape [B,C,H,W] (every DownSample floors)."""
+        b, _, h, w = image_shape
+        for _ in range(self.n_down):
+            h, w = h // 2, w // 2
+        return (b, self.latent_channels, h, w)
 
     # -- encoder ---------------------------------------------------------------------
     def encode(self, x: torch.Tensor):

@@ -46,13 +46,30 @@ inline int fail(int code, const char* fmt, ...) {
     OTM_CHECK_CUDA(cudaGetLastError());        \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember it
+// per (call site = kernel instantiation, device), thread-safe.  One bit per device ordinal.
+#define OTM_ENSURE_SMEM(kern, bytes)                                                         \
+  do {                                                                                        \
+    static std::atomic<unsigned long long> done_{0};                                          \
+    int dev_ = 0;                                                                             \
+    OTM_CHECK_CUDA(cudaGetDevice(&dev_));                                                     \
+    const unsigned long long bit_ = 1ull << (dev_ & 63);                                      \
+    if (!(done_.load(std::memory_order_acquire) & bit_)) {                                    \
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          (int)(bytes)));                                     \
+      done_.fetch_or(bit_, std::memory_order_release);                                        \
+    }                                                                                         \
+  } while (0)
+
 inline int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = cached[dev & 63].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cached[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -324,11 +324,7 @@ static int launch_cout1_tiled(const ConvP& p, int n, cudaStream_t st) {
   const int tiles_w = (p.y.w + TT - 1) / TT, tiles_h = (p.y.h + TT - 1) / TT;
   const int per_img = tiles_w * tiles_h, total = per_img * n;
   auto kern = conv_cout1_tiled_kernel<TI, TO, KS>;
-  static bool attr_set = false;  // once, outside any stream capture
-  if (!attr_set) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  OTM_ENSURE_SMEM(kern, (int)smem);
   int ctas = num_sms() * (smem > 110 * 1024 ? 1 : 2);
   if (ctas > total) ctas = total;
   kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);
@@ -1352,12 +1348,8 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
     const int tiles_w = (a->y.w + G::TWO - 1) / G::TWO, tiles_h = (a->y.h + G::TH - 1) / G::TH;   \
     const int per_img = tiles_w * tiles_h, total = per_img * a->y.n;                              \
     auto kern = conv_cout1_mma_kernel<TO, KS, MW>;                                                \
-    static bool set_ = false;                                                                     \
-    if (!set_) {                                                                                  \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                          (int)smem));                                            \
-      set_ = true;                                                                                \
-    }                                                                                             \
+    OTM_ENSURE_SMEM(kern,      \
+                                          (int)smem);                                                                                             \
     int ctas = num_sms() * (MW == 1 ? 3 : 1);                                                     \
     if (ctas > total) ctas = total;                                                               \
     kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);                                    \
@@ -1398,12 +1390,8 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
 #define OTM_LAUNCH_SMALL(TI, TO, V)                                                          \
   do {                                                                                        \
     auto kern = conv_small_cout_kernel<TI, TO, V>;                                            \
-    static bool set_ = false;                                                                 \
-    if (!set_) {                                                                              \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                          160 * 1024));                                       \
-      set_ = true;                                                                            \
-    }                                                                                         \
+    OTM_ENSURE_SMEM(kern,  \
+                                          160 * 1024);                                                                                         \
     kern<<<grid, 128, smem, st>>>(p);                                                         \
   } while (0)
     if (in_bf && out_bf) { if (v8) OTM_LAUNCH_SMALL(__nv_bfloat16, __nv_bfloat16, 8); else OTM_LAUNCH_SMALL(__nv_bfloat16, __nv_bfloat16, 1); }
@@ -1442,12 +1430,8 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
   do {                                                                                            \
     const size_t smem = sizeof(TDY) * TT * TT * 64 + sizeof(float) * (TT + KS - 1) * (TT + KS - 1); \
     auto kern = wgrad_cin1_kernel<TDY, KS>;                                                       \
-    static bool set_ = false;                                                                     \
-    if (!set_) {                                                                                  \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                          (int)smem));                                            \
-      set_ = true;                                                                                \
-    }                                                                                             \
+    OTM_ENSURE_SMEM(kern,      \
+                                          (int)smem);                                                                                             \
     kern<<<ctas, NT, smem, st>>>(p, tiles_w, per_img, total);                                     \
   } while (0)
     static const int thin_mma = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
@@ -1456,12 +1440,8 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
   do {                                                                                            \
     const size_t smem = sizeof(__nv_bfloat16) * (TT * TT * 72 + (TT + KS - 1) * (TT + KS - 1) + 8); \
     auto kern = wgrad_cin1_mma_kernel<KS>;                                                        \
-    static bool set_ = false;                                                                     \
-    if (!set_) {                                                                                  \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                          (int)smem));                                            \
-      set_ = true;                                                                                \
-    }                                                                                             \
+    OTM_ENSURE_SMEM(kern,      \
+                                          (int)smem);                                                                                             \
     kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);                                    \
   } while (0)
       if (a->kh == 7) OTM_WM1(7); else OTM_WM1(4);
@@ -1490,12 +1470,8 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
     const int tiles_w = (a->dy.w + G::TWO - 1) / G::TWO, tiles_h = (a->dy.h + G::TH - 1) / G::TH; \
     const int per_img = tiles_w * tiles_h, total = per_img * a->dy.n;                             \
     auto kern = wgrad_cout1_mma_kernel<TDY, KS, MW>;                                              \
-    static bool set_ = false;                                                                     \
-    if (!set_) {                                                                                  \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                          (int)smem));                                            \
-      set_ = true;                                                                                \
-    }                                                                                             \
+    OTM_ENSURE_SMEM(kern,      \
+                                          (int)smem);                                                                                             \
     int ctas = num_sms() * (MW == 1 ? 3 : 1);                                                     \
     if (ctas > total) ctas = total;                                                               \
     kern<<<ctas, 256, smem, st>>>(p, tiles_w, per_img, total);                                    \
@@ -1527,12 +1503,8 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
 #define OTM_WO1(TX, TDY)                                                                        \
   do {                                                                                          \
     auto kern = wgrad_cout1_kernel<TX, TDY>;                                                    \
-    static bool set_ = false;                                                                   \
-    if (!set_) {                                                                                \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                          100 * 1024));                                         \
-      set_ = true;                                                                              \
-    }                                                                                           \
+    OTM_ENSURE_SMEM(kern,    \
+                                          100 * 1024);                                                                                           \
     kern<<<ctas, nthreads, smem, st>>>(p, TT, tiles_w, per_img, total_tiles);                   \
   } while (0)
       const bool xb = a->x.dtype == OTM_BF16, yb = a->dy.dtype == OTM_BF16;
@@ -1563,12 +1535,8 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
 #define OTM_WG_SMALL(TX, TDY)                                                                   \
   do {                                                                                          \
     auto kern = wgrad_small_cout_kernel<TX, TDY>;                                               \
-    static bool set_ = false;                                                                   \
-    if (!set_) {                                                                                \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                          200 * 1024));                                         \
-      set_ = true;                                                                              \
-    }                                                                                           \
+    OTM_ENSURE_SMEM(kern,    \
+                                          200 * 1024);                                                                                           \
     kern<<<ctas, 256, smem, st>>>(p, TT, tiles_w, per_img, total_tiles, vec8);                  \
   } while (0)
       const int vec8 = vec_ok(a->x, 8) ? 1 : 0;

@@ -1709,11 +1709,7 @@ static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcFw
   constexpr int tile = 128 * (BN * 2 + 16);  // epilogue staging tile aliases the ring
   constexpr int smem = (ring > tile ? ring : tile) + 1024 + 256 + 2 * BN * 4;
   auto kern = conv_tc_fwd_kernel<BN, STAGES, OCC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  OTM_ENSURE_SMEM(kern, smem);
   kern<<<grid, 256, smem, st>>>(tmA, tmB, p);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
@@ -1728,11 +1724,7 @@ static int launch_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB,
   constexpr int smem = ring + tile + 1024 + 256 + 2 * BN * 4;
   static_assert(smem <= 227 * 1024, "persistent conv kernel exceeds shared memory");
   auto kern = conv_tc_fwd_persist_kernel<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  OTM_ENSURE_SMEM(kern, smem);
   kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
@@ -1745,11 +1737,7 @@ static int launch_fwd_rr(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                        512 + 2 * BN * 4;
   static_assert(smem <= 227 * 1024, "row-reuse conv kernel exceeds shared memory");
   auto kern = conv_tc_fwd_rr_kernel<BN, KS, NA, NB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  OTM_ENSURE_SMEM(kern, smem);
   kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
@@ -1763,11 +1751,7 @@ static int launch_fwd_rr2(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   static_assert(smem <= 227 * 1024, "pair conv kernel exceeds shared memory");
   static_assert(4 * BN <= 512, "pair conv kernel exceeds TMEM");
   auto kern = conv_tc_fwd_rr2_kernel<BN, KS, NA, NB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  OTM_ENSURE_SMEM(kern, smem);
   kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
@@ -1779,11 +1763,7 @@ static int launch_fwd_rr2t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   constexpr int smem = NA * (32 + KS - 1) * 8 * 128 + NB * 128 * 128 + 2 * 128 * 128 + 1024 + 512;
   static_assert(smem <= 227 * 1024, "transposed pair conv kernel exceeds shared memory");
   auto kern = conv_tc_fwd_rr2t_kernel<KS, NA, NB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  OTM_ENSURE_SMEM(kern, smem);
   kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
@@ -1921,11 +1901,7 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
                         cudaStream_t st) {
   constexpr int smem = STAGES * (2 * WG_CHUNK_BYTES + (BN / 64) * WG_CHUNK_BYTES) + 1024 + 256;
   auto kern = conv_tc_wgrad_kernel<BN, STAGES, OCC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  OTM_ENSURE_SMEM(kern, smem);
   kern<<<grid, 256, smem, st>>>(tmA, tmB, p);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
@@ -1937,11 +1913,7 @@ static int launch_wgrad_rr(const CUtensorMap& tmX, const CUtensorMap& tmDy, cons
   constexpr int smem = STAGES * (XCH * (8 + KS - 1) * 1024 + DCH * 8 * 1024) + 1024 + 256;
   static_assert(smem <= 227 * 1024, "wgrad rr ring exceeds shared memory");
   auto kern = conv_tc_wgrad_rr_kernel<XCH, DCH, KS, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  OTM_ENSURE_SMEM(kern, smem);
   kern<<<grid, 256, smem, st>>>(tmX, tmDy, p);
   OTM_LAUNCH_CHECK();
   return OTM_OK;

@@ -1536,11 +1536,7 @@ template <typename T, typename OP>
 static int launch_row_stream(const OP& op, int N, int H, int W, int C, int stages, size_t smem,
                              float* red_out, cudaStream_t st) {
   auto kern = row_stream_kernel<T, OP>;
-  static bool set_ = false;
-  if (!set_) {
-    OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    set_ = true;
-  }
+  OTM_ENSURE_SMEM(kern, 200 * 1024);
   int grid = num_sms();
   if (grid > N * H) grid = N * H;
   kern<<<grid, RS_THREADS + 32, smem, st>>>(op, N, H, W, C, stages, red_out);
@@ -2107,11 +2103,7 @@ int otm_down(const otm_down_args* a, otm_stream stream) {
     DownF<T, 8> f{make_view(a->x), make_view(a->y), a->stats, a->act, a->y_halo, a->x.c,           \
                   (float)a->x.h / (float)a->y.h, (float)a->x.w / (float)a->y.w};                   \
     auto kern = down_stream_kernel<T>;                                                             \
-    static bool set_ = false;                                                                      \
-    if (!set_) {                                                                                   \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      set_ = true;                                                                                 \
-    }                                                                                              \
+    OTM_ENSURE_SMEM(kern, 200 * 1024);                                                                                              \
     kern<<<grid, 288, smem, st>>>(f, a->y.n, a->y.h, a->y.w, a->y.c, S);                           \
   } while (0)
       if (a->x.dtype == OTM_BF16) OTM_DOWN_STREAM(__nv_bfloat16); else OTM_DOWN_STREAM(float);
@@ -2166,11 +2158,7 @@ int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_
 #define OTM_DBS(T)                                                                                 \
   do {                                                                                              \
     auto kern = down_bwd_stream_kernel<T>;                                                          \
-    static bool set_ = false;                                                                       \
-    if (!set_) {                                                                                    \
-      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      set_ = true;                                                                                  \
-    }                                                                                               \
+    OTM_ENSURE_SMEM(kern, 200 * 1024);                                                                                               \
     kern<<<grid, 288, smem, st>>>(make_view(*g), make_view(*ga), (float)ga->h / (float)g->h,        \
                                   (float)ga->w / (float)g->w, C, S);                                \
   } while (0)

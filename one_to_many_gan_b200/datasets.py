@@ -9,7 +9,11 @@ from pathlib import Path
 import torch
 
 
-def image_folder_loader(config, key: str, seed: int):
+def image_folder_loader(config, key: str, generator: torch.Generator, rank: int = 0, world: int = 1):
+    """`generator`: ONE torch.Generator shared by every loader of a run, like the reference's
+    `dataloader_g` (train.py:56-58): successive epochs of the two folders then draw different
+    permutations.  Every data-parallel rank must pass an identically seeded generator: each epoch
+    all ranks draw the same permutation and flip mask and rank r takes batches r, r+world, ..."""
     from PIL import Image  # optional dependency, only for real-image training
 
     size = tuple(config["data"]["image_size"])
@@ -25,15 +29,19 @@ def image_folder_loader(config, key: str, seed: int):
         images.append((t - 0.5) / 0.5)
     data = torch.stack(images)
     batch = config["training"]["batch_size"]
-    gen = torch.Generator().manual_seed(seed)
+    gen = generator
+    if len(data) < batch * world:
+        raise ValueError(f"{path}: {len(data)} images cannot fill {world} batches of {batch}")
 
     class _Loader:
         def __iter__(self):
             perm = torch.randperm(len(data), generator=gen)
-            for i in range(0, len(perm) - batch + 1, batch):
-                x = data[perm[i : i + batch]]
-                flip = torch.rand(batch, generator=gen) < 0.5
-                x = torch.where(flip[:, None, None, None], x.flip(-1), x)
+            flips = torch.rand(len(data), generator=gen) < 0.5
+            n_batches = len(perm) // batch // world * world  # drop_last, equal work per rank
+            for b in range(rank, n_batches, world):
+                idx = perm[b * batch : (b + 1) * batch]
+                x = data[idx]
+                x = torch.where(flips[idx][:, None, None, None], x.flip(-1), x)
                 yield x.pin_memory()
 
     return _Loader()

@@ -17,6 +17,7 @@ identical): style mixing is a `where(block < crossover, s1, s2)` instead of expa
 
 from __future__ import annotations
 
+import gc
 import random
 
 import torch
@@ -91,11 +92,16 @@ class TrainIteration:
         self.style_base = (0, 2 * B * wd, 2 * B * wd + 2 * BK * wd)
         self.theta_base = 2 * B * wd + 4 * BK * wd
         self.n_rng = self.theta_base + 2 * BK
-        self.rng_host = torch.zeros(self.n_rng, dtype=torch.float32).pin_memory()
+        # pinned staging is double-buffered: with sync_losses=False the GPU may still be reading
+        # iteration i's buffers (asynchronous H2D) while the host draws iteration i+1
+        self._rng_hosts = [torch.zeros(self.n_rng, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._staged = [None, None]  # event recorded after each buffer's H2D copies
+        self.rng_host = self._rng_hosts[0]
         self.rng_dev = torch.zeros(self.n_rng, dtype=torch.float32, device=self.dev)
         # integer controls: 3 crossovers, B pool sources, B pool destinations, B stored images
         self.n_idx = 3 + 3 * B
-        self.idx_host = torch.zeros(self.n_idx, dtype=torch.int64).pin_memory()
+        self._idx_hosts = [torch.zeros(self.n_idx, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.idx_host = self._idx_hosts[0]
         self.idx_dev = torch.zeros(self.n_idx, dtype=torch.int64, device=self.dev)
         self.pool_size = config["training"].get("image_buffer_size", 100)
         if self.pool_size < 1:
@@ -192,6 +198,9 @@ class TrainIteration:
         BK = B * self.K
         tbase = self.theta_base
         theta = self.rng_dev[tbase : tbase + BK]
+        latent_noise = None
+        if cfg["architecture"]["add_latent_noise"]:  # device draw BEFORE h (training.py:166 vs :216)
+            latent_noise = torch.randn(self.G.latent_shape((2 * B, *self.x.shape[2:])), device=self.dev)
         if self.inject_h:
             h = self.rng_dev[tbase + BK : tbase + 2 * BK]
         else:
@@ -203,7 +212,8 @@ class TrainIteration:
         w1 = torch.lerp(zero, s, d1.view(1, -1, 1))  # builder.py:66-71
         w2 = torch.lerp(zero, s, d2.view(1, -1, 1))
         losses = training.generator_losses(cfg, self.G, self.D, self.S, self.x[2], self.x[3],
-                                           reconstruct_w, translation_w, w1, w2, h)
+                                           reconstruct_w, translation_w, w1, w2, h,
+                                           latent_noise=latent_noise)
         training.backward_unit(losses[0])
         self.losses[3:].copy_(torch.cat([v.detach().reshape(1).float() for v in losses]))
 
@@ -219,6 +229,19 @@ class TrainIteration:
         for o in opts:
             o.wait_all_reduce()
 
+    # ---------------------------------------------------------------- image pool I/O
+    def pool_images(self):
+        """The pool as the reference's `ImageBuffer.images` list of [1,C,H,W] tensors."""
+        return [self.pool[i : i + 1].clone() for i in range(self.pool_index.count)]
+
+    def load_pool(self, images):
+        """Restore the pool from a checkpoint (a list like pool_images() returns)."""
+        if len(images) > self.pool_size:
+            raise ValueError(f"checkpoint holds {len(images)} pool images, pool size is {self.pool_size}")
+        for i, img in enumerate(images):
+            self.pool[i].copy_(img.reshape(self.pool.shape[1:]))
+        self.pool_index.count = len(images)
+
     # ---------------------------------------------------------------- driver
     def load_inputs(self, d_prints, d_marks, g_prints, g_marks):
         """Copy the four batches of this iteration into the static input buffers (device
@@ -233,9 +256,16 @@ class TrainIteration:
             if self.graph is not None:
                 raise RuntimeError("cannot switch h injection after the graph was captured")
             self.inject_h = h is not None
+        slot = self.iterations & 1
+        if self._staged[slot] is not None:
+            self._staged[slot].synchronize()  # the copies issued two iterations ago have run
+        self.rng_host, self.idx_host = self._rng_hosts[slot], self._idx_hosts[slot]
         self._sample_host(h)
         self.rng_dev.copy_(self.rng_host, non_blocking=True)
         self.idx_dev.copy_(self.idx_host, non_blocking=True)
+        if self._staged[slot] is None:
+            self._staged[slot] = torch.cuda.Event()
+        self._staged[slot].record()
         segs = (self._segment_a, self._segment_b, self._segment_c)
         exch = ((self.oD,), (self.oG, self.oM, self.oS), ())
         if not self.use_graph or self._warm_left > 0:
@@ -249,13 +279,22 @@ class TrainIteration:
                 torch.cuda.synchronize()
                 self.graph = []
                 pool = torch.cuda.graph_pool_handle()
-                for seg, ex in zip(segs, exch):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, pool=pool):
-                        seg()
-                    self.graph.append(g)
-                    g.replay()
-                    self._exchange(ex)
+                # no cyclic GC while a stream is capturing: collecting some OTHER dead graph or
+                # tensor would cudaFree inside the capture and invalidate it
+                gc_was_on = gc.isenabled()
+                gc.collect()
+                gc.disable()
+                try:
+                    for seg, ex in zip(segs, exch):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, pool=pool):
+                            seg()
+                        self.graph.append(g)
+                        g.replay()
+                        self._exchange(ex)
+                finally:
+                    if gc_was_on:
+                        gc.enable()
             else:
                 for g, ex in zip(self.graph, exch):
                     g.replay()
@@ -267,6 +306,4 @@ class TrainIteration:
         self.losses_host.copy_(self.losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         v = self.losses_host.tolist()
-        g = training.unweighted(self.cfg, v[3:])
-        return {"disc": v[0], "sign_real": v[1], "sign_fake": v[2], "total_gen": g[0], "gan": g[1],
-                "rec": g[2], "idt": g[3], "kl": g[4], "path": g[5], "style": g[6]}
+        return dict(zip(self.LOSS_NAMES, v))

@@ -84,6 +84,30 @@ def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None,
     return dw
 
 
+def _lib_uses_tc_fwd(x, wpack, cout, k, pad, x_halo=0) -> bool:
+    """Would otm_conv_fwd take the tcgen05 path for this (bf16) input?  (tests)"""
+    n, cin, h, w = x.shape
+    y = alloc(n, cout, h + 2 * pad - k + 1, w + 2 * pad - k + 1, x.dtype, x.device)
+    a = L.ConvFwdArgs()
+    a.x = L.tdesc(x)
+    a.x_halo = x_halo
+    a.wpack = L.ptr(wpack)
+    a.kh, a.kw, a.pad = k, k, pad
+    a.y = L.tdesc(y)
+    a.path = PATH_AUTO
+    return bool(L.lib.otm_conv_fwd_uses_tcgen05(_byref(a)))
+
+
+def _lib_uses_tc_wgrad(x, dy, k, pad, x_halo=0) -> bool:
+    a = L.ConvWgradArgs()
+    a.x = L.tdesc(x)
+    a.x_halo = x_halo
+    a.dy = L.tdesc(dy)
+    a.kh, a.kw, a.pad = k, k, pad
+    a.path = PATH_AUTO
+    return bool(L.lib.otm_conv_wgrad_uses_tcgen05(_byref(a)))
+
+
 def wgrad_fuses_P(x, dy, kh, kw, pad, x_halo=0) -> bool:
     a = L.ConvWgradArgs()
     a.x = L.tdesc(x)

@@ -434,17 +434,18 @@ class LsganFn(torch.autograd.Function):
         out, seed = K.loss_lsgan(scores, target, weight, want_grad=ctx.needs_input_grad[0])
         ctx.save_for_backward(seed)
         conf = out[1:2].clone()
-        ctx.mark_non_differentiable(conf)
-        return out[0:1] * weight, conf
+        raw = out[0:1].clone()
+        ctx.mark_non_differentiable(conf, raw)
+        return out[0:1] * weight, conf, raw
 
     @staticmethod
-    def backward(ctx, g, _):
+    def backward(ctx, g, _c, _r):
         (seed,) = ctx.saved_tensors
         return _scaled(seed, g), None, None
 
 
 def lsgan(scores, target, weight=1.0):
-    """Returns (weight * loss, confidence) as 1-element tensors."""
+    """Returns (weight * loss, confidence, loss) as 1-element tensors."""
     return LsganFn.apply(nhwc(scores), float(target), float(weight))
 
 
@@ -453,15 +454,17 @@ class L1Fn(torch.autograd.Function):
     def forward(ctx, a, b, weight):
         out, seed = K.loss_l1(a, b, weight, want_grad=ctx.needs_input_grad[0])
         ctx.save_for_backward(seed)
-        return out * weight
+        ctx.mark_non_differentiable(out)
+        return out * weight, out
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _):
         (seed,) = ctx.saved_tensors
         return _scaled(seed, g), None, None
 
 
 def l1(a, b, weight=1.0):
+    """Returns (weight * loss, loss): the raw value is what the reference logs."""
     return L1Fn.apply(nhwc(a), nhwc(b, a.dtype), float(weight))
 
 
@@ -478,15 +481,18 @@ class KlFn(torch.autograd.Function):
         c1 = 4.0 * (v - 1.0) / n * weight
         c0 = (2.0 * m / n) * weight - c1 * m
         ctx.save_for_backward(x, torch.stack([c0, c1]))
-        return (m * m + (v - 1.0) ** 2).reshape(1) * weight
+        raw = (m * m + (v - 1.0) ** 2).reshape(1)
+        ctx.mark_non_differentiable(raw)
+        return raw * weight, raw
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _):
         x, coef = ctx.saved_tensors
         return K.affine_grad(x, (coef * g.reshape(())).contiguous()), None
 
 
 def kl(x, weight=1.0):
+    """Returns (weight * loss, loss)."""
     return KlFn.apply(x, float(weight))
 
 
@@ -509,13 +515,15 @@ class PathFn(torch.autograd.Function):
                         g1=None if g is None else g[:b], g2=None if g is None else g[b:])
             seeds.append(g)
         ctx.save_for_backward(*seeds)
-        return out * weight
+        ctx.mark_non_differentiable(out)
+        return out * weight, out
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _):
         return (None, None, *[_scaled(s, g) for s in ctx.saved_tensors])
 
 
 def path(feats, h, weight=1.0):
-    """feats: list of [2B,C,H,W] tensors ([f1 ; f2] stacked); h: [B] finite-difference steps."""
+    """feats: list of [2B,C,H,W] tensors ([f1 ; f2] stacked); h: [B] finite-difference steps.
+    Returns (weight * loss, loss)."""
     return PathFn.apply(h.contiguous().float(), float(weight), *feats)

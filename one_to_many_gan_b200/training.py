@@ -136,8 +136,8 @@ def discriminator_losses(discriminator, fake, real, r1_gamma: float = 0.0):
     scores = discriminator(torch.cat([fake, real], dim=0))
     fake_scores, real_scores = scores[:batch], scores[batch:]
     # disc_loss = (mse(real, 1) + mse(fake, 0)) / 2
-    real_loss, sign_real = ops.lsgan(real_scores, 1.0, 0.5)
-    fake_loss, sign_fake = ops.lsgan(fake_scores, 0.0, 0.5)
+    real_loss, sign_real, _ = ops.lsgan(real_scores, 1.0, 0.5)
+    fake_loss, sign_fake, _ = ops.lsgan(fake_scores, 0.0, 0.5)
     loss = real_loss + fake_loss
     if r1_gamma > 0:
         from . import r1
@@ -156,9 +156,12 @@ def styles_per_input(config) -> int:
 
 
 def generator_losses(config, generator, discriminator, style_extractor, prints, marks,
-                     reconstruct_w, translation_w, w1, w2, cent_fin_diff_h, ada=None):
-    """(reference training.py:158-243) all generator-side losses with their lambdas folded in.
-    Returns (total, gan, rec, idt, kl, path, style): WEIGHTED 1-element tensors.
+                     reconstruct_w, translation_w, w1, w2, cent_fin_diff_h, ada=None,
+                     latent_noise=None):
+    """(reference training.py:158-243) all generator-side losses; each lambda is folded into the
+    kernel that writes the term's backward seed.  Returns (total, gan, rec, idt, kl, path, style)
+    as 1-element tensors: `total` is the weighted sum that is differentiated, the six terms are
+    the RAW (unweighted, detached) values the reference logs (training.py:250-257).
 
     With K = translation_w.shape[1] / B > 1 styles per input, every sampled-style pass
     (translation decode, D and S on the translations, both path-length extractions) runs on the
@@ -172,9 +175,13 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     if translation_w.shape[1] != batch * n_sty or w1.shape[1] != batch * n_sty:
         raise ValueError("style batch must be a multiple of the image batch")
     combined_latents = generator.encode(torch.cat([prints, marks], dim=0))
-    kl_loss = ops.kl(combined_latents, opt["kl_loss_lambda"])
+    kl_loss, kl_raw = ops.kl(combined_latents, opt["kl_loss_lambda"])
     if config["architecture"]["add_latent_noise"]:
-        combined_latents = combined_latents + torch.randn_like(combined_latents)
+        # (training.py:166-167) the caller pre-draws the noise so the device generator is
+        # consumed in the reference's order: latent noise BEFORE the finite-difference step h
+        if latent_noise is None:
+            latent_noise = torch.randn_like(combined_latents)
+        combined_latents = combined_latents + latent_noise.to(combined_latents.dtype)
     shoeprint_latent, shoemark_latent = combined_latents.chunk(2, dim=0)
 
     real_shoemark_w = style_extractor(marks)
@@ -186,8 +193,8 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     dec_latents = torch.cat([shoeprint_latent, shoemark_latent, shoeprint_latent_k], dim=0)
     dec_w = torch.cat([reconstruct_w, identity_w, translation_w], dim=1)
     images = generator.decode(dec_latents, dec_w)
-    reconstruction_loss = ops.l1(images[:batch], prints, opt["reconstruction_loss_lambda"])
-    identity_loss = ops.l1(images[batch : 2 * batch], marks, opt["identity_loss_lambda"])
+    reconstruction_loss, rec_raw = ops.l1(images[:batch], prints, opt["reconstruction_loss_lambda"])
+    identity_loss, idt_raw = ops.l1(images[batch : 2 * batch], marks, opt["identity_loss_lambda"])
     generated_shoemarks = images[2 * batch :]
 
     # GAN loss (the discriminator's own weight gradients are not needed here)
@@ -200,29 +207,19 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     finally:
         for p in d_params:
             p.requires_grad_(True)
-    gan_loss, _ = ops.lsgan(fake_shoemark_scores, 1.0, 1.0)
+    gan_loss, _, gan_raw = ops.lsgan(fake_shoemark_scores, 1.0, 1.0)
 
     reconstructed_w = style_extractor(generated_shoemarks)
-    style_loss = opt["style_cycle_loss_lambda"] * style_cycle_loss_func(
-        translation_w[-1], reconstructed_w
-    ).reshape(1)
+    style_raw = style_cycle_loss_func(translation_w[-1], reconstructed_w).reshape(1)
+    style_loss = opt["style_cycle_loss_lambda"] * style_raw
 
     # path length: two extractions of the same latent as one 2B batch
     feats = generator.extract(torch.cat([shoeprint_latent_k, shoeprint_latent_k], dim=0),
                               torch.cat([w1, w2], dim=1))
-    path_loss = ops.path(feats, cent_fin_diff_h, opt["path_loss_lambda"])
+    path_loss, path_raw = ops.path(feats, cent_fin_diff_h, opt["path_loss_lambda"])
 
     total = gan_loss + identity_loss + reconstruction_loss + kl_loss + path_loss + style_loss
-    return total, gan_loss, reconstruction_loss, identity_loss, kl_loss, path_loss, style_loss
-
-
-def unweighted(config, values):
-    """Undo the folded lambdas so the logged numbers are the reference's (training.py:250-257).
-    values = [total, gan, rec, idt, kl, path, style]."""
-    opt = config["optimisation"]
-    lam = [1.0, 1.0, opt["reconstruction_loss_lambda"], opt["identity_loss_lambda"],
-           opt["kl_loss_lambda"], opt["path_loss_lambda"], opt["style_cycle_loss_lambda"]]
-    return [v / l if l != 0 else 0.0 for v, l in zip(values, lam)]
+    return total, gan_raw, rec_raw, idt_raw, kl_raw, path_raw, style_raw.detach()
 
 
 def backward_unit(loss):
@@ -296,7 +293,8 @@ def generator_step(
 
     `cent_fin_diff_h` (optional, not in the reference signature) injects the finite-difference
     step the reference draws from the device generator (training.py:216-223) so seeded parity
-    tests can replay it."""
+    tests can replay it: a tensor, or a callable theta -> h invoked at the reference's position
+    in the draw order (a CPU run of the reference draws h from the HOST generator there)."""
     generator_optimiser.zero_grad()
     mapping_network_optimiser.zero_grad()
     style_extractor_optimiser.zero_grad()
@@ -315,11 +313,18 @@ def generator_step(
     translation_w = mapping_network.get_single_w(
         batch_size=style_batch, n_gen_blocks=nb, device=device, domain_variable=1
     )
-    theta = torch.rand(style_batch).to(device)
+    latent_noise = None
+    if config["architecture"]["add_latent_noise"]:  # device draw, before h (training.py:166 vs :216)
+        b2, c, lh, lw = generator.latent_shape((2 * batch, *real_shoeprint_images.shape[1:]))
+        latent_noise = torch.randn((b2, c, lh, lw), device=device)  # NCHW element order, like randn_like
+    theta_host = torch.rand(style_batch)
+    theta = theta_host.to(device)
     if cent_fin_diff_h is None:
         lo, hi = opt["path_loss_jacobian_granularity"]
         cent_fin_diff_h = torch.ones_like(theta).uniform_(lo, hi)
     else:
+        if callable(cent_fin_diff_h):
+            cent_fin_diff_h = cent_fin_diff_h(theta_host)
         cent_fin_diff_h = cent_fin_diff_h.to(device=device, dtype=torch.float32)
     d1 = (theta + cent_fin_diff_h / 2).clamp(0, 1)
     d2 = (theta - cent_fin_diff_h / 2).clamp(0, 1)
@@ -329,11 +334,11 @@ def generator_step(
 
     losses = generator_losses(config, generator, discriminator, style_extractor,
                               real_shoeprint_images, real_shoemark_images, reconstruct_w,
-                              translation_w, w1, w2, cent_fin_diff_h, ada)
+                              translation_w, w1, w2, cent_fin_diff_h, ada, latent_noise)
     backward_unit(losses[0])
     generator_optimiser.step()
     mapping_network_optimiser.step()
     style_extractor_optimiser.step()
 
-    vals = unweighted(config, _floats(*losses))
+    vals = _floats(*losses)
     return vals[0], tuple(vals[1:])

@@ -396,39 +396,45 @@ def sample_style(P, batch, n_blocks, arch: Arch, mix_styles=True):
     """builder.py:106-132 — draws on the default host generator, in order."""
     if mix_styles and torch.rand(()).lt(arch.style_mixing_prob):
         cross = int(torch.randint(0, n_blocks, ()))
-        z1 = torch.randn(batch, arch.w_dim)
+        z1 = torch.randn(batch, arch.w_dim)  # host generator, then moved (builder.py:117-118)
         z2 = torch.randn(batch, arch.w_dim)
-        s1 = mapping_forward(P, z1.to(_dtype_of(P)), arch)
-        s2 = mapping_forward(P, z2.to(_dtype_of(P)), arch)
+        s1 = mapping_forward(P, z1.to(_like(P)), arch)
+        s2 = mapping_forward(P, z2.to(_like(P)), arch)
         return torch.cat(
             (s1[None].expand(cross, -1, -1), s2[None].expand(n_blocks - cross, -1, -1)), 0
         )
     z = torch.randn(batch, arch.w_dim)
-    return mapping_forward(P, z.to(_dtype_of(P)), arch)[None].expand(n_blocks, -1, -1)
+    return mapping_forward(P, z.to(_like(P)), arch)[None].expand(n_blocks, -1, -1)
 
 
 def _dtype_of(P):
     return next(iter(P.values())).dtype
 
 
+def _like(P):
+    """A parameter of the dict: `.to(_like(P))` adopts its dtype AND device (the oracle also runs
+    on cuda:0 as bench.py's eager-PyTorch baseline; everywhere else it is a CPU program)."""
+    return next(iter(P.values()))
+
+
 def get_single_w(P, batch, n_blocks, arch: Arch, domain_variable, mix_styles=True):
     """builder.py:75-104; d == 0 draws nothing (builder.py:87-90)."""
     dt = _dtype_of(P)
     if not isinstance(domain_variable, Tensor) and domain_variable == 0:
-        return torch.zeros(1, 1, arch.w_dim, dtype=dt).expand(n_blocks, batch, arch.w_dim)
+        return torch.zeros(1, 1, arch.w_dim, dtype=dt, device=_like(P).device).expand(
+            n_blocks, batch, arch.w_dim)
     s = sample_style(P, batch, n_blocks, arch, mix_styles)
     if isinstance(domain_variable, Tensor):
-        d = domain_variable.view(1, -1, 1).to(dt)
+        d = domain_variable.view(1, -1, 1).to(s)
     else:
-        d = torch.tensor(float(domain_variable), dtype=dt).view(1, 1, 1)
+        d = torch.tensor(float(domain_variable), dtype=dt, device=s.device).view(1, 1, 1)
     return d * s  # lerp(0, s, d)
 
 
 def get_two_w(P, batch, n_blocks, arch: Arch, d1, d2, mix_styles=True):
     """builder.py:51-73 — one sampled style, two domain variables."""
     s = sample_style(P, batch, n_blocks, arch, mix_styles)
-    dt = s.dtype
-    return d1.view(1, -1, 1).to(dt) * s, d2.view(1, -1, 1).to(dt) * s
+    return d1.view(1, -1, 1).to(s) * s, d2.view(1, -1, 1).to(s) * s
 
 
 # ---------------------------------------------------------------------------
@@ -453,7 +459,7 @@ def kl_loss(latents):
 
 def path_loss(f1, f2, h):
     # loss.py:98-111
-    total = torch.zeros((), dtype=f1[0].dtype)
+    total = torch.zeros((), dtype=f1[0].dtype, device=f1[0].device)
     for a, b in zip(f1, f2, strict=True):
         jac = (a - b) / h[:, None, None, None]
         total = total + (jac**2).mean()
@@ -585,13 +591,15 @@ class Trainer:
     hyper: Hyper
     params: dict[str, dict[str, Tensor]]
     dtype: torch.dtype = torch.float32
+    device: str = "cpu"  # "cuda:0" only for bench.py's eager-PyTorch-on-GPU baseline
     opt: dict[str, Adam] = field(default_factory=dict)
     last_grads: dict[str, dict[str, Tensor]] = field(default_factory=dict)
     last_h: Tensor | None = None
 
     def __post_init__(self):
         self.params = {
-            n: {k: v.to(self.dtype).clone() for k, v in p.items()} for n, p in self.params.items()
+            n: {k: v.to(device=self.device, dtype=self.dtype).clone() for k, v in p.items()}
+            for n, p in self.params.items()
         }
         h = self.hyper
         for n in ("D", "G", "S"):
@@ -607,9 +615,9 @@ class Trainer:
         G, M = self.params["G"], self.params["M"]
         with torch.no_grad():  # the reference builds and discards this graph (:98)
             w = get_single_w(M, h.batch_size, a.n_style_blocks, a, 1)
-            fake = generator_forward(G, shoeprints.to(self.dtype), w, a)
+            fake = generator_forward(G, shoeprints.to(_like(G)), w, a)
         fake = self.buffer(fake)
-        real = shoemarks.to(self.dtype)
+        real = shoemarks.to(_like(G))
         fake_scores = discriminator_forward(D, fake)
         real_scores = discriminator_forward(D, real)
         real_loss = F.mse_loss(real_scores, torch.ones_like(real_scores))
@@ -641,8 +649,8 @@ class Trainer:
         BK = B * K
         G, M, S = _leaf(self.params["G"]), _leaf(self.params["M"]), _leaf(self.params["S"])
         D = self.params["D"]
-        prints = shoeprints.to(self.dtype)
-        marks = shoemarks.to(self.dtype)
+        prints = shoeprints.to(_like(G))
+        marks = shoemarks.to(_like(G))
         latents = generator_encode(G, torch.cat([prints, marks], 0), a)
         kl = kl_loss(latents)
         if hy.add_latent_noise:
@@ -665,11 +673,13 @@ class Trainer:
         # style cycle (:207-210)
         style_loss = style_cycle_loss(tw[-1], style_extractor_forward(S, transl))
         # path length (:214-234)
-        theta = torch.rand(BK).to(self.dtype)
+        theta = torch.rand(BK).to(prints)  # host draw, then moved (training.py:214)
         if h_override is None:
-            hh = torch.ones_like(theta).uniform_(*hy.path_h_range)
+            # drawn in fp32 on the host generator whatever self.dtype is, so an fp64 replay
+            # consumes the generator exactly like the reference's fp32 CPU run (training.py:216-223)
+            hh = torch.ones(BK).uniform_(*hy.path_h_range).to(prints)
         else:
-            hh = h_override.to(self.dtype)
+            hh = h_override.to(prints)
         self.last_h = hh
         d1 = (theta + hh / 2).clamp(0, 1)
         d2 = (theta - hh / 2).clamp(0, 1)
@@ -685,13 +695,14 @@ class Trainer:
             + hy.path_loss_lambda * p_loss
             + hy.style_cycle_loss_lambda * style_loss
         )
-        for name, P in (("G", G), ("M", M), ("S", S)):
-            names = [k for k in P if not is_buffer(k)]
-            grads = torch.autograd.grad(
-                total, [P[k] for k in names], retain_graph=True, allow_unused=True
-            )
-            g = {k: (gr if gr is not None else torch.zeros_like(P[k])) for k, gr in zip(names, grads)}
-            self.last_grads[name] = g
+        # ONE backward pass for the three networks, like the reference's total.backward() (:245)
+        keys = [(name, k) for name, P in (("G", G), ("M", M), ("S", S)) for k in P if not is_buffer(k)]
+        nets = {"G": G, "M": M, "S": S}
+        grads = torch.autograd.grad(total, [nets[n][k] for n, k in keys], allow_unused=True)
+        for name in nets:
+            self.last_grads[name] = {}
+        for (name, k), gr in zip(keys, grads):
+            self.last_grads[name][k] = gr if gr is not None else torch.zeros_like(nets[name][k])
         for name in ("G", "M", "S"):
             self.opt[name].step(self.params[name], self.last_grads[name])
         return float(total), (

@@ -33,3 +33,18 @@ def fp_err(got: torch.Tensor, want: torch.Tensor) -> float:
     smp_scale = want[3:].abs().max().clamp_min(1e-30)
     e_smp = ((got[3:] - want[3:]).abs().max() / smp_scale).item()
     return max(e_norm, e_abs, e_smp)
+
+
+LOSS_COLS = [0, 3, 4, 5, 6, 7, 8, 9]  # disc, total_gen, gan, rec, idt, kl, path, style (not the signs)
+
+
+def chaos_envelope(g, margin: float = 5.0) -> torch.Tensor:
+    """Per-iteration relative tolerance for a long seeded run (golden case d): `margin` x the
+    running maximum of the reference's fp32 losses against the fp64 replay of the same run
+    (recorded by make_golden.py), floored at 2e-4 and capped at 0.5.  Training is chaotic: from
+    iteration ~3 on two fp32 executions only agree statistically, and this is the measured size
+    of that effect, not a guess."""
+    ref, p64 = g["losses"].double(), g["losses_port_fp64"].double()
+    rel = ((ref - p64).abs() / p64.abs().clamp_min(1e-6))[:, LOSS_COLS].max(dim=1).values
+    env = torch.cummax(rel, 0).values
+    return torch.clamp(margin * env, min=2e-4, max=0.5)

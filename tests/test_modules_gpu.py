@@ -168,14 +168,23 @@ def test_training_step_matches_oracle_fp32(case):
                 # the oracle's own fp32-vs-fp64 noise: per tensor, and the network's median
                 # (one tensor's sample of the sign/ReLU-flip noise can be accidentally tiny)
                 net_floor = sorted(floors.values())[len(floors) // 2]
+                flips = []
                 for k in live:
                     gm = mine[net][k] if net == "D" else mine[net][k].grad
                     e = relerr(gm, ref64[0][1][net][k])
                     worst = max(worst, e)
-                    # 5e-3: one ReLU/LeakyReLU/sign() mask flip (fp32 summation order of the
-                    # atomics differs run to run) moves a gradient of these tiny networks by up
-                    # to ~2e-3; the layer-local 1e-4 gate lives in test_kernels_gpu.py
-                    assert e <= max(3 * floors[k], 3 * net_floor, 5e-3), (net, k, e, floors[k], net_floor)
+                    # Gate: 3x the oracle's own fp32-vs-fp64 noise, floored at 1e-3.  ONE
+                    # ReLU/LeakyReLU/sign() mask flip (the fp32 summation order of the atomics
+                    # differs run to run) moves a gradient of these tiny networks by up to ~2e-3,
+                    # so at most two tensors per network may sit between that gate and 5e-3; they
+                    # are counted and printed.  (The layer-local 1e-4 gate is test_kernels_gpu.py.)
+                    lim = max(3 * floors[k], 3 * net_floor, 1e-3)
+                    if e > lim:
+                        assert e <= 5e-3, (net, k, e, floors[k], net_floor)
+                        flips.append((k, f"{e:.1e}"))
+                assert len(flips) <= 2, (net, flips)
+                if flips:
+                    print(f"[{case}] {net}: tensors past the 1e-3 gate (mask flips): {flips}")
             _check_weights_after_one_step(
                 case, {n: {k: p.detach().cpu() for k, p in m.named_parameters()}
                        for n, m in (("D", D), ("G", G), ("M", M), ("S", S))}, ref64, ref32)

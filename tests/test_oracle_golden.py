@@ -96,3 +96,25 @@ def _dead_bias_names():
     dead |= {("D", f"model.{i}.bias") for i in (3, 7, 11)}
     dead |= {("G", f"encoder.{i}.bias") for i in (1, 4, 8, 12)}
     return dead
+
+
+def test_config1_twenty_iterations_match_reference():
+    """BASELINE configs[0] literally (64x64, batch 4, 20 iterations): the port's fp32 losses
+    against the reference's, iteration by iteration, inside the measured chaos envelope."""
+    from tests.golden_util import LOSS_COLS, chaos_envelope
+
+    g = load("d_64x64_config1_20it")
+    meta = g["meta"]
+    arch = _arch(meta)
+    tr = rp.Trainer(arch, rp.Hyper(batch_size=meta["batch"]), rp.init_all(arch, meta["seed"]))
+    shape = (meta["batch"], 1, *meta["image_size"])
+    prints, marks = _batches(shape, meta["print_seed"]), _batches(shape, meta["mark_seed"])
+    tol = chaos_envelope(g)
+    assert tol[0] == 2e-4 and tol[1] < 1e-3  # the first iterations are gated tightly
+    for it in range(meta["iters"]):
+        d = tr.discriminator_step(next(prints), next(marks))
+        gl = tr.generator_step(next(prints), next(marks))
+        got = torch.tensor([d[0], d[1][0], d[1][1], gl[0], *gl[1]], dtype=torch.float64)
+        want = g["losses"][it]
+        rel = ((got - want).abs() / want.abs().clamp_min(1e-6))[LOSS_COLS].max().item()
+        assert rel <= tol[it].item(), (it, rel, tol[it].item())
