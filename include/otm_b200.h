@@ -60,7 +60,12 @@ int64_t otm_launch_count(void);
  * the cuDNN dgrad/wgrad that autograd runs for both.
  *
  *   y[n,h,w,o] = epi( alpha * sum_{r,s,i} x[n, h+r-pad, w+s-pad, i] * wpack[nb][o][r][s][i] )
- *   epi(v) = act( v * row_scale[n,o] + bias[o] ) + residual[n,h,w,o]
+ *   epi(v) = act( v * row_scale[n,o] + bias[o] ) * post_scale[n,o] + residual[n,h,w,o]
+ *
+ * post_scale is how a modulated conv gets SHARED weights (y = sigma_inv *
+ * conv(s * x, cW)): the producer of x multiplies its output by the consumer's style scale
+ * s[n,i] after its activation, so the consumer reads x~ = s * x and its weights need no
+ * per-sample copy.
  *
  * x positions outside [-x_halo, H+x_halo) x [-x_halo, W+x_halo) read as zero; positions
  * inside the halo read the materialised halo (e.g. a reflect halo written by a producer).
@@ -83,6 +88,7 @@ typedef struct {
   int32_t act;            /* otm_act */
   otm_tensor residual;    /* ptr NULL = none */
   int32_t path;           /* otm_path */
+  const float* post_scale; /* [n, Cout] or NULL */
 } otm_conv_fwd_args;
 int otm_conv_fwd(const otm_conv_fwd_args* a, otm_stream stream);
 /* 1 if the tcgen05 path would be used for these arguments, 0 if SIMT */
@@ -108,11 +114,14 @@ typedef struct {
   /* Optional fused demodulation-gradient term of the modulated conv:
    *   P[n,o] += rs[n,o] * sum_{r,s,i} G_n[o,i,r,s] * wfwd[n][o][r][s][i]
    * where G_n is the un-scaled per-sample weight gradient this kernel already holds in TMEM and
-   * wfwd the per-sample forward pack (alpha*w*cs).  This equals sum_hw dy*y, so the separate
-   * pass over dy and y (otm_mod_out) is not needed.  tcgen05 path with Cout % 128 == 0 only
+   * wfwd the forward pack: per-sample (alpha*w*cs, wfwd_batch_stride = Cout*kh*kw*Cin) when x is
+   * the un-modulated input, or the ONE shared pack (alpha*w, stride 0) when x already carries the
+   * modulation (x~ = s*x).  This equals sum_hw dy*y, so the separate pass over dy and y
+   * (otm_mod_out) is not needed.  tcgen05 path with Cout % 128 == 0 only
    * (otm_conv_wgrad_fuses_P tells); P must be zeroed by the caller. */
   const void* wfwd;
   float* P;
+  int64_t wfwd_batch_stride;
 } otm_conv_wgrad_args;
 int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream);
 int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a);
@@ -158,6 +167,9 @@ typedef struct {
   int32_t nb;
   float* ds; /* [nb, Cin] written */
   float* dw; /* [Cout,Cin,taps] accumulated */
+  int32_t q_scaled; /* 1: Q was reduced against the MODULATED input x~ = s*x (the un-modulated x is
+                       not stored): Q[b,i] is divided by s[b,i] here.  A style scale that is exactly
+                       0 loses that term (x~ == 0 carries no information about x): measure zero. */
 } otm_mod_bwd_args;
 int otm_mod_bwd(const otm_mod_bwd_args* a, otm_stream stream);
 
@@ -220,8 +232,12 @@ typedef struct {
 int otm_down(const otm_down_args* a, otm_stream stream);
 /* ga[n,H,W,c] = transpose(stencil)(g);  g_halo folds a reflect-padded g first. */
 int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_stream stream);
-int otm_up(const otm_tensor* x, const otm_tensor* y, int32_t y_halo, otm_stream stream);
-int otm_up_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* gx, otm_stream stream);
+/* scale: optional [n, c] per-sample channel factor on the result (the style scale of the
+ * modulated conv that consumes the up-sampled tensor; the stencil is per channel, so it commutes) */
+int otm_up(const otm_tensor* x, const otm_tensor* y, int32_t y_halo, const float* scale,
+           otm_stream stream);
+int otm_up_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* gx, const float* scale,
+               otm_stream stream);
 
 /* ---------------------------------------------------------------------------------
  * Modulated-conv side passes (HBM-bound).  SURVEY App. B.2.
@@ -237,9 +253,13 @@ typedef struct {
   int32_t act;
   otm_tensor gy; /* ptr NULL = do not materialise (act NONE, no fold, no g2) */
   float* P;      /* [n, c] zeroed here then accumulated */
+  const float* gy_scale; /* [n, c] or NULL: the STORED gy is multiplied by it (sigma_inv: gy is then
+                            the gradient w.r.t. the conv's raw output u, ready for a shared-weight
+                            dgrad / wgrad); P is reduced from the un-scaled value */
 } otm_mod_out_args;
 int otm_mod_out(const otm_mod_out_args* a, otm_stream stream);
-/* in side:  gxt = fold(g_padded) ; Q[n,i] = sum_hw gxt * x ; gx = s[n,i] * gxt [+ gadd] */
+/* in side:  gxt = fold(g_padded) ; Q[n,i] = sum_hw gxt * x ; gx = s[n,i] * gxt [+ gadd]
+ * (gx.ptr NULL: reduction only) */
 typedef struct {
   otm_tensor g;
   int32_t g_halo;
@@ -248,13 +268,16 @@ typedef struct {
   otm_tensor gadd; /* ptr NULL = none */
   otm_tensor gx;
   float* Q; /* [n, c] zeroed here then accumulated */
-  int32_t relu_mask; /* 1: gx *= (x > 0) -- x is a ReLU output, so this is the ReLU backward of
-                        the producer fused into this pass */
+  int32_t relu_mask; /* 1: gx *= (x != 0) -- x is a (possibly style-scaled) ReLU output, so this is
+                        the ReLU backward of the producer fused into this pass */
+  const float* gx_scale; /* [n, c] or NULL: gx *= gx_scale after the mask (the producer conv's
+                            sigma_inv: gx is then the gradient w.r.t. ITS raw output u) */
 } otm_mod_in_args;
 int otm_mod_in(const otm_mod_in_args* a, otm_stream stream);
 
-/* per-channel sum over n,h,w of fold(g): bias gradients (dy -> db[c]); out zeroed here */
-int otm_channel_sum(const otm_tensor* g, float* out, otm_stream stream);
+/* per-channel sum over n,h,w of g: bias gradients (dy -> db[c]).  accumulate == 0: out is zeroed
+ * here first; != 0: out += (straight into the gradient arena) */
+int otm_channel_sum(const otm_tensor* g, float* out, int32_t accumulate, otm_stream stream);
 /* global average pool fwd/bwd (StyleExtractor head, builder.py:314) */
 int otm_avgpool(const otm_tensor* x, float* out /*[n,c] fp32*/, otm_stream stream);
 int otm_avgpool_bwd(const float* g /*[n,c]*/, const otm_tensor* gx, otm_stream stream);
@@ -280,6 +303,63 @@ int otm_affine_grad(const otm_tensor* x, const float* coef, const otm_tensor* gr
 int otm_loss_path(const otm_tensor* f1, const otm_tensor* f2, const float* h, float weight,
                   float scale, float* out, const otm_tensor* g1, const otm_tensor* g2,
                   otm_stream stream);
+
+/* out[0] = style_cycle_loss_func(a, b) (reference loss.py:60-75: both L2-normalised with eps
+ * 1e-12, 1 - mean cosine similarity (eps 1e-8) + ratio * mse) on [batch, features] fp32 rows
+ * (row strides in elements); da / db (dense [batch, features], may be NULL) = scale * d loss. */
+int otm_loss_style_cycle(const float* a, int64_t a_stride, const float* b, int64_t b_stride,
+                         int32_t batch, int32_t features, float ratio, float scale, float* out,
+                         float* da, float* db, otm_stream stream);
+
+/* ---------------------------------------------------------------------------------
+ * Small dense layers (fp32, SIMT: K is 6 or 512, below a tensor-core tile).
+ * --------------------------------------------------------------------------------- */
+#define OTM_MAX_LINEAR_JOBS 16
+#define OTM_MAX_STYLE_DIM 32
+#define OTM_MAX_MAPPING_LAYERS 8
+/* EqualisedLinear (reference layers.py:27-43): y = x @ (c W)^T + bias, c = 1/sqrt(k), W the raw
+ * parameter.  Up to OTM_MAX_LINEAR_JOBS independent layers per call -- e.g. every `to_style` of
+ * one decoder pass (layers.py:138-140,148) or the StyleExtractor head (builder.py:316) -- run as
+ * ONE launch.  Backward: dw / dbias are accumulated (+=, each written by one thread), dx is
+ * accumulated atomically (jobs may share it); jobs with dy == NULL are skipped. */
+typedef struct {
+  const float* x;       /* [n, k] */
+  int64_t x_row_stride; /* elements; 0 = one row broadcast over n */
+  const float* w;       /* [o, k] */
+  const float* bias;    /* [o] or NULL */
+  float* y;             /* forward: [n, o] dense */
+  const float* dy;      /* backward: [n, o] dense, or NULL */
+  float* dw;            /* backward: [o, k] += , or NULL */
+  float* dbias;         /* backward: [o] +=, or NULL */
+  float* dx;            /* backward: rows of k, atomically +=, or NULL */
+  int64_t dx_row_stride;
+  int32_t n, k, o;
+} otm_linear_job;
+int otm_linear_fwd(const otm_linear_job* jobs, int32_t n_jobs, otm_stream stream);
+int otm_linear_bwd(const otm_linear_job* jobs, int32_t n_jobs, otm_stream stream);
+
+/* MappingNetwork.forward (reference builder.py:46-49: F.normalize, [Linear, LeakyReLU 0.2] x
+ * (L-1), Linear, ReLU) fused with the style mixing of _get_style_vector (builder.py:115-132) and
+ * the domain-variable interpolation of get_single_w / get_two_w (builder.py:66-71,104):
+ *   out[j][blk, b, :] = d_j[b] * (blk < *cross ? net(z1[b]) : net(z2[b])),   j = 0, 1
+ * The host draws z1, z2 and the crossover (the reference's host-RNG order) and copies them to the
+ * device; everything else is this one launch.  Backward accumulates dw / db from dout[j]. */
+typedef struct {
+  const float* z1;   /* [batch, features] */
+  const float* z2;   /* NULL = no mixing */
+  const void* cross; /* device int64 scalar, NULL = all blocks take z1 */
+  const float* w[OTM_MAX_MAPPING_LAYERS]; /* [features, features] raw parameters */
+  const float* b[OTM_MAX_MAPPING_LAYERS];
+  float* dw[OTM_MAX_MAPPING_LAYERS];      /* backward: accumulated */
+  float* db[OTM_MAX_MAPPING_LAYERS];
+  int32_t features, n_layers, batch, n_blocks;
+  const float* d[2];  /* [batch] per-sample domain variable, NULL = d_const[j] */
+  float d_const[2];
+  float* out[2];        /* [n_blocks, batch, features]; out[1] NULL = one output */
+  const float* dout[2]; /* backward */
+} otm_mapping_args;
+int otm_mapping_fwd(const otm_mapping_args* a, otm_stream stream);
+int otm_mapping_bwd(const otm_mapping_args* a, otm_stream stream);
 
 /* ---------------------------------------------------------------------------------
  * Optimiser and data.

@@ -51,6 +51,7 @@ class ConvFwdArgs(C.Structure):
         ("act", C.c_int32),
         ("residual", Tensor),
         ("path", C.c_int32),
+        ("post_scale", C.c_void_p),
     ]
 
 
@@ -70,6 +71,7 @@ class ConvWgradArgs(C.Structure):
         ("ws", C.c_void_p),
         ("wfwd", C.c_void_p),
         ("P", C.c_void_p),
+        ("wfwd_batch_stride", C.c_int64),
     ]
 
 
@@ -105,6 +107,7 @@ class ModBwdArgs(C.Structure):
         ("nb", C.c_int32),
         ("ds", C.c_void_p),
         ("dw", C.c_void_p),
+        ("q_scaled", C.c_int32),
     ]
 
 
@@ -154,6 +157,7 @@ class ModOutArgs(C.Structure):
         ("act", C.c_int32),
         ("gy", Tensor),
         ("P", C.c_void_p),
+        ("gy_scale", C.c_void_p),
     ]
 
 
@@ -167,6 +171,7 @@ class ModInArgs(C.Structure):
         ("gx", Tensor),
         ("Q", C.c_void_p),
         ("relu_mask", C.c_int32),
+        ("gx_scale", C.c_void_p),
     ]
 
 
@@ -183,6 +188,47 @@ class AdamArgs(C.Structure):
         ("eps", C.c_float),
         ("grad_scale", C.c_float),
         ("step", C.c_void_p),
+    ]
+
+
+MAX_LINEAR_JOBS, MAX_STYLE_DIM, MAX_MAPPING_LAYERS = 16, 32, 8
+
+
+class LinearJob(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("x_row_stride", C.c_int64),
+        ("w", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("y", C.c_void_p),
+        ("dy", C.c_void_p),
+        ("dw", C.c_void_p),
+        ("dbias", C.c_void_p),
+        ("dx", C.c_void_p),
+        ("dx_row_stride", C.c_int64),
+        ("n", C.c_int32),
+        ("k", C.c_int32),
+        ("o", C.c_int32),
+    ]
+
+
+class MappingArgs(C.Structure):
+    _fields_ = [
+        ("z1", C.c_void_p),
+        ("z2", C.c_void_p),
+        ("cross", C.c_void_p),
+        ("w", C.c_void_p * MAX_MAPPING_LAYERS),
+        ("b", C.c_void_p * MAX_MAPPING_LAYERS),
+        ("dw", C.c_void_p * MAX_MAPPING_LAYERS),
+        ("db", C.c_void_p * MAX_MAPPING_LAYERS),
+        ("features", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("batch", C.c_int32),
+        ("n_blocks", C.c_int32),
+        ("d", C.c_void_p * 2),
+        ("d_const", C.c_float * 2),
+        ("out", C.c_void_p * 2),
+        ("dout", C.c_void_p * 2),
     ]
 
 
@@ -212,11 +258,20 @@ SYMBOLS = {
     "otm_norm_act_bwd": (C.c_int, [_P(NormActBwdArgs), C.c_void_p]),
     "otm_down": (C.c_int, [_P(DownArgs), C.c_void_p]),
     "otm_down_bwd": (C.c_int, [_P(Tensor), C.c_int32, _P(Tensor), C.c_void_p]),
-    "otm_up": (C.c_int, [_P(Tensor), _P(Tensor), C.c_int32, C.c_void_p]),
-    "otm_up_bwd": (C.c_int, [_P(Tensor), C.c_int32, _P(Tensor), C.c_void_p]),
+    "otm_up": (C.c_int, [_P(Tensor), _P(Tensor), C.c_int32, C.c_void_p, C.c_void_p]),
+    "otm_up_bwd": (C.c_int, [_P(Tensor), C.c_int32, _P(Tensor), C.c_void_p, C.c_void_p]),
     "otm_mod_out": (C.c_int, [_P(ModOutArgs), C.c_void_p]),
     "otm_mod_in": (C.c_int, [_P(ModInArgs), C.c_void_p]),
-    "otm_channel_sum": (C.c_int, [_P(Tensor), C.c_void_p, C.c_void_p]),
+    "otm_channel_sum": (C.c_int, [_P(Tensor), C.c_void_p, C.c_int32, C.c_void_p]),
+    "otm_loss_style_cycle": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float,
+         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "otm_linear_fwd": (C.c_int, [_P(LinearJob), C.c_int32, C.c_void_p]),
+    "otm_linear_bwd": (C.c_int, [_P(LinearJob), C.c_int32, C.c_void_p]),
+    "otm_mapping_fwd": (C.c_int, [_P(MappingArgs), C.c_void_p]),
+    "otm_mapping_bwd": (C.c_int, [_P(MappingArgs), C.c_void_p]),
     "otm_avgpool": (C.c_int, [_P(Tensor), C.c_void_p, C.c_void_p]),
     "otm_avgpool_bwd": (C.c_int, [C.c_void_p, _P(Tensor), C.c_void_p]),
     "otm_loss_lsgan": (

@@ -60,6 +60,6 @@ class ModulatedResnetBlock(nn.Module):
     def forward(self, x: torch.Tensor, w: torch.Tensor):
         x = _ensure_halo(x, 1)
         c1, c2 = self.conv_block[1], self.conv_block[4]
-        y = ops.mod_res_block(x, c1.to_style(w), c2.to_style(w), c1.weight.weight, c2.weight.weight,
-                              y_halo=self.out_halo)
+        s1, s2 = ops.linears([w, w], [c1.to_style, c2.to_style])
+        y = ops.mod_res_block(x, s1, s2, c1.weight.weight, c2.weight.weight, y_halo=self.out_halo)
         return ops.with_halo(y, self.out_halo)

@@ -10,7 +10,6 @@ import math
 from typing import cast
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import ops
@@ -24,6 +23,8 @@ class MappingNetwork(nn.Module):
 
     def __init__(self, features: int, n_layers: int, style_mixing_prob: float):
         super().__init__()
+        if features > 32 or n_layers > 8:
+            raise ValueError("the B200 mapping kernel implements w_dim <= 32 and <= 8 layers")
         self.d_latent = features
         self.style_mixing_prob = style_mixing_prob
         layers: list[nn.Module] = []
@@ -35,8 +36,12 @@ class MappingNetwork(nn.Module):
         self.register_buffer("shoeprint_style_vector",
                              torch.zeros((1, 1, features), dtype=torch.float), persistent=False)
 
+    def linears(self):
+        return [m for m in self.net if isinstance(m, EqualisedLinear)]
+
     def forward(self, z: torch.Tensor):
-        return self.net(F.normalize(z, dim=1))
+        """One fused kernel: F.normalize -> [Linear, LeakyReLU] ... Linear, ReLU (builder.py:46-49)."""
+        return ops.mapping(self.linears(), z)[0][0]
 
     def get_two_w(self, batch_size, n_gen_blocks, device, domain_variables, *, mix_styles=True):
         d1, d2 = domain_variables
@@ -153,8 +158,23 @@ class Generator(nn.Module):
         return ops.with_halo(a, halo_after(n_tail))
 
     # -- decoder ---------------------------------------------------------------------
+    def _styles(self, w: torch.Tensor):
+        """s = to_style(w[i]) of EVERY modulated conv of the decoder in one launch
+        (reference layers.py:138-140,148; blocks.py:62-68: both convs of a block read w[i])."""
+        dec = self.decoder
+        layers, xs = [], []
+        for r in range(self.n_dec_res):
+            for c in (1, 4):
+                layers.append(dec[r].conv_block[c].to_style)
+                xs.append(w[r])
+        for d in range(self.n_down):
+            layers.append(dec[self.n_dec_res + 3 * d + 1].to_style)
+            xs.append(w[self.n_dec_res + d])
+        return ops.linears(xs, layers)
+
     def _decode(self, z: torch.Tensor, w: torch.Tensor, collect: bool):
         dec = self.decoder
+        styles = self._styles(w) if self.n_style_blocks else ()
         z = ops.nhwc(z, self.act_dtype) if (z.dtype != self.act_dtype or ops.halo_of(z) == 0) else z
         feats = []
         n_styled = self.n_style_blocks
@@ -166,7 +186,7 @@ class Generator(nn.Module):
             last_res = r == self.n_dec_res - 1
             nxt = 1 if not last_res else (0 if self.n_down > 0 else 3)
             c1, c2 = blk.conv_block[1], blk.conv_block[4]
-            z = ops.mod_res_block(z, c1.to_style(w[i]), c2.to_style(w[i]), c1.weight.weight,
+            z = ops.mod_res_block(z, styles[2 * r], styles[2 * r + 1], c1.weight.weight,
                                   c2.weight.weight, y_halo=nxt)
             ops.with_halo(z, nxt)
             feats.append(z)
@@ -175,15 +195,14 @@ class Generator(nn.Module):
         for d in range(self.n_down):
             conv = dec[j + 1]
             last = d == self.n_down - 1
-            u = ops.up(z)
             i += 1
             if collect and i == n_styled:
                 # the final styled layer is returned before its ReLU (reference builder.py:243-244)
-                feats.append(ops.mod_conv(u, conv.to_style(w[i - 1]), conv.weight.weight,
-                                          act=ops.ACT_NONE))
+                feats.append(ops.up_mod_conv(z, styles[2 * self.n_dec_res + d], conv.weight.weight,
+                                             act=ops.ACT_NONE))
                 return feats
-            z = ops.mod_conv(u, conv.to_style(w[i - 1]), conv.weight.weight, act=ops.ACT_RELU,
-                             y_halo=3 if last else 0)
+            z = ops.up_mod_conv(z, styles[2 * self.n_dec_res + d], conv.weight.weight,
+                                act=ops.ACT_RELU, y_halo=3 if last else 0)
             ops.with_halo(z, 3 if last else 0)
             # nn.ReLU(inplace=True) overwrites the tensor `extract` appended (builder.py:190-197,
             # 241): non-final up-sampling features reach the path loss post-ReLU.

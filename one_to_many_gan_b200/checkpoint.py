@@ -53,6 +53,7 @@ def save_checkpoint(path, *, nets: dict, optimisers: dict, ada_p, pool_images, p
         "ada_scores": [float(s) for s in getattr(ada_p, "mean_real_scores", [])],
         "torch_rng": torch.get_rng_state(),
         "python_rng": random.getstate(),
+        "cuda_rng": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
     }
     torch.save(blob, path)
     return path
@@ -82,6 +83,8 @@ def load_checkpoint(path, *, nets: dict, optimisers: dict, ada_p=None, device=No
     if restore_rng and "torch_rng" in extra:
         torch.set_rng_state(extra["torch_rng"].cpu())
         random.setstate(extra["python_rng"])
+        if extra.get("cuda_rng") is not None and torch.cuda.is_available():
+            torch.cuda.set_rng_state(extra["cuda_rng"].cpu())
     return {"step": int(step), "pool_images": blob["image_buffer_images"],
             "pool_size": int(blob["image_buffer_size"]), "ada_p": float(blob["ada_p"])}
 

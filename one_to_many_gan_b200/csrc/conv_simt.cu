@@ -19,6 +19,7 @@ struct ConvP {
   const float* bias;
   int act;
   int tiles_w;
+  const float* post_scale;  // generic tile kernel only (conv_fwd_simt routes there)
 };
 
 struct WgradP {
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p) {
       if (p.row_scale) v *= p.row_scale[(long long)n * p.cout + o];
       if (p.bias) v += p.bias[o];
       v = act_fwd(v, p.act);
+      if (p.post_scale) v *= p.post_scale[(long long)n * p.cout + o];
       if (p.res.ptr) v += to_f(*vptr<TO>(p.res, n, oh, ow, o));
       float vv[1] = {v};
       store_halo<TO, 1>(p.y, p.y_halo, n, oh, ow, o, vv);
@@ -1268,7 +1270,9 @@ __global__ void __launch_bounds__(128) mod_bwd_ds_kernel(otm_mod_bwd_args a) {
   __syncthreads();
   if (wq == 0 && i < a.cin) {
     const int idx = b * a.cin + i;
-    a.ds[idx] = a.Q[idx] + 2.f * a.s[idx] * (part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane]);
+    float qv = a.Q[idx];
+    if (a.q_scaled) qv = a.s[idx] != 0.f ? qv / a.s[idx] : 0.f;  // Q was reduced against s * x
+    a.ds[idx] = qv + 2.f * a.s[idx] * (part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane]);
   }
 }
 // dw[o,i,k] += 2 alpha^2 w[o,i,k] sum_b dd[b,o] s[b,i]^2
@@ -1313,9 +1317,19 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
   p.x_halo = a->x_halo; p.y_halo = a->y_halo; p.kh = a->kh; p.kw = a->kw; p.pad = a->pad;
   p.cin = a->x.c; p.cout = a->y.c; p.ktot = a->kh * a->kw * a->x.c;
   p.alpha = a->alpha; p.row_scale = a->row_scale; p.bias = a->bias; p.act = a->act;
+  p.post_scale = a->post_scale;
   p.tiles_w = (a->y.w + 7) / 8;
   const int tiles_h = (a->y.h + 7) / 8;
   const bool in_bf = a->x.dtype == OTM_BF16, out_bf = a->y.dtype == OTM_BF16;
+  if (a->post_scale) {  // only the generic tile kernel applies the post-activation scale
+    dim3 grid_ps(p.tiles_w * tiles_h, (p.cout + TN - 1) / TN, a->y.n);
+    if (in_bf && out_bf) conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_ps, 256, 0, st>>>(p);
+    else if (in_bf) conv_simt_kernel<__nv_bfloat16, float><<<grid_ps, 256, 0, st>>>(p);
+    else if (out_bf) conv_simt_kernel<float, __nv_bfloat16><<<grid_ps, 256, 0, st>>>(p);
+    else conv_simt_kernel<float, float><<<grid_ps, 256, 0, st>>>(p);
+    OTM_LAUNCH_CHECK();
+    return OTM_OK;
+  }
   if (p.cin == 1 && p.cout == 64 && a->kh == a->kw && (a->kh == 4 || a->kh == 7) && !in_bf &&
       a->w_batch_stride == 0 && vec_ok(a->y, 8) && vec_ok(a->residual, 8)) {
     constexpr int TT = 16;
@@ -1323,8 +1337,7 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
     const int per_img = tiles_w * tiles_h, total = per_img * a->y.n;
     int ctas = num_sms() * 2;
     if (ctas > total) ctas = total;
-    static const int thin_mma = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
-    const bool mma = thin_mma && out_bf && !a->row_scale && !a->residual.ptr;
+    const bool mma = out_bf && !a->row_scale && !a->residual.ptr;
     if (a->kh == 7) {
       if (mma) conv_cin1_mma_kernel<7><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
       else if (out_bf) conv_cin1_kernel<__nv_bfloat16, 7><<<ctas, 256, 0, st>>>(p, tiles_w, per_img, total);
@@ -1337,10 +1350,9 @@ int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st) {
     OTM_LAUNCH_CHECK();
     return OTM_OK;
   }
-  static const int thin_mma1 = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
-  if (thin_mma1 && p.cout == 1 && p.cin == 64 && in_bf && a->kh == a->kw && (a->kh == 4 || a->kh == 7) &&
+  if (p.cout == 1 && p.cin == 64 && in_bf && a->kh == a->kw && (a->kh == 4 || a->kh == 7) &&
       a->w_batch_stride == 0 && vec_ok(a->x, 8) && a->y.h * a->y.w >= 256) {
-    static const int mw = [] { const char* e = getenv("OTM_COUT1_MW"); return e ? atoi(e) : 1; }();
+    constexpr int mw = 1;  // one M-warp per CTA measured best (3 CTAs / SM)
 #define OTM_C1M(TO, KS, MW)                                                                      \
   do {                                                                                            \
     using G = Cout1Geom<KS, MW>;                                                                  \
@@ -1434,8 +1446,7 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
                                           (int)smem);                                                                                             \
     kern<<<ctas, NT, smem, st>>>(p, tiles_w, per_img, total);                                     \
   } while (0)
-    static const int thin_mma = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
-    if (thin_mma && yb) {
+    if (yb) {
 #define OTM_WM1(KS)                                                                              \
   do {                                                                                            \
     const size_t smem = sizeof(__nv_bfloat16) * (TT * TT * 72 + (TT + KS - 1) * (TT + KS - 1) + 8); \
@@ -1459,10 +1470,9 @@ int conv_wgrad_simt(const otm_conv_wgrad_args* a, cudaStream_t st) {
     return OTM_OK;
   }
   // single output channel, 64 input channels, bf16 activations: mma.sync kernel
-  static const int thin_mma1 = [] { const char* e = getenv("OTM_THIN_MMA"); return e ? atoi(e) : 1; }();
-  if (thin_mma1 && p.cout == 1 && p.cin == 64 && a->x.dtype == OTM_BF16 && a->kh == a->kw &&
+  if (p.cout == 1 && p.cin == 64 && a->x.dtype == OTM_BF16 && a->kh == a->kw &&
       (a->kh == 4 || a->kh == 7) && !a->rs && !a->cs && vec_ok(a->x, 8) && a->dy.h * a->dy.w >= 256) {
-    static const int mw = [] { const char* e = getenv("OTM_COUT1_MW"); return e ? atoi(e) : 1; }();
+    constexpr int mw = 1;  // one M-warp per CTA measured best (3 CTAs / SM)
 #define OTM_W1M(TDY, KS, MW)                                                                     \
   do {                                                                                            \
     using G = Cout1Geom<KS, MW>;                                                                  \

@@ -182,10 +182,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 struct TcFwdP {
   View y, res;
   const float* row_scale;
+  const float* post_scale;  // [n, cout] applied AFTER the activation (NULL = 1)
   const float* bias;
   float alpha;
   int act, y_halo;
-  int debug;  // 0 normal; 1 skip epilogue stores; 2 skip the TMEM read-out too (timing experiments)
   int cin, cout, kh, kw;
   int coord_off;  // x_halo - pad : added to (h0 + r), (w0 + s) to index the halo'd tensor map
   int TW, TH, tiles_w;
@@ -202,6 +202,7 @@ __device__ __forceinline__ void epilogue_math16(const TcFwdP& p, int n, int oh, 
                                                 bool valid, float (&v)[16], uint8_t* dst,
                                                 const float* sc /* smem: alpha*row_scale */,
                                                 const float* bi /* smem: bias */,
+                                                const float* po /* smem: post-activation scale */,
                                                 uint8_t* dst_hi = nullptr) {
   {
     const float4* rs = reinterpret_cast<const float4*>(sc);
@@ -216,6 +217,14 @@ __device__ __forceinline__ void epilogue_math16(const TcFwdP& p, int n, int oh, 
     }
   }
   act_fwd_vec<16>(v, p.act);
+  if (p.post_scale) {
+    const float4* ps = reinterpret_cast<const float4*>(po);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = ps[q];
+      v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+    }
+  }
   if (p.res.ptr && valid) {
     const __nv_bfloat16* rp = vptr<__nv_bfloat16>(p.res, n, oh, ow, o);
     float r0[8], r1[8];
@@ -236,154 +245,6 @@ __device__ __forceinline__ void epilogue_math16(const TcFwdP& p, int n, int oh, 
   *reinterpret_cast<uint4*>(dst_hi ? dst_hi : dst + 16) = hi;
 }
 
-template <int BN, int STAGES, int OCC>
-__global__ void __launch_bounds__(256, OCC)
-conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   TcFwdP p) {
-  constexpr int B_STAGE_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* accum_full = bars + 2 * STAGES;
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 1);
-  float* s_scale = (float*)(((uintptr_t)(bars + 2 * STAGES + 2) + 15) & ~(uintptr_t)15);  // [BN]
-  float* s_bias = s_scale + BN;                      // [BN]
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int n = blockIdx.z;
-  const int tile = blockIdx.x;
-  const int h0 = (tile / p.tiles_w) * p.TH, w0 = (tile % p.tiles_w) * p.TW;
-  const int o0 = blockIdx.y * BN;
-  const int cin_chunks = p.cin / 64;
-  const int num_k = p.kh * p.kw * cin_chunks;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), 1);
-    }
-    mbar_init(smem_u32(accum_full), 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<BN>(smem_u32(tmem_ptr));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    const int wrow = n * p.w_rows_per_sample + o0;
-    for (int it = 0; it < num_k; ++it) {
-      const int stage = it % STAGES;
-      const uint32_t parity = ((it / STAGES) & 1) ^ 1;
-      mbar_wait(smem_u32(&empty[stage]), parity);
-      if (lane == 0) {
-        const int tap = it / cin_chunks, cc = it - tap * cin_chunks;
-        const int r = tap / p.kw, s = tap - r * p.kw;
-        const uint32_t bar = smem_u32(&full[stage]);
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        mbar_expect_tx(bar, STAGE_BYTES);
-        tma_load_4d(sa, &tmA, bar, cc * 64, w0 + s + p.coord_off, h0 + r + p.coord_off, n);
-        tma_load_2d(sa + A_STAGE_BYTES, &tmB, bar, tap * p.cin + cc * 64, wrow);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-    for (int it = 0; it < num_k; ++it) {
-      const int stage = it % STAGES;
-      const uint32_t parity = (it / STAGES) & 1;
-      mbar_wait(smem_u32(&full[stage]), parity);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t da = make_desc(sa, 16, 1024);
-        const uint64_t db = make_desc(sa + A_STAGE_BYTES, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // 4 x (K=16 bf16 = 32 B) per 128-B swizzled row
-          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                    (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(smem_u32(&empty[stage]));
-        if (it == num_k - 1) umma_commit(smem_u32(accum_full));
-      }
-      __syncwarp();
-    }
-  } else if (warp >= 4) {
-    // ---------------- epilogue ----------------
-    const int wq = warp - 4;
-    // stage the per-channel epilogue constants while the main loop runs
-    for (int t = threadIdx.x - 128; t < BN; t += 128) {
-      s_scale[t] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + t] : 1.f);
-      s_bias[t] = p.bias ? p.bias[o0 + t] : 0.f;
-    }
-    asm volatile("bar.sync 2, 128;" ::: "memory");
-    mbar_wait(smem_u32(accum_full), 0);
-    tc_fence_after();
-    const int m = wq * 32 + lane;
-    const int oh = h0 + m / p.TW, ow = w0 + m % p.TW;
-    const bool valid = (oh < p.y.h) && (ow < p.y.w);
-    // Phase 1: TMEM -> registers -> epilogue math -> bf16 staging tile in shared memory.  The
-    // operand ring is drained once accum_full has fired, so the tile aliases it.
-    constexpr int PITCH = BN * 2 + 16;
-    static_assert(128 * PITCH <= STAGES * STAGE_BYTES, "staging tile must fit inside the ring");
-    uint8_t* stage_out = smem;
-    if (p.debug < 2) {
-#pragma unroll 1
-      for (int j = 0; j < BN / 16; ++j) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
-        epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, stage_out + m * PITCH + j * 32,
-                            s_scale + j * 16, s_bias + j * 16);
-      }
-    }
-    if (p.debug == 4) {  // experiment: TMEM read-out only, no math, no staging
-#pragma unroll 1
-      for (int j = 0; j < BN / 16; ++j) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
-        if (v[0] == 123.456f) stage_out[m] = 1;
-      }
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-    // Phase 2: coalesced write-out, one 16-byte lane per 8 channels, whole pixel rows per warp
-    // instruction; the reflect halo of the consumer conv is written from the same registers.
-    if (p.debug == 0 || p.debug == 3) {
-      constexpr int LPR = BN / 8;          // lanes per pixel row
-      constexpr int RPP = 128 / LPR;       // pixel rows per pass
-      const int t = threadIdx.x - 128;
-      const int lr = t % LPR, r0 = t / LPR;
-#pragma unroll 1
-      for (int row = r0; row < 128; row += RPP) {
-        const int rh = h0 + row / p.TW, rw = w0 + row % p.TW;
-        if (rh >= p.y.h || rw >= p.y.w) continue;
-        const uint4 val = *reinterpret_cast<const uint4*>(stage_out + row * PITCH + lr * 16);
-        int hs[3], ws[3];
-        const int nh = mirror_set(rh, p.y.h, p.y_halo, hs);
-        const int nw = mirror_set(rw, p.y.w, p.y_halo, ws);
-        for (int a = 0; a < nh; ++a)
-          for (int b = 0; b < nw; ++b)
-            *reinterpret_cast<uint4*>(vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + lr * 8)) = val;
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
-  }
-}
-
 // ---------------------------------------------------------------------------
 // Persistent forward / dgrad kernel: one CTA per SM loops over output tiles; the fp32
 // accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i
@@ -402,195 +263,6 @@ struct TcFwdPP {
   int tiles_per_img;   // pixel tiles per image
   int cout_tiles;
 };
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1)
-conv_tc_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA,
-                           const __grid_constant__ CUtensorMap tmB,
-                           const __grid_constant__ CUtensorMap tmY, TcFwdPP pp) {
-  const TcFwdP& p = pp.p;
-  constexpr int B_STAGE_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  // staging tile = BN/64 sub-tiles of [128 pixel rows][64 ch = 128 B], 128-byte swizzled: the
-  // layout a SWIZZLE_128B TMA store box {64, TW, TH, 1} reads, conflict-free for the writers
-  constexpr int SUB_BYTES = 128 * 128;
-  constexpr int TILE_BYTES = (BN / 64) * SUB_BYTES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* stage_out = smem + STAGES * STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(stage_out + TILE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
-  float* s_scale = (float*)(((uintptr_t)(bars + 2 * STAGES + 5) + 15) & ~(uintptr_t)15);
-  float* s_bias = s_scale + BN;
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int cin_chunks = p.cin / 64;
-  const int num_k = p.kh * p.kw * cin_chunks;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmY);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&tmem_full[b]), 1);
-      mbar_init(smem_u32(&tmem_empty[b]), 128);  // every epilogue thread arrives
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<2 * BN>(smem_u32(tmem_ptr));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // tile -> (n, pixel tile, cout tile); cout tile fastest so the A tile is reused from L2
-  auto decode = [&](int t, int& n, int& h0, int& w0, int& o0) {
-    const int ct = t % pp.cout_tiles;
-    const int rest = t / pp.cout_tiles;
-    const int pt = rest % pp.tiles_per_img;
-    n = rest / pp.tiles_per_img;
-    h0 = (pt / p.tiles_w) * p.TH;
-    w0 = (pt % p.tiles_w) * p.TW;
-    o0 = ct * BN;
-  };
-
-  if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    int gi = 0;  // running k-iteration counter across tiles
-    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
-      int n, h0, w0, o0;
-      decode(t, n, h0, w0, o0);
-      const int wrow = n * p.w_rows_per_sample + o0;
-      for (int it = 0; it < num_k; ++it, ++gi) {
-        const int stage = gi % STAGES;
-        const uint32_t parity = ((gi / STAGES) & 1) ^ 1;
-        mbar_wait(smem_u32(&empty[stage]), parity);
-        if (lane == 0) {
-          const int tap = it / cin_chunks, cc = it - tap * cin_chunks;
-          const int r = tap / p.kw, s = tap - r * p.kw;
-          const uint32_t bar = smem_u32(&full[stage]);
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          mbar_expect_tx(bar, STAGE_BYTES);
-          tma_load_4d(sa, &tmA, bar, cc * 64, w0 + s + p.coord_off, h0 + r + p.coord_off, n);
-          tma_load_2d(sa + A_STAGE_BYTES, &tmB, bar, tap * p.cin + cc * 64, wrow);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-    int gi = 0, lt = 0;
-    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      // wait until the epilogue has drained this accumulator buffer (first use: free)
-      mbar_wait(smem_u32(&tmem_empty[buf]), ((lt >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-      for (int it = 0; it < num_k; ++it, ++gi) {
-        const int stage = gi % STAGES;
-        const uint32_t parity = (gi / STAGES) & 1;
-        mbar_wait(smem_u32(&full[stage]), parity);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = make_desc(sa, 16, 1024);
-          const uint64_t db = make_desc(sa + A_STAGE_BYTES, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                      (it > 0 || k > 0) ? 1u : 0u);
-          umma_commit(smem_u32(&empty[stage]));
-          if (it == num_k - 1) umma_commit(smem_u32(&tmem_full[buf]));
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp >= 4) {
-    // ---------------- epilogue (4 warps, TMEM lane quarter = warp - 4) ----------------
-    const int wq = warp - 4;
-    const int te = threadIdx.x - 128;
-    const int m = wq * 32 + lane;
-    int lt = 0;
-    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
-      int n, h0, w0, o0;
-      decode(t, n, h0, w0, o0);
-      const int buf = lt & 1;
-      for (int c = te; c < BN; c += 128) {
-        s_scale[c] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + c] : 1.f);
-        s_bias[c] = p.bias ? p.bias[o0 + c] : 0.f;
-      }
-      // the TMA store of the previous tile must have finished READING the staging tile
-      if (te == 0) tma_store_wait_read();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
-      tc_fence_after();
-      const int oh = h0 + m / p.TW, ow = w0 + m % p.TW;
-      const bool valid = (oh < p.y.h) && (ow < p.y.w);
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(wq * 32) << 16);
-      uint8_t* myrow = stage_out + m * 128;
-      const int sw = m & 7;
-      if (p.debug == 2) {  // timing experiment: main loop only
-        tc_fence_before();
-        mbar_arrive(smem_u32(&tmem_empty[buf]));
-        continue;
-      }
-#pragma unroll 1
-      for (int j = 0; j < BN / 16; ++j) {
-        float v[16];
-        tmem_ld16(tacc + (uint32_t)(j * 16), v);
-        uint8_t* sub = myrow + (j >> 2) * SUB_BYTES;
-        const int c = (j & 3) * 2;
-        epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, sub + ((c ^ sw) << 4),
-                            s_scale + j * 16, s_bias + j * 16, sub + (((c + 1) ^ sw) << 4));
-      }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty[buf]));  // accumulator buffer may be overwritten
-      fence_proxy_async();                      // generic-proxy smem writes -> async proxy
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (te == 0 && p.debug != 1) {
-#pragma unroll
-        for (int sb = 0; sb < BN / 64; ++sb)
-          tma_store_4d(&tmY, smem_u32(stage_out + sb * SUB_BYTES), o0 + sb * 64, w0, h0, n);
-        tma_store_commit();
-      }
-      // reflect halo of the consumer conv: only pixels in the border frame have mirror images
-      if (p.y_halo > 0 && valid) {
-        int hs[3], ws[3];
-        const int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
-        const int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
-        if (nh * nw > 1) {
-          for (int piece = 0; piece < BN / 8; ++piece) {
-            const uint4 val = *reinterpret_cast<const uint4*>(
-                myrow + (piece >> 3) * SUB_BYTES + (((piece & 7) ^ sw) << 4));
-            for (int a = 0; a < nh; ++a)
-              for (int b = 0; b < nw; ++b)
-                if (a + b > 0)
-                  *reinterpret_cast<uint4*>(
-                      vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + piece * 8)) = val;
-          }
-        }
-      }
-    }
-    if (te == 0) tma_store_wait_all();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
-  }
-}
 
 // ---------------------------------------------------------------------------
 // Row-reuse variant of the persistent kernel (square KxK filters, K = 3 or 4).
@@ -626,6 +298,7 @@ conv_tc_fwd_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
   float* s_scale = (float*)(((uintptr_t)(tmem_ptr + 2) + 15) & ~(uintptr_t)15);
   float* s_bias = s_scale + BN;
+  float* s_post = s_bias + BN;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int cin_chunks = p.cin / 64;
@@ -741,6 +414,7 @@ conv_tc_fwd_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int c = te; c < BN; c += 128) {
         s_scale[c] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + c] : 1.f);
         s_bias[c] = p.bias ? p.bias[o0 + c] : 0.f;
+        s_post[c] = p.post_scale ? p.post_scale[(long long)n * p.cout + o0 + c] : 1.f;
       }
       if (te == 0) tma_store_wait_read();
       asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -758,7 +432,8 @@ conv_tc_fwd_rr_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         uint8_t* sub = myrow + (j >> 2) * SUB_BYTES;
         const int c = (j & 3) * 2;
         epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, sub + ((c ^ sw) << 4),
-                            s_scale + j * 16, s_bias + j * 16, sub + (((c + 1) ^ sw) << 4));
+                            s_scale + j * 16, s_bias + j * 16, s_post + j * 16,
+                            sub + (((c + 1) ^ sw) << 4));
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tmem_empty[buf]));
@@ -829,6 +504,7 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
   float* s_scale = (float*)(((uintptr_t)(tmem_ptr + 2) + 15) & ~(uintptr_t)15);
   float* s_bias = s_scale + BN;
+  float* s_post = s_bias + BN;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int cin_chunks = p.cin / 64;
@@ -959,6 +635,7 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int c = te; c < BN; c += 128) {
         s_scale[c] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + c] : 1.f);
         s_bias[c] = p.bias ? p.bias[o0 + c] : 0.f;
+        s_post[c] = p.post_scale ? p.post_scale[(long long)n * p.cout + o0 + c] : 1.f;
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");  // s_scale / s_bias visible
       mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
@@ -989,7 +666,8 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             uint8_t* sub = myrow + (j >> 2) * SUB_BYTES;
             const int c = (j & 3) * 2;
             epilogue_math16<BN>(p, n, oh, ow, o0 + j * 16, valid, v, sub + ((c ^ sw) << 4),
-                                s_scale + j * 16, s_bias + j * 16, sub + (((c + 1) ^ sw) << 4));
+                                s_scale + j * 16, s_bias + j * 16, s_post + j * 16,
+                            sub + (((c + 1) ^ sw) << 4));
           }
         }
         tc_fence_before();
@@ -1188,6 +866,7 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int buf = lt & 1;
       const float scale = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + m] : 1.f);
       const float bias = p.bias ? p.bias[o0 + m] : 0.f;
+      const float post = p.post_scale ? p.post_scale[(long long)n * p.cout + o0 + m] : 1.f;
       mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
       tc_fence_after();
       const int nhalf = (h0 + TH) < p.y.h ? 2 : 1;
@@ -1204,10 +883,8 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll 1
         for (int j2 = 0; j2 < 4; ++j2) {
-          if (p.debug & 2) break;  // timing experiment: no TMEM read-out
           float v[32];
           tmem_ld32(tacc + (uint32_t)(j2 * 32), v);
-          if (p.debug & 1) continue;  // timing experiment: no epilogue math / staging stores
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], scale, bias);
           act_fwd_vec<32>(v, p.act);
@@ -1215,7 +892,7 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           for (int i = 0; i < 32; ++i) {
             const int q = j2 * 32 + i;  // pixel of this half-tile
             *reinterpret_cast<__nv_bfloat16*>(chan_base + q * 128 + ((chunk ^ (q & 7)) << 4)) =
-                __float2bfloat16_rn(v[i]);
+                __float2bfloat16_rn(v[i] * post);
           }
         }
         tc_fence_before();
@@ -1248,7 +925,7 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (te == 0 && hh0 < p.y.h && !(p.debug & 4)) {  // debug 4: no TMA store
+        if (te == 0 && hh0 < p.y.h) {
 #pragma unroll
           for (int sb = 0; sb < BN / 64; ++sb)
             tma_store_4d(&tmY, smem_u32(stage_out + sb * SUB_BYTES), o0 + sb * 64, w0, hh0, n);
@@ -1288,7 +965,7 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 struct TcWgP {
   float* dw;
   float* ws;  // [tap][M][N] fp32 partial-sum workspace (NULL: scalar reds into dw)
-  const __nv_bfloat16* wfwd;  // per-sample forward pack [n][cout][taps][cin] (fused P term)
+  const __nv_bfloat16* wfwd;  // forward pack [n | 1][cout][taps][cin] (fused P term)
   float* P;                   // [n][cout]
   const float* rs;
   const float* cs;
@@ -1298,18 +975,26 @@ struct TcWgP {
   int x_coord_off;   // x_halo - pad
   int tiles_w, tiles_total, splits;
   int n_tiles_n;     // number of N tiles (grid.y = m_tiles * n_tiles_n)
-  int debug;         // 1: skip the reduction into dw (timing experiments)
+  long long wfwd_n_stride;  // elements between per-sample forward packs (0: one shared pack)
 };
 
 constexpr int WG_CHUNK_BYTES = 64 * 128;  // 64 pixels x 64 channels bf16
 
-template <int BN, int STAGES, int OCC>
+// TPC = filter taps per CTA.  The dy tile (the M operand when Cout % 128 == 0) is the same for
+// every tap, only the x tile shifts: TPC x tiles are laid side by side in the ring as ONE
+// MN-major B operand of N = TPC * BN columns (the 64-channel chunk stride is uniform), so one
+// 128 x (TPC*BN) x 16 MMA serves TPC taps and reads the dy tile once.  A 128 x 128 MMA needs
+// 128 B/clk of operands (= the SM's shared-memory bandwidth, ~1.0-1.1 PFLOP/s measured with the
+// reduction skipped); at N = 256 it is 96 B/clk, the same ratio that lifted the forward kernel.
+template <int BN, int STAGES, int OCC, int TPC>
 __global__ void __launch_bounds__(256, OCC)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmB, TcWgP p) {
+  static_assert(BN * TPC <= 256, "accumulator exceeds one MMA's N / the TMEM share of a CTA");
+  constexpr int NCOLS = BN * TPC;
   constexpr int A_BYTES = 2 * WG_CHUNK_BYTES;
-  constexpr int B_BYTES = (BN / 64) * WG_CHUNK_BYTES;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int B_TAP_BYTES = (BN / 64) * WG_CHUNK_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + TPC * B_TAP_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -1319,8 +1004,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int tap = blockIdx.x;
-  const int r = tap / p.kw, s = tap - r * p.kw;
+  const int taps = p.kh * p.kw;
+  const int tap0 = blockIdx.x * TPC;
+  const int ntap = min(TPC, taps - tap0);  // the last CTA of an odd tap count takes fewer
   const int mt = blockIdx.y / p.n_tiles_n, nt = blockIdx.y % p.n_tiles_n;
   const int m0 = mt * 128, n0 = nt * BN;
   const int n = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
@@ -1340,7 +1026,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
     mbar_init(smem_u32(accum_full), 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<BN>(smem_u32(tmem_ptr));
+  if (warp == 2) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1348,8 +1034,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (num_k > 0) {
     if (warp == 0) {
-      const int sh_a = p.a_is_x ? (r + p.x_coord_off) : 0, sw_a = p.a_is_x ? (s + p.x_coord_off) : 0;
-      const int sh_b = p.a_is_x ? 0 : (r + p.x_coord_off), sw_b = p.a_is_x ? 0 : (s + p.x_coord_off);
+      // TPC > 1 only with a_is_x == 0 (host): the A operand (dy) does not depend on the tap
+      const int r0 = tap0 / p.kw, s0 = tap0 - r0 * p.kw;
+      const int sh_a = p.a_is_x ? (r0 + p.x_coord_off) : 0, sw_a = p.a_is_x ? (s0 + p.x_coord_off) : 0;
+      const uint32_t stage_tx = (uint32_t)(A_BYTES + ntap * B_TAP_BYTES);
       for (int it = 0; it < num_k; ++it) {
         const int stage = it % STAGES;
         const uint32_t parity = ((it / STAGES) & 1) ^ 1;
@@ -1359,19 +1047,24 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
           const int h0 = (t / p.tiles_w) * 8, w0 = (t % p.tiles_w) * 8;
           const uint32_t bar = smem_u32(&full[stage]);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          mbar_expect_tx(bar, STAGE_BYTES);
+          mbar_expect_tx(bar, stage_tx);
 #pragma unroll
           for (int c = 0; c < 2; ++c)
             tma_load_4d(sa + c * WG_CHUNK_BYTES, &tmA, bar, m0 + c * 64, w0 + sw_a, h0 + sh_a, n);
+          for (int tp = 0; tp < ntap; ++tp) {
+            const int tap = tap0 + tp;
+            const int r = tap / p.kw, s = tap - r * p.kw;
+            const int sh_b = p.a_is_x ? 0 : (r + p.x_coord_off), sw_b = p.a_is_x ? 0 : (s + p.x_coord_off);
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c)
-            tma_load_4d(sa + A_BYTES + c * WG_CHUNK_BYTES, &tmB, bar, n0 + c * 64, w0 + sw_b,
-                        h0 + sh_b, n);
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_4d(sa + A_BYTES + tp * B_TAP_BYTES + c * WG_CHUNK_BYTES, &tmB, bar, n0 + c * 64,
+                          w0 + sw_b, h0 + sh_b, n);
+          }
         }
         __syncwarp();
       }
     } else if (warp == 1) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+      const uint32_t idesc = make_idesc(128, BN * ntap, 1, 1);
       for (int it = 0; it < num_k; ++it) {
         const int stage = it % STAGES;
         const uint32_t parity = (it / STAGES) & 1;
@@ -1396,7 +1089,6 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_wait(smem_u32(accum_full), 0);
       tc_fence_after();
       const int m = m0 + wq * 32 + lane;
-      const int taps = p.kh * p.kw;
       // row factor
       float rowf = p.alpha;
       if (p.a_is_x) { if (p.cs) rowf *= p.cs[(long long)n * p.cin + m]; }
@@ -1404,183 +1096,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
       const int Mtot = p.a_is_x ? p.cin : p.cout, Ntot = p.a_is_x ? p.cout : p.cin;
       const float* colv = p.a_is_x ? p.rs : p.cs;  // per-sample factor along the N (column) axis
       float pacc = 0.f;  // sum_i G[o,i,tap] * wfwd[n][o][tap][i] over this tile's columns
-      const __nv_bfloat16* wrow =
-          p.P ? p.wfwd + (((long long)n * p.cout + m) * taps + tap) * p.cin : nullptr;
 #pragma unroll 1
-      for (int j = 0; j < BN / 16; ++j) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * 16), v);
-        const int nn0 = n0 + j * 16;
-        if (wrow) {
-          float w0[8], w1[8];
-          load_vec<__nv_bfloat16, 8>(wrow + nn0, w0);
-          load_vec<__nv_bfloat16, 8>(wrow + nn0 + 8, w1);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pacc = fmaf(v[i], w0[i], fmaf(v[8 + i], w1[i], pacc));
-        }
-        if (colv) {
-          const float4* cp = reinterpret_cast<const float4*>(colv + (long long)n * Ntot + nn0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 t = cp[q];
-            v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= rowf;
-        if (p.debug) continue;
-        if (p.ws) {  // 128-bit vector reds, contiguous along N
-          float4* dst = reinterpret_cast<float4*>(p.ws + ((long long)tap * Mtot + m) * Ntot + nn0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            atomicAdd(dst + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int nn = nn0 + i;
-            const int o = p.a_is_x ? nn : m, ci = p.a_is_x ? m : nn;
-            atomicAdd(p.dw + ((long long)o * p.cin + ci) * taps + tap, v[i]);
-          }
-        }
-      }
-      if (wrow && p.debug == 0) {
-        const float rsv = p.rs ? p.rs[(long long)n * p.cout + m] : 1.f;
-        atomicAdd(p.P + (long long)n * p.cout + m, pacc * rsv);
-      }
-      tc_fence_before();
-    }
-  }
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Row-reuse wgrad: one CTA owns a filter COLUMN s and all KS filter rows of it.  Per K stage
-// (an 8 x 8 pixel tile of one sample) it loads the dy tile once and ONE x box of (8 + KS - 1)
-// rows; the operand of tap (r, s) is that box read through a descriptor offset by r pixel rows
-// (1024 B), exactly like the forward row-reuse kernel.  KS accumulators live in TMEM
-// (KS * BN columns).  L2 -> shared traffic per MMA drops from 8 KB (the per-tap kernel above
-// re-fetches both tiles for each of the kh*kw taps and measured ~9 TB/s of L2 reads at
-// 600 TFLOP/s, i.e. L2-bound) to 3 KB.
-//   XCH / DCH = 64-channel chunks of the x / dy operand (the M side always has 2 = 128 rows).
-// ---------------------------------------------------------------------------
-template <int XCH, int DCH, int KS, int STAGES>
-__global__ void __launch_bounds__(256, 1)
-conv_tc_wgrad_rr_kernel(const __grid_constant__ CUtensorMap tmX,
-                        const __grid_constant__ CUtensorMap tmDy, TcWgP p) {
-  constexpr int TH = 8;
-  constexpr int X_BOX = (TH + KS - 1) * 1024;  // (8 + KS - 1) rows x 8 pixels x 128 B
-  constexpr int D_BOX = TH * 1024;
-  constexpr int X_BYTES = XCH * X_BOX, D_BYTES = DCH * D_BOX;
-  constexpr int STAGE_BYTES = X_BYTES + D_BYTES;
-  constexpr int BN = 64 * (XCH + DCH - 2);  // the side that is not the 128-row M side
-  constexpr int TCOLS = KS * BN <= 256 ? 256 : 512;
-  static_assert(KS * BN <= 512, "accumulators exceed TMEM");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* accum_full = bars + 2 * STAGES;
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 1);
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int s = blockIdx.x;  // filter column
-  const int mt = blockIdx.y / p.n_tiles_n, nt = blockIdx.y % p.n_tiles_n;
-  const int m0 = mt * 128, n0 = nt * BN;
-  const int n = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
-  const int t_beg = (int)((long long)p.tiles_total * split / p.splits);
-  const int t_end = (int)((long long)p.tiles_total * (split + 1) / p.splits);
-  const int num_k = t_end - t_beg;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmDy);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int st = 0; st < STAGES; ++st) {
-      mbar_init(smem_u32(&full[st]), 1);
-      mbar_init(smem_u32(&empty[st]), 1);
-    }
-    mbar_init(smem_u32(accum_full), 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<TCOLS>(smem_u32(tmem_ptr));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (num_k > 0) {
-    if (warp == 0) {
-      const int xc0 = p.a_is_x ? m0 : n0, dc0 = p.a_is_x ? n0 : m0;
-      for (int it = 0; it < num_k; ++it) {
-        const int stage = it % STAGES;
-        mbar_wait(smem_u32(&empty[stage]), ((it / STAGES) & 1) ^ 1);
-        if (lane == 0) {
-          const int t = t_beg + it;
-          const int h0 = (t / p.tiles_w) * TH, w0 = (t % p.tiles_w) * 8;
-          const uint32_t bar = smem_u32(&full[stage]);
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          mbar_expect_tx(bar, STAGE_BYTES);
-#pragma unroll
-          for (int c = 0; c < XCH; ++c)
-            tma_load_4d(sa + c * X_BOX, &tmX, bar, xc0 + c * 64, w0 + s + p.x_coord_off,
-                        h0 + p.x_coord_off, n);
-#pragma unroll
-          for (int c = 0; c < DCH; ++c)
-            tma_load_4d(sa + X_BYTES + c * D_BOX, &tmDy, bar, dc0 + c * 64, w0, h0, n);
-        }
-        __syncwarp();
-      }
-    } else if (warp == 1) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
-      for (int it = 0; it < num_k; ++it) {
-        const int stage = it % STAGES;
-        mbar_wait(smem_u32(&full[stage]), (it / STAGES) & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          // MN-major SW128: LBO = stride between 64-channel chunks, SBO = 8 pixels (1024 B)
-          const uint64_t dd = make_desc(sa + X_BYTES, D_BOX, 1024);
-#pragma unroll
-          for (int r = 0; r < KS; ++r) {
-            const uint64_t dx = make_desc(sa + r * 1024, X_BOX, 1024);
-            const uint64_t da = p.a_is_x ? dx : dd, db = p.a_is_x ? dd : dx;
-#pragma unroll
-            for (int k = 0; k < TH / 2; ++k)  // 16 pixels (K) = 2 pixel rows = 2048 B per step
-              umma_bf16(tmem_base + (uint32_t)(r * BN), da + (uint64_t)(k * 128),
-                        db + (uint64_t)(k * 128), idesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(smem_u32(&empty[stage]));
-          if (it == num_k - 1) umma_commit(smem_u32(accum_full));
-        }
-        __syncwarp();
-      }
-    } else if (warp >= 4) {
-      const int wq = warp - 4;
-      mbar_wait(smem_u32(accum_full), 0);
-      tc_fence_after();
-      const int m = m0 + wq * 32 + lane;
-      const int taps = p.kh * p.kw;
-      float rowf = p.alpha;
-      if (p.a_is_x) { if (p.cs) rowf *= p.cs[(long long)n * p.cin + m]; }
-      else { if (p.rs) rowf *= p.rs[(long long)n * p.cout + m]; }
-      const int Mtot = p.a_is_x ? p.cin : p.cout, Ntot = p.a_is_x ? p.cout : p.cin;
-      const float* colv = p.a_is_x ? p.rs : p.cs;
-      float pacc = 0.f;
-#pragma unroll 1
-      for (int r = 0; r < KS; ++r) {
-        const int tap = r * p.kw + s;
+      for (int tp = 0; tp < ntap; ++tp) {
+        const int tap = tap0 + tp;
         const __nv_bfloat16* wrow =
-            p.P ? p.wfwd + (((long long)n * p.cout + m) * taps + tap) * p.cin : nullptr;
+            p.P ? p.wfwd + (long long)n * p.wfwd_n_stride + ((long long)m * taps + tap) * p.cin : nullptr;
 #pragma unroll 1
         for (int j = 0; j < BN / 16; ++j) {
           float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(r * BN + j * 16), v);
+          tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tp * BN + j * 16), v);
           const int nn0 = n0 + j * 16;
           if (wrow) {
             float w0[8], w1[8];
@@ -1599,8 +1123,7 @@ conv_tc_wgrad_rr_kernel(const __grid_constant__ CUtensorMap tmX,
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= rowf;
-          if (p.debug) continue;
-          if (p.ws) {
+          if (p.ws) {  // 128-bit vector reds, contiguous along N
             float4* dst = reinterpret_cast<float4*>(p.ws + ((long long)tap * Mtot + m) * Ntot + nn0);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -1615,7 +1138,7 @@ conv_tc_wgrad_rr_kernel(const __grid_constant__ CUtensorMap tmX,
           }
         }
       }
-      if (p.P && p.debug == 0) {
+      if (p.P) {
         const float rsv = p.rs ? p.rs[(long long)n * p.cout + m] : 1.f;
         atomicAdd(p.P + (long long)n * p.cout + m, pacc * rsv);
       }
@@ -1625,7 +1148,7 @@ conv_tc_wgrad_rr_kernel(const __grid_constant__ CUtensorMap tmX,
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TCOLS>(tmem_base);
+    tmem_dealloc<NCOLS>(tmem_base);
   }
 }
 
@@ -1690,6 +1213,7 @@ static bool act_tma_ok(const otm_tensor& t) {
 }
 
 bool conv_fwd_tc_eligible(const otm_conv_fwd_args* a) {
+  if (a->kh != a->kw || (a->kh != 3 && a->kh != 4)) return false;  // the row-reuse kernels
   if (!act_tma_ok(a->x) || a->y.dtype != OTM_BF16) return false;
   if (a->y.c % 64 != 0 || a->y.sw % 8 || a->y.sh % 8 || a->y.sn % 8) return false;
   if ((uintptr_t)a->y.ptr % 16 || (uintptr_t)a->wpack % 16) return false;
@@ -1702,39 +1226,11 @@ bool conv_fwd_tc_eligible(const otm_conv_fwd_args* a) {
   return true;
 }
 
-template <int BN, int STAGES, int OCC>
-static int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcFwdP& p, dim3 grid,
-                      cudaStream_t st) {
-  constexpr int ring = STAGES * (A_STAGE_BYTES + BN * 128);
-  constexpr int tile = 128 * (BN * 2 + 16);  // epilogue staging tile aliases the ring
-  constexpr int smem = (ring > tile ? ring : tile) + 1024 + 256 + 2 * BN * 4;
-  auto kern = conv_tc_fwd_kernel<BN, STAGES, OCC>;
-  OTM_ENSURE_SMEM(kern, smem);
-  kern<<<grid, 256, smem, st>>>(tmA, tmB, p);
-  OTM_LAUNCH_CHECK();
-  return OTM_OK;
-}
-
-template <int BN, int STAGES>
-static int launch_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB,
-                              const CUtensorMap& tmY, const TcFwdPP& pp, int ctas,
-                              cudaStream_t st) {
-  constexpr int ring = STAGES * (A_STAGE_BYTES + BN * 128);
-  constexpr int tile = (BN / 64) * 128 * 128;
-  constexpr int smem = ring + tile + 1024 + 256 + 2 * BN * 4;
-  static_assert(smem <= 227 * 1024, "persistent conv kernel exceeds shared memory");
-  auto kern = conv_tc_fwd_persist_kernel<BN, STAGES>;
-  OTM_ENSURE_SMEM(kern, smem);
-  kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
-  OTM_LAUNCH_CHECK();
-  return OTM_OK;
-}
-
 template <int BN, int KS, int NA, int NB>
 static int launch_fwd_rr(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                          const TcFwdPP& pp, int ctas, cudaStream_t st) {
   constexpr int smem = NA * (16 + KS - 1) * 8 * 128 + NB * BN * 128 + (BN / 64) * 128 * 128 + 1024 +
-                       512 + 2 * BN * 4;
+                       512 + 3 * BN * 4;
   static_assert(smem <= 227 * 1024, "row-reuse conv kernel exceeds shared memory");
   auto kern = conv_tc_fwd_rr_kernel<BN, KS, NA, NB>;
   OTM_ENSURE_SMEM(kern, smem);
@@ -1747,7 +1243,7 @@ template <int BN, int KS, int NA, int NB>
 static int launch_fwd_rr2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                           const TcFwdPP& pp, int ctas, cudaStream_t st) {
   constexpr int smem = NA * 2 * (16 + KS - 1) * 8 * 128 + NB * BN * 128 + (BN / 64) * 128 * 128 +
-                       1024 + 512 + 2 * BN * 4;
+                       1024 + 512 + 3 * BN * 4;
   static_assert(smem <= 227 * 1024, "pair conv kernel exceeds shared memory");
   static_assert(4 * BN <= 512, "pair conv kernel exceeds TMEM");
   auto kern = conv_tc_fwd_rr2_kernel<BN, KS, NA, NB>;
@@ -1771,107 +1267,64 @@ static int launch_fwd_rr2t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 
 int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   const int Ho = a->y.h, Wo = a->y.w, cout = a->y.c, cin = a->x.c;
-  // pixel tile shape: 128 = TW x TH, minimise the number of tiles (ties -> squarer)
-  int best_tw = 16, best_tiles = 1 << 30;
-  const int cand[5] = {16, 32, 8, 64, 128};
-  for (int i = 0; i < 5; ++i) {
-    int tw = cand[i], th = 128 / tw;
-    int tiles = ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
-    if (tiles < best_tiles) { best_tiles = tiles; best_tw = tw; }
-  }
-  static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
-  const bool rr = (variant == 0) && a->kh == a->kw && (a->kh == 3 || a->kh == 4);
-  if (rr) {  // row-reuse kernel: fixed 16 x 8 pixel tile
-    best_tw = 8;
-    best_tiles = ((Wo + 7) / 8) * ((Ho + 15) / 16);
-  }
-  const int TW = best_tw, TH = 128 / TW;
+  const int KS = a->kh;  // 3 or 4 (conv_fwd_tc_eligible)
+  // row-reuse kernels: fixed 16 x 8 pixel tile
+  constexpr int TW = 8, TH = 16;
+  const int tile_rows = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
+  const int tiles = tile_rows * tiles_w;
   int BN = 128;
   if (cout % 128 != 0) BN = 64;
-  else if (cout % 256 == 0 && (long long)best_tiles * a->y.n * (cout / 256) >= 2 * num_sms()) BN = 256;
+  else if (cout % 256 == 0 && (long long)tiles * a->y.n * (cout / 256) >= 2 * num_sms()) BN = 256;
 
-  CUtensorMap tmA, tmB;
-  int rc = make_act_map(&tmA, a->x, a->x_halo, TW, rr ? TH + a->kh - 1 : TH);
+  CUtensorMap tmA, tmB, tmY;
+  int rc = make_act_map(&tmA, a->x, a->x_halo, TW, TH + KS - 1);
   if (rc) return rc;
-  const long long ktot = (long long)a->kh * a->kw * cin;
+  const long long ktot = (long long)KS * KS * cin;
   const long long rows = (a->w_batch_stride ? (long long)a->x.n : 1) * cout;
   rc = make_weight_map(&tmB, a->wpack, rows, ktot, BN);
   if (rc) return rc;
+  rc = make_act_map(&tmY, a->y, 0, TW, TH);  // interior of y: the TMA store clips tile tails
+  if (rc) return rc;
 
-  TcFwdP p;
+  TcFwdPP pp;
+  TcFwdP& p = pp.p;
   p.y = make_view(a->y);
   p.res = a->residual.ptr ? make_view(a->residual) : null_view();
-  p.row_scale = a->row_scale; p.bias = a->bias; p.alpha = a->alpha; p.act = a->act;
-  p.y_halo = a->y_halo; p.cin = cin; p.cout = cout; p.kh = a->kh; p.kw = a->kw;
+  p.row_scale = a->row_scale; p.post_scale = a->post_scale; p.bias = a->bias; p.alpha = a->alpha;
+  p.act = a->act;
+  p.y_halo = a->y_halo; p.cin = cin; p.cout = cout; p.kh = KS; p.kw = KS;
   p.coord_off = a->x_halo - a->pad;
-  p.TW = TW; p.TH = TH; p.tiles_w = (Wo + TW - 1) / TW;
+  p.TW = TW; p.TH = TH; p.tiles_w = tiles_w;
   p.w_rows_per_sample = a->w_batch_stride ? cout : 0;
-  static const int dbg = [] { const char* e = getenv("OTM_TC_DEBUG"); return e ? atoi(e) : 0; }();
-  p.debug = dbg;
-  dim3 grid(best_tiles, cout / BN, a->y.n);
-  // variant 0 (default): persistent kernels (row-reuse for 3x3 / 4x4); 4: persistent without
-  // row reuse; 2/3: 3 or 2 CTAs per SM, one tile per CTA; 1: 1 CTA per SM with a deep ring.
-  if (variant == 1) {
-    if (BN == 64) return launch_fwd<64, 6, 1>(tmA, tmB, p, grid, st);
-    if (BN == 128) return launch_fwd<128, 6, 1>(tmA, tmB, p, grid, st);
-    return launch_fwd<256, 4, 1>(tmA, tmB, p, grid, st);
-  }
-  if (variant == 3) {  // 2 CTAs per SM, 3/4-deep ring
-    if (BN == 64) return launch_fwd<64, 4, 2>(tmA, tmB, p, grid, st);
-    if (BN == 128) return launch_fwd<128, 3, 2>(tmA, tmB, p, grid, st);
-    return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
-  }
-  if (variant == 0 || variant == 4) {  // persistent, double-buffered TMEM accumulator
-    TcFwdPP pp;
-    pp.p = p;
-    pp.cout_tiles = cout / BN;
-    pp.tiles_per_img = best_tiles;
-    pp.total_tiles = best_tiles * pp.cout_tiles * a->y.n;
-    int ctas = num_sms();
-    if (ctas > pp.total_tiles) ctas = pp.total_tiles;
-    CUtensorMap tmY;  // interior of y only: the TMA store clips tile tails at the image edge
-    rc = make_act_map(&tmY, a->y, 0, TW, TH);
-    if (rc) return rc;
-    // pair kernel: two tile rows per CTA when there are enough pairs to fill the SMs
-    const int tile_rows = (Ho + 15) / 16, tiles_w8 = (Wo + 7) / 8;
-    const long long pairs = (long long)((tile_rows + 1) / 2) * tiles_w8 * pp.cout_tiles * a->y.n;
-    if (rr && variant == 0 && BN <= 128 && pairs >= 2LL * num_sms()) {
-      pp.tiles_per_img = ((tile_rows + 1) / 2) * tiles_w8;
-      pp.total_tiles = (int)pairs;
-      int c2 = num_sms();
-      static const int rr2t = [] { const char* e = getenv("OTM_RR2T"); return e ? atoi(e) : 1; }();
-      if (rr2t && BN == 128) {  // weights as the M operand, 256-pixel N operand
-        CUtensorMap tmA2;       // one box for both tiles of the pair
-        rc = make_act_map(&tmA2, a->x, a->x_halo, 8, 32 + a->kh - 1);
-        if (rc) return rc;
-        if (a->kh == 3) return launch_fwd_rr2t<3, 2, 6>(tmA2, tmB, tmY, pp, c2, st);
-        return launch_fwd_rr2t<4, 2, 6>(tmA2, tmB, tmY, pp, c2, st);
-      }
-      if (a->kh == 3) {
-        if (BN == 64) return launch_fwd_rr2<64, 3, 3, 8>(tmA, tmB, tmY, pp, c2, st);
-        return launch_fwd_rr2<128, 3, 2, 6>(tmA, tmB, tmY, pp, c2, st);
-      }
-      if (BN == 64) return launch_fwd_rr2<64, 4, 3, 8>(tmA, tmB, tmY, pp, c2, st);
-      return launch_fwd_rr2<128, 4, 2, 6>(tmA, tmB, tmY, pp, c2, st);
+  pp.cout_tiles = cout / BN;
+  pp.tiles_per_img = tiles;
+  pp.total_tiles = tiles * pp.cout_tiles * a->y.n;
+  int ctas = num_sms();
+  // pair kernels: two vertically adjacent tiles per CTA step when there are enough pairs to fill
+  // the SMs twice
+  const long long pairs = (long long)((tile_rows + 1) / 2) * tiles_w * pp.cout_tiles * a->y.n;
+  if (BN <= 128 && pairs >= 2LL * num_sms()) {
+    pp.tiles_per_img = ((tile_rows + 1) / 2) * tiles_w;
+    pp.total_tiles = (int)pairs;
+    if (BN == 128) {  // weights as the M operand, ONE 256-pixel box for both tiles of the pair
+      CUtensorMap tmA2;
+      rc = make_act_map(&tmA2, a->x, a->x_halo, TW, 2 * TH + KS - 1);
+      if (rc) return rc;
+      if (KS == 3) return launch_fwd_rr2t<3, 2, 6>(tmA2, tmB, tmY, pp, ctas, st);
+      return launch_fwd_rr2t<4, 2, 6>(tmA2, tmB, tmY, pp, ctas, st);
     }
-    if (rr) {
-      if (a->kh == 3) {
-        if (BN == 64) return launch_fwd_rr<64, 3, 4, 12>(tmA, tmB, tmY, pp, ctas, st);
-        if (BN == 128) return launch_fwd_rr<128, 3, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
-        return launch_fwd_rr<256, 3, 3, 3>(tmA, tmB, tmY, pp, ctas, st);
-      }
-      if (BN == 64) return launch_fwd_rr<64, 4, 4, 12>(tmA, tmB, tmY, pp, ctas, st);
-      if (BN == 128) return launch_fwd_rr<128, 4, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
-      return launch_fwd_rr<256, 4, 3, 3>(tmA, tmB, tmY, pp, ctas, st);
-    }
-    if (BN == 64) return launch_fwd_persist<64, 6>(tmA, tmB, tmY, pp, ctas, st);
-    if (BN == 128) return launch_fwd_persist<128, 5>(tmA, tmB, tmY, pp, ctas, st);
-    return launch_fwd_persist<256, 3>(tmA, tmB, tmY, pp, ctas, st);
+    if (KS == 3) return launch_fwd_rr2<64, 3, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
+    return launch_fwd_rr2<64, 4, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
   }
-  // variant 2: 3 CTAs per SM with a 2-deep ring
-  if (BN == 64) return launch_fwd<64, 3, 3>(tmA, tmB, p, grid, st);
-  if (BN == 128) return launch_fwd<128, 2, 3>(tmA, tmB, p, grid, st);
-  return launch_fwd<256, 2, 2>(tmA, tmB, p, grid, st);
+  if (ctas > pp.total_tiles) ctas = pp.total_tiles;
+  if (KS == 3) {
+    if (BN == 64) return launch_fwd_rr<64, 3, 4, 12>(tmA, tmB, tmY, pp, ctas, st);
+    if (BN == 128) return launch_fwd_rr<128, 3, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
+    return launch_fwd_rr<256, 3, 3, 3>(tmA, tmB, tmY, pp, ctas, st);
+  }
+  if (BN == 64) return launch_fwd_rr<64, 4, 4, 12>(tmA, tmB, tmY, pp, ctas, st);
+  if (BN == 128) return launch_fwd_rr<128, 4, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
+  return launch_fwd_rr<256, 4, 3, 3>(tmA, tmB, tmY, pp, ctas, st);
 }
 
 bool conv_wgrad_tc_eligible(const otm_conv_wgrad_args* a) {
@@ -1896,25 +1349,14 @@ __global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict
   }
 }
 
-template <int BN, int STAGES, int OCC>
+template <int BN, int STAGES, int OCC, int TPC>
 static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcWgP& p, dim3 grid,
                         cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * WG_CHUNK_BYTES + (BN / 64) * WG_CHUNK_BYTES) + 1024 + 256;
-  auto kern = conv_tc_wgrad_kernel<BN, STAGES, OCC>;
+  constexpr int smem = STAGES * (2 * WG_CHUNK_BYTES + TPC * (BN / 64) * WG_CHUNK_BYTES) + 1024 + 256;
+  static_assert(smem * OCC <= 226 * 1024, "wgrad ring exceeds the shared memory of an SM");
+  auto kern = conv_tc_wgrad_kernel<BN, STAGES, OCC, TPC>;
   OTM_ENSURE_SMEM(kern, smem);
   kern<<<grid, 256, smem, st>>>(tmA, tmB, p);
-  OTM_LAUNCH_CHECK();
-  return OTM_OK;
-}
-
-template <int XCH, int DCH, int KS, int STAGES>
-static int launch_wgrad_rr(const CUtensorMap& tmX, const CUtensorMap& tmDy, const TcWgP& p, dim3 grid,
-                           cudaStream_t st) {
-  constexpr int smem = STAGES * (XCH * (8 + KS - 1) * 1024 + DCH * 8 * 1024) + 1024 + 256;
-  static_assert(smem <= 227 * 1024, "wgrad rr ring exceeds shared memory");
-  auto kern = conv_tc_wgrad_rr_kernel<XCH, DCH, KS, STAGES>;
-  OTM_ENSURE_SMEM(kern, smem);
-  kern<<<grid, 256, smem, st>>>(tmX, tmDy, p);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
 }
@@ -1934,89 +1376,42 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const int taps = a->kh * a->kw;
   const int m_tiles = M / 128;
   p.n_tiles_n = N / BN;
-  long long base = (long long)taps * m_tiles * p.n_tiles_n * a->dy.n;
+  // taps per CTA: as many shifted x tiles as fit a 256-column MMA next to the one dy tile
+  // (OTM_WGRAD_TPC=1 restores one tap per CTA, for A/B measurements)
+  static const int tpc_cap = [] { const char* e = getenv("OTM_WGRAD_TPC"); return e ? atoi(e) : 4; }();
+  int tpc = p.a_is_x ? 1 : 256 / BN;
+  if (tpc > tpc_cap) tpc = tpc_cap;
+  const int tap_ctas = (taps + tpc - 1) / tpc;
+  long long base = (long long)tap_ctas * m_tiles * p.n_tiles_n * a->dy.n;
   int splits = (int)((4LL * num_sms() + base - 1) / base);  // ~2 waves at 2 CTAs per SM
   int max_splits = (p.tiles_total + 31) / 32;  // keep >= 32 K-stages per CTA (amortise the reds)
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.splits = splits;
   OTM_REQUIRE((long long)a->dy.n * splits <= 65535, "wgrad_tc: grid.z too large");
-  static const int dbg = [] { const char* e = getenv("OTM_WG_DEBUG"); return e ? atoi(e) : 0; }();
-  p.debug = dbg;
-
-  static const int variant = [] { const char* e = getenv("OTM_TC_VARIANT"); return e ? atoi(e) : 0; }();
-  // OTM_WG_RR=1 selects the row-reuse wgrad kernel.  Measured (tools/bench_wgrad.py, B200): 959 vs
-  // 928 TFLOP/s at n=96 128->128, but 656 vs 733 at n=64 and 689-706 vs 799-896 on the 64-wide
-  // layers (1 CTA/SM: coarser waves, epilogue not overlapped); with the reduction skipped both
-  // kernels run at 1.0-1.1 PFLOP/s = the shared-memory operand bandwidth of a 128x128 MMA, so
-  // L2 re-fetches were not the limiter.  Default: the per-tap kernel.
-  static const int wg_rr = [] { const char* e = getenv("OTM_WG_RR"); return e ? atoi(e) : 0; }();
   p.ws = a->ws;
   p.wfwd = (const __nv_bfloat16*)a->wfwd;
+  p.wfwd_n_stride = a->wfwd_batch_stride;
   p.P = a->P;
   if (p.P) OTM_REQUIRE(!p.a_is_x && p.wfwd, "conv_wgrad: fused P needs Cout %% 128 == 0 and wfwd");
   CUtensorMap tmX, tmDy;
-  int rc;
-  if (wg_rr && variant == 0 && a->kh == a->kw && (a->kh == 3 || a->kh == 4)) {
-    // row-reuse kernel: one CTA per (filter column, 128 x BN block, sample, K split), 1 CTA/SM
-    const int KS = a->kh;
-    const int bn = (N % 128 == 0) ? 128 : 64;
-    p.n_tiles_n = N / bn;
-    const long long base_rr = (long long)KS * m_tiles * p.n_tiles_n * a->dy.n;
-    // K splits: minimise waves x (main loop + epilogue) in units of one MMA-stage
-    const double t_stage = KS * 4.0, t_epi = KS * (bn / 16) * 1.2 + 6.0;
-    int best = 1;
-    double best_cost = 1e30;
-    const int smax = p.tiles_total < 64 ? (p.tiles_total + 7) / 8 : 8;
-    for (int sp = 1; sp <= smax; ++sp) {
-      if ((long long)a->dy.n * sp > 65535) break;
-      const double waves = (double)((base_rr * sp + num_sms() - 1) / num_sms());
-      const double cost = waves * (((p.tiles_total + sp - 1) / sp) * t_stage + t_epi);
-      if (cost < best_cost) { best_cost = cost; best = sp; }
-    }
-    p.splits = best;
-    rc = make_act_map(&tmX, a->x, a->x_halo, 8, 8 + KS - 1);
-    if (rc) return rc;
-    rc = make_act_map(&tmDy, a->dy, 0, 8, 8);
-    if (rc) return rc;
-    dim3 grid_rr(KS, m_tiles * p.n_tiles_n, a->dy.n * p.splits);
-    if (p.ws) OTM_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, sizeof(float) * (size_t)taps * cin * cout, st));
-    if (bn == 128) {
-      rc = KS == 3 ? launch_wgrad_rr<2, 2, 3, 5>(tmX, tmDy, p, grid_rr, st)
-                   : launch_wgrad_rr<2, 2, 4, 5>(tmX, tmDy, p, grid_rr, st);
-    } else if (p.a_is_x) {
-      rc = KS == 3 ? launch_wgrad_rr<2, 1, 3, 6>(tmX, tmDy, p, grid_rr, st)
-                   : launch_wgrad_rr<2, 1, 4, 6>(tmX, tmDy, p, grid_rr, st);
-    } else {
-      rc = KS == 3 ? launch_wgrad_rr<1, 2, 3, 6>(tmX, tmDy, p, grid_rr, st)
-                   : launch_wgrad_rr<1, 2, 4, 6>(tmX, tmDy, p, grid_rr, st);
-    }
-    if (rc) return rc;
-    if (p.ws) {
-      const long long total = (long long)taps * cin * cout;
-      int blocks = (int)((total + 255) / 256);
-      if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-      wgrad_fold_kernel<<<blocks, 256, 0, st>>>(p.ws, p.dw, cout, cin, taps, p.a_is_x);
-      OTM_LAUNCH_CHECK();
-    }
-    return OTM_OK;
-  }
-  rc = make_act_map(&tmX, a->x, a->x_halo, 8, 8);
+  int rc = make_act_map(&tmX, a->x, a->x_halo, 8, 8);
   if (rc) return rc;
   rc = make_act_map(&tmDy, a->dy, 0, 8, 8);
   if (rc) return rc;
   const CUtensorMap& tmA = p.a_is_x ? tmX : tmDy;
   const CUtensorMap& tmB = p.a_is_x ? tmDy : tmX;
-  dim3 grid(taps, m_tiles * p.n_tiles_n, a->dy.n * splits);
+  dim3 grid(tap_ctas, m_tiles * p.n_tiles_n, a->dy.n * splits);
   if (p.ws) OTM_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, sizeof(float) * (size_t)taps * cin * cout, st));
-  if (variant == 1) {
-    if (BN == 64) rc = launch_wgrad<64, 6, 1>(tmA, tmB, p, grid, st);
-    else if (BN == 128) rc = launch_wgrad<128, 6, 1>(tmA, tmB, p, grid, st);
-    else rc = launch_wgrad<256, 4, 1>(tmA, tmB, p, grid, st);
+  if (BN == 64) {
+    if (tpc == 4) rc = launch_wgrad<64, 2, 2, 4>(tmA, tmB, p, grid, st);
+    else if (tpc == 2) rc = launch_wgrad<64, 3, 2, 2>(tmA, tmB, p, grid, st);
+    else rc = launch_wgrad<64, 4, 2, 1>(tmA, tmB, p, grid, st);
+  } else if (BN == 128) {
+    if (tpc >= 2) rc = launch_wgrad<128, 2, 2, 2>(tmA, tmB, p, grid, st);
+    else rc = launch_wgrad<128, 3, 2, 1>(tmA, tmB, p, grid, st);
   } else {
-    if (BN == 64) rc = launch_wgrad<64, 4, 2>(tmA, tmB, p, grid, st);
-    else if (BN == 128) rc = launch_wgrad<128, 3, 2>(tmA, tmB, p, grid, st);
-    else rc = launch_wgrad<256, 2, 2>(tmA, tmB, p, grid, st);
+    rc = launch_wgrad<256, 2, 2, 1>(tmA, tmB, p, grid, st);
   }
   if (rc) return rc;
   if (p.ws) {

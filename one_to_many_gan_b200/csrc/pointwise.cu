@@ -627,9 +627,14 @@ struct UpF {
   __device__ void prefetch(int, int, int, int) const {}
   View x, y;
   int halo;
-  struct State {};
-  __device__ void prepare(int, int, State&) const {}
-  __device__ void operator()(int n, int ho, int wo, int c, const State&) const {
+  const float* scale;  // [n, C] or NULL
+  int C;
+  struct State { float sc[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) st.sc[i] = scale ? scale[(long long)n * C + c + i] : 1.f;
+  }
+  __device__ void operator()(int n, int ho, int wo, int c, const State& st) const {
     int ph[4], pw[4];
     float wh[4], ww[4];
     up_taps(ho, x.h, ph, wh);
@@ -650,6 +655,8 @@ struct UpF {
         for (int i = 0; i < V; ++i) acc[i] += wgt * v[i];
       }
     }
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] *= st.sc[i];
     store_halo<T, V>(y, halo, n, ho, wo, c, acc);
   }
 };
@@ -659,9 +666,14 @@ struct UpBwdF {
   __device__ void prefetch(int, int, int, int) const {}
   View g, gx;
   int g_halo;
-  struct State {};
-  __device__ void prepare(int, int, State&) const {}
-  __device__ void operator()(int n, int h, int w, int c, const State&) const {
+  const float* scale;  // [n, C] or NULL
+  int C;
+  struct State { float sc[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) st.sc[i] = scale ? scale[(long long)n * C + c + i] : 1.f;
+  }
+  __device__ void operator()(int n, int h, int w, int c, const State& st) const {
     int jh[10], jw[10];
     float wh[10], ww[10];
     int nh = up_bwd_taps<10>(h, gx.h, jh, wh);
@@ -677,6 +689,8 @@ struct UpBwdF {
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] += wgt * v[i];
       }
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] *= st.sc[i];
     store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), acc);
   }
 };
@@ -819,8 +833,18 @@ struct Up2x2F {
   __device__ void prefetch(int, int, int, int) const {}
   View x, y;
   int halo;
-  struct State {};
-  __device__ void prepare(int, int, State&) const {}
+  const float* scale;  // [n, C] or NULL
+  int C;
+  struct State { float sc[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) st.sc[i] = scale ? scale[(long long)n * C + c + i] : 1.f;
+  }
+  __device__ void put(int n, int h, int w, int c, float (&o)[V], const State& st) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) o[i] *= st.sc[i];
+    store_halo<T, V>(y, halo, n, h, w, c, o);
+  }
   __device__ void operator()(int n, int h, int w, int c, const State& st) const {
     if (h >= 1 && h < x.h - 1 && w >= 1 && w < x.w - 1) {
       float he[3][V], ho[3][V];
@@ -839,21 +863,20 @@ struct Up2x2F {
       float o[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = 0.3125f * he[0][i] + 0.625f * he[1][i] + 0.0625f * he[2][i];
-      store_halo<T, V>(y, halo, n, 2 * h, 2 * w, c, o);
+      put(n, 2 * h, 2 * w, c, o, st);
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = 0.3125f * ho[0][i] + 0.625f * ho[1][i] + 0.0625f * ho[2][i];
-      store_halo<T, V>(y, halo, n, 2 * h, 2 * w + 1, c, o);
+      put(n, 2 * h, 2 * w + 1, c, o, st);
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = 0.0625f * he[0][i] + 0.625f * he[1][i] + 0.3125f * he[2][i];
-      store_halo<T, V>(y, halo, n, 2 * h + 1, 2 * w, c, o);
+      put(n, 2 * h + 1, 2 * w, c, o, st);
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = 0.0625f * ho[0][i] + 0.625f * ho[1][i] + 0.3125f * ho[2][i];
-      store_halo<T, V>(y, halo, n, 2 * h + 1, 2 * w + 1, c, o);
+      put(n, 2 * h + 1, 2 * w + 1, c, o, st);
       return;
     }
     // border block: same separable 3x3 -> 2x2 scheme with per-axis weights from the general
     // tap generator (window clamped into the image)
-    (void)st;
     const int hs = min(max(h - 1, 0), x.h - 3), ws = min(max(w - 1, 0), x.w - 3);
     float wr[2][3], wc[2][3];
 #pragma unroll
@@ -897,7 +920,7 @@ struct Up2x2F {
 #pragma unroll
         for (int i = 0; i < V; ++i)
           o[i] = wr[a][0] * hv[q][0][i] + wr[a][1] * hv[q][1][i] + wr[a][2] * hv[q][2][i];
-        store_halo<T, V>(y, halo, n, 2 * h + a, 2 * w + q, c, o);
+        put(n, 2 * h + a, 2 * w + q, c, o, st);
       }
   }
 };
@@ -907,8 +930,18 @@ struct UpBwd2x2F {
   static constexpr int OCC = 2;
   __device__ void prefetch(int, int, int, int) const {}
   View g, gx;  // g: [n, 2H, 2W, c] output gradient (g_halo == 0 only), gx: [n, H, W, c]
-  struct State {};
-  __device__ void prepare(int, int, State&) const {}
+  const float* scale;  // [n, C] or NULL
+  int C;
+  struct State { float sc[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) st.sc[i] = scale ? scale[(long long)n * C + c + i] : 1.f;
+  }
+  __device__ void put(int n, int h, int w, int c, float (&o)[V], const State& st) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) o[i] *= st.sc[i];
+    store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), o);
+  }
   // (h2, w2) index 2x2 blocks of gx
   __device__ void operator()(int n, int h2, int w2, int c, const State& st) const {
     const int h = 2 * h2, w = 2 * w2;
@@ -946,13 +979,12 @@ struct UpBwd2x2F {
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) store_vec<T, V>(vptr_mut<T>(gx, n, h + a, w + b, c), acc[a][b]);
+        for (int b = 0; b < 2; ++b) put(n, h + a, w + b, c, acc[a][b], st);
       return;
     }
     // border block: the same 8x8 -> 2x2 separable scheme with per-axis weights derived from
     // the forward tap generator (window clamped into the image; an odd trailing row/column of gx
     // gets zero weights and is not stored)
-    (void)st;
     const int hs = min(max(2 * h - 2, 0), g.h - 8), ws = min(max(2 * w - 2, 0), g.w - 8);
     float wr[2][8], wc[2][8];
 #pragma unroll
@@ -1005,7 +1037,7 @@ struct UpBwd2x2F {
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b)
-        if (h + a < gx.h && w + b < gx.w) store_vec<T, V>(vptr_mut<T>(gx, n, h + a, w + b, c), acc[a][b]);
+        if (h + a < gx.h && w + b < gx.w) put(n, h + a, w + b, c, acc[a][b], st);
   }
 };
 
@@ -1023,9 +1055,13 @@ struct ModOutF {
   static constexpr int NQ = 1;
   View g, g2, out, res, gy;
   int g_halo, act, C;
-  struct State {};
-  __device__ void prepare(int, int, State&) const {}
-  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V], const State&) const {
+  const float* gys;  // [n, C] scale of the STORED gy (NULL = 1)
+  struct State { float gs[V]; };
+  __device__ void prepare(int n, int c, State& st) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) st.gs[i] = gys ? gys[(long long)n * C + c + i] : 1.f;
+  }
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V], const State& st) const {
     float ga[V], o[V];
     load_fold<T, V>(g, g_halo, n, h, w, c, ga);
     if (g2.ptr) {
@@ -1046,7 +1082,7 @@ struct ModOutF {
       for (int i = 0; i < V; ++i) o[i] -= r[i];
     }
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[0][i] += ga[i] * o[i];
+    for (int i = 0; i < V; ++i) { acc[0][i] += ga[i] * o[i]; ga[i] *= st.gs[i]; }
     if (gy.ptr) store_vec<T, V>(vptr_mut<T>(gy, n, h, w, c), ga);
   }
   __device__ int out_index(int n, int c, int) const { return n * C + c; }
@@ -1063,10 +1099,14 @@ struct ModInF {
   View g, x, gadd, gx;
   const float* s;
   int g_halo, C, relu_mask;
-  struct State { float s[V]; };
+  const float* gxs;  // [n, C] scale of the stored gx (NULL = 1)
+  struct State { float s[V], gs[V]; };
   __device__ void prepare(int n, int c, State& st) const {
 #pragma unroll
-    for (int i = 0; i < V; ++i) st.s[i] = s[(long long)n * C + c + i];
+    for (int i = 0; i < V; ++i) {
+      st.s[i] = s[(long long)n * C + c + i];
+      st.gs[i] = gxs ? gxs[(long long)n * C + c + i] : 1.f;
+    }
   }
   __device__ void operator()(int n, int h, int w, int c, float (&acc)[1][V], const State& st) const {
     float gt[V], xv[V];
@@ -1083,10 +1123,13 @@ struct ModInF {
 #pragma unroll
       for (int i = 0; i < V; ++i) gt[i] += t[i];
     }
+    if (!gx.ptr) return;
     if (relu_mask) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) gt[i] = xv[i] > 0.f ? gt[i] : 0.f;
+      for (int i = 0; i < V; ++i) gt[i] = xv[i] != 0.f ? gt[i] : 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < V; ++i) gt[i] *= st.gs[i];
     store_vec<T, V>(vptr_mut<T>(gx, n, h, w, c), gt);
   }
   __device__ int out_index(int n, int c, int) const { return n * C + c; }
@@ -1420,10 +1463,13 @@ struct ModInRowOp {
       acc[0][e] += gt[e] * xv[e];
       gt[e] = fmaf(gt[e], st.s[e], ga[e]);
     }
+    if (!f.gx.ptr) return;
     if (f.relu_mask) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) gt[e] = xv[e] > 0.f ? gt[e] : 0.f;
+      for (int e = 0; e < 8; ++e) gt[e] = xv[e] != 0.f ? gt[e] : 0.f;
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gt[e] *= st.gs[e];
     store_vec<T, 8>(vptr_mut<T>(f.gx, n, h, w, c), gt);
   }
 };
@@ -2183,7 +2229,8 @@ int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_
   return rc;
 }
 
-int otm_up(const otm_tensor* x, const otm_tensor* y, int32_t y_halo, otm_stream stream) {
+int otm_up(const otm_tensor* x, const otm_tensor* y, int32_t y_halo, const float* scale,
+           otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OTM_REQUIRE(x && y && x->ptr && y->ptr, "up: null tensor");
   OTM_REQUIRE(y->h == 2 * x->h && y->w == 2 * x->w && y->n == x->n && y->c == x->c,
@@ -2191,20 +2238,20 @@ int otm_up(const otm_tensor* x, const otm_tensor* y, int32_t y_halo, otm_stream 
   OTM_REQUIRE(x->dtype == y->dtype, "up: dtype mismatch");
   bool vok = vec_ok(*x, 8) && vec_ok(*y, 8);
   int rc = OTM_OK;
-  static const int blk = [] { const char* e = getenv("OTM_UP_BLOCK"); return e ? atoi(e) : 1; }();
   OTM_DISPATCH_TV(x->dtype, vok, {
-    if (blk && V == 8 && x->h >= 4 && x->w >= 4) {
-      Up2x2F<T, V> f{make_view(*x), make_view(*y), y_halo};
+    if (V == 8 && x->h >= 4 && x->w >= 4) {
+      Up2x2F<T, V> f{make_view(*x), make_view(*y), y_halo, scale, x->c};
       rc = launch_ew<V>(f, x->n, x->h, x->w, x->c, st);
     } else {
-      UpF<T, V> f{make_view(*x), make_view(*y), y_halo};
+      UpF<T, V> f{make_view(*x), make_view(*y), y_halo, scale, x->c};
       rc = launch_ew<V>(f, y->n, y->h, y->w, y->c, st);
     }
   });
   return rc;
 }
 
-int otm_up_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* gx, otm_stream stream) {
+int otm_up_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* gx, const float* scale,
+               otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OTM_REQUIRE(g && gx && g->ptr && gx->ptr, "up_bwd: null tensor");
   OTM_REQUIRE(g->h == 2 * gx->h && g->w == 2 * gx->w && g->n == gx->n && g->c == gx->c,
@@ -2212,13 +2259,12 @@ int otm_up_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* gx, otm_st
   OTM_REQUIRE(g->dtype == gx->dtype, "up_bwd: dtype mismatch");
   bool vok = vec_ok(*g, 8) && vec_ok(*gx, 8);
   int rc = OTM_OK;
-  static const int blk = [] { const char* e = getenv("OTM_UP_BLOCK"); return e ? atoi(e) : 1; }();
   OTM_DISPATCH_TV(g->dtype, vok, {
-    if (blk && V == 8 && g_halo == 0 && gx->h >= 8 && gx->w >= 8) {
-      UpBwd2x2F<T, V> f{make_view(*g), make_view(*gx)};
+    if (V == 8 && g_halo == 0 && gx->h >= 8 && gx->w >= 8) {
+      UpBwd2x2F<T, V> f{make_view(*g), make_view(*gx), scale, gx->c};
       rc = launch_ew<V>(f, gx->n, (gx->h + 1) / 2, (gx->w + 1) / 2, gx->c, st);
     } else {
-      UpBwdF<T, V> f{make_view(*g), make_view(*gx), g_halo};
+      UpBwdF<T, V> f{make_view(*g), make_view(*gx), g_halo, scale, gx->c};
       rc = launch_ew<V>(f, gx->n, gx->h, gx->w, gx->c, st);
     }
   });
@@ -2241,7 +2287,7 @@ int otm_mod_out(const otm_mod_out_args* a, otm_stream stream) {
                     make_view(a->out),
                     a->res.ptr ? make_view(a->res) : null_view(),
                     a->gy.ptr ? make_view(a->gy) : null_view(),
-                    a->g_halo, a->act, C};
+                    a->g_halo, a->act, C, a->gy_scale};
     rc = launch_nc_reduce<V>(f, a->out.n, a->out.h, a->out.w, C, a->P, st);
   });
   return rc;
@@ -2249,8 +2295,8 @@ int otm_mod_out(const otm_mod_out_args* a, otm_stream stream) {
 
 int otm_mod_in(const otm_mod_in_args* a, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  OTM_REQUIRE(a && a->g.ptr && a->x.ptr && a->gx.ptr && a->Q && a->s, "mod_in: null argument");
-  OTM_REQUIRE(same_shape(a->g, a->x) && same_shape(a->gx, a->x), "mod_in: shape mismatch");
+  OTM_REQUIRE(a && a->g.ptr && a->x.ptr && a->Q && a->s, "mod_in: null argument");
+  OTM_REQUIRE(same_shape(a->g, a->x) && (!a->gx.ptr || same_shape(a->gx, a->x)), "mod_in: shape mismatch");
   const int C = a->x.c;
   OTM_CHECK_CUDA(cudaMemsetAsync(a->Q, 0, sizeof(float) * a->x.n * C, st));
   bool vok = vec_ok(a->g, 8) && vec_ok(a->x, 8) && vec_ok(a->gadd, 8) && vec_ok(a->gx, 8);
@@ -2262,28 +2308,29 @@ int otm_mod_in(const otm_mod_in_args* a, otm_stream stream) {
       if (a->x.dtype == OTM_BF16) {
         ModInRowOp<__nv_bfloat16> op{ModInF<__nv_bfloat16, 8>{
             make_view(a->g), make_view(a->x), a->gadd.ptr ? make_view(a->gadd) : null_view(),
-            make_view(a->gx), a->s, a->g_halo, C, a->relu_mask}};
+            a->gx.ptr ? make_view(a->gx) : null_view(), a->s, a->g_halo, C, a->relu_mask, a->gx_scale}};
         return launch_row_stream<__nv_bfloat16>(op, a->x.n, a->x.h, a->x.w, C, stages, smem, a->Q, st);
       }
       ModInRowOp<float> op{ModInF<float, 8>{
           make_view(a->g), make_view(a->x), a->gadd.ptr ? make_view(a->gadd) : null_view(),
-          make_view(a->gx), a->s, a->g_halo, C, a->relu_mask}};
+          a->gx.ptr ? make_view(a->gx) : null_view(), a->s, a->g_halo, C, a->relu_mask, a->gx_scale}};
       return launch_row_stream<float>(op, a->x.n, a->x.h, a->x.w, C, stages, smem, a->Q, st);
     }
   }
   OTM_DISPATCH_TV(a->x.dtype, vok, {
     ModInF<T, V> f{make_view(a->g), make_view(a->x),
-                   a->gadd.ptr ? make_view(a->gadd) : null_view(), make_view(a->gx),
-                   a->s, a->g_halo, C, a->relu_mask};
+                   a->gadd.ptr ? make_view(a->gadd) : null_view(),
+                   a->gx.ptr ? make_view(a->gx) : null_view(), a->s, a->g_halo, C, a->relu_mask,
+                   a->gx_scale};
     rc = launch_nc_reduce<V>(f, a->x.n, a->x.h, a->x.w, C, a->Q, st);
   });
   return rc;
 }
 
-int otm_channel_sum(const otm_tensor* g, float* out, otm_stream stream) {
+int otm_channel_sum(const otm_tensor* g, float* out, int32_t accumulate, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OTM_REQUIRE(g && g->ptr && out, "channel_sum: null argument");
-  OTM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * g->c, st));
+  if (!accumulate) OTM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * g->c, st));
   bool vok = vec_ok(*g, 8);
   int rc = OTM_OK;
   {

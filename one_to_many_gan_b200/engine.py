@@ -18,6 +18,7 @@ identical): style mixing is a `where(block < crossover, s1, s2)` instead of expa
 from __future__ import annotations
 
 import gc
+import os
 import random
 
 import torch
@@ -112,6 +113,11 @@ class TrainIteration:
         self.losses_host = torch.zeros(len(self.LOSS_NAMES), dtype=torch.float32).pin_memory()
         self.inject_h = False
         self.use_graph = use_graph
+        # "full": the whole iteration (NCCL included) is ONE graph and the gradient exchange
+        # overlaps compute; "segmented": three graphs with blocking NCCL between them
+        self.mode = "segmented" if os.environ.get("OTM_DDP_CAPTURE", "1") == "0" else "full"
+        self.g_dec_start = opt_g.offset_of(next(generator.decoder.parameters()))
+        self.on_decoder_grads_final = None  # test hook
         self.graph = None
         self._warm_left = warmup
         self.iterations = 0
@@ -147,31 +153,41 @@ class TrainIteration:
         self._draw_style(1)              # G step: translation w
         tbase = self.theta_base
         self.rng_host[tbase : tbase + BK] = torch.rand(BK)  # theta
+        if isinstance(h, str):  # "host": drawn HERE from the host generator, exactly where a CPU run
+            lo, hi = self.cfg["optimisation"]["path_loss_jacobian_granularity"]  # of the reference
+            h = torch.ones(BK).uniform_(lo, hi)                                  # draws it (:216-223)
         if h is not None:
             self.rng_host[tbase + BK : tbase + 2 * BK] = h.float().cpu()
         self._draw_style(2)              # G step: get_two_w
 
     # ---------------------------------------------------------------- device part
-    def _style(self, slot: int):
+    def _style(self, slot: int, d=(None, None), n_out: int = 1):
+        """get_single_w(d=1) / get_two_w (reference builder.py:51-132) as ONE launch: mapping
+        network on both host-drawn z, style mixing at the host-drawn crossover, lerp(0, s, d)."""
         B, wd, nb = self.style_batch[slot], self.wd, self.nb
         base = self.style_base[slot]
         z1 = self.rng_dev[base : base + B * wd].view(B, wd)
         z2 = self.rng_dev[base + B * wd : base + 2 * B * wd].view(B, wd)
-        s1, s2 = self.M(z1), self.M(z2)
-        first = (torch.arange(nb, device=self.dev) < self.idx_dev[slot]).view(nb, 1, 1)
-        return torch.where(first, s1[None], s2[None])
+        return ops.mapping(self.M.linears(), z1, z2, self.idx_dev[slot : slot + 1], n_blocks=nb, d=d,
+                           n_out=n_out)
 
-    # The iteration is three device segments with the two data-parallel exchanges between them
-    # (NCCL calls stay outside the captured graphs):
-    #   A: D forward/backward            -> all-reduce(D grads)
-    #   B: Adam(D), G forward/backward   -> all-reduce(G, M, S grads)
-    #   C: Adam(G), Adam(M), Adam(S)
-    def _segment_a(self):
+    # The device part of one iteration, in stream order (data-parallel exchanges marked *):
+    #   D forward / backward
+    #   * all-reduce(D grads) launched asynchronously ...
+    #   G step forward up to the generated images (encode, style extractor, 3B decode, L1 terms)
+    #   ... waited for here: Adam(D) runs right before the G step first uses the discriminator
+    #   rest of the G step forward, then backward; when autograd reaches the encoder (hook on
+    #   the latents) every decoder / style-extractor gradient is final:
+    #   * all-reduce(G decoder slice, S) launched asynchronously under the encoder backward
+    #   * all-reduce(G encoder slice, M) after backward; wait; Adam(G), Adam(M), Adam(S)
+    # NCCL collectives are capture-safe, so the WHOLE iteration is one CUDA graph (mode "full");
+    # mode "segmented" keeps NCCL outside three captured segments (OTM_DDP_CAPTURE=0).
+    def _d_step_and_zero(self):
         B = self.B
         ops.invalidate_packs()
         self.oD.zero_grad()
         with torch.no_grad():
-            w = self._style(0)
+            (w,) = self._style(0)
             generated = self.G(self.x[0], w)
             o = 3
             sources = torch.cat([self.pool, generated], dim=0)
@@ -184,17 +200,30 @@ class TrainIteration:
         self.losses[0:3].copy_(torch.cat([v.detach().reshape(1).float()
                                           for v in (disc_loss, sign_real, sign_fake)]))
 
-    def _segment_b(self):
+    def _update_d(self):
+        """Adam(D): the reference runs it at the end of the D step (training.py:123); nothing
+        before the G step's discriminator forward reads D, so it is deferred to there and D's
+        all-reduce hides behind the G step's encode / decode."""
+        self.oD.wait_all_reduce()
+        self.oD.step(reduced=True)
+
+    def _decoder_grads_final(self):
+        """Autograd is about to run the encoder backward: decoder, to_style and style-extractor
+        gradients are complete (verified by test_engine_gpu.test_bucket_gradients_are_final)."""
+        self.oG.all_reduce_async(self.g_dec_start, self.oG.numel)
+        self.oS.all_reduce_async()
+        if self.on_decoder_grads_final is not None:
+            self.on_decoder_grads_final()
+
+    def _g_step(self, update_d, overlap: bool = True):
         cfg, B = self.cfg, self.B
         opt = cfg["optimisation"]
-        ops.invalidate_packs()
-        self.oD.step(reduced=True)
         self.oG.zero_grad()
         self.oM.zero_grad()
         self.oS.zero_grad()
         zero = self.M.shoeprint_style_vector
         reconstruct_w = zero.expand(self.nb, B, self.wd)
-        translation_w = self._style(1)
+        (translation_w,) = self._style(1)
         BK = B * self.K
         tbase = self.theta_base
         theta = self.rng_dev[tbase : tbase + BK]
@@ -208,14 +237,36 @@ class TrainIteration:
             h = torch.empty(BK, device=self.dev).uniform_(lo, hi)
         d1 = (theta + h / 2).clamp(0, 1)
         d2 = (theta - h / 2).clamp(0, 1)
-        s = self._style(2)
-        w1 = torch.lerp(zero, s, d1.view(1, -1, 1))  # builder.py:66-71
-        w2 = torch.lerp(zero, s, d2.view(1, -1, 1))
+        w1, w2 = self._style(2, d=(d1, d2), n_out=2)  # builder.py:66-71
         losses = training.generator_losses(cfg, self.G, self.D, self.S, self.x[2], self.x[3],
                                            reconstruct_w, translation_w, w1, w2, h,
-                                           latent_noise=latent_noise)
+                                           latent_noise=latent_noise, before_discriminator=update_d,
+                                           on_latent_grad=self._decoder_grads_final if overlap else None)
         training.backward_unit(losses[0])
         self.losses[3:].copy_(torch.cat([v.detach().reshape(1).float() for v in losses]))
+
+    def _update_gms(self):
+        for o in (self.oG, self.oM, self.oS):
+            o.wait_all_reduce()  # issues the buckets not launched yet (G encoder slice, M)
+        self.oG.step(reduced=True)
+        self.oM.step(reduced=True)
+        self.oS.step(reduced=True)
+        ops.invalidate_packs()
+
+    def _iteration(self):
+        self._d_step_and_zero()
+        self.oD.all_reduce_async()
+        self._g_step(self._update_d)
+        self._update_gms()
+
+    # mode "segmented": NCCL between three captured segments, no overlap
+    def _segment_a(self):
+        self._d_step_and_zero()
+
+    def _segment_b(self):
+        ops.invalidate_packs()
+        self.oD.step(reduced=True)
+        self._g_step(None, overlap=False)
 
     def _segment_c(self):
         self.oG.step(reduced=True)
@@ -243,15 +294,39 @@ class TrainIteration:
         self.pool_index.count = len(images)
 
     # ---------------------------------------------------------------- driver
+    def _capture(self, parts):
+        torch.cuda.synchronize()
+        graphs = []
+        pool = torch.cuda.graph_pool_handle()
+        # no cyclic GC while a stream is capturing: collecting some OTHER dead graph or tensor
+        # would cudaFree inside the capture and invalidate it
+        gc_was_on = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        try:
+            for part in parts:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    part()
+                graphs.append(g)
+        finally:
+            if gc_was_on:
+                gc.enable()
+        self.graph = graphs
+
     def load_inputs(self, d_prints, d_marks, g_prints, g_marks):
         """Copy the four batches of this iteration into the static input buffers (device
         tensors: device-to-device; pinned host tensors: asynchronous H2D)."""
         for i, t in enumerate((d_prints, d_marks, g_prints, g_marks)):
             self.x[i].copy_(t, non_blocking=True)
 
-    def run(self, *, h: torch.Tensor | None = None, sync_losses: bool = True):
+    def run(self, *, h: torch.Tensor | str | None = None, sync_losses: bool = True):
         """Run one iteration on the batches last given to load_inputs().  Returns the ten
-        logged scalars as floats (one device->host copy) or None if sync_losses is False."""
+        logged scalars as floats (one device->host copy) or None if sync_losses is False.
+        h: the finite-difference steps of the path-length loss -- None: drawn on the device
+        generator like the reference's GPU run; "host": drawn on the host generator at the
+        reference's position in the draw order (its CPU run; makes a run reproducible from the
+        host RNG state alone); a tensor: injected (parity tests)."""
         if (h is not None) != self.inject_h:
             if self.graph is not None:
                 raise RuntimeError("cannot switch h injection after the graph was captured")
@@ -266,36 +341,26 @@ class TrainIteration:
         if self._staged[slot] is None:
             self._staged[slot] = torch.cuda.Event()
         self._staged[slot].record()
-        segs = (self._segment_a, self._segment_b, self._segment_c)
-        exch = ((self.oD,), (self.oG, self.oM, self.oS), ())
-        if not self.use_graph or self._warm_left > 0:
-            # eager (also the warm-up: lazy inits, allocator pools, cuBLAS handles, NCCL comms)
-            self._warm_left = max(0, self._warm_left - 1)
-            for seg, ex in zip(segs, exch):
-                seg()
-                self._exchange(ex)
-        else:
-            if self.graph is None:
-                torch.cuda.synchronize()
-                self.graph = []
-                pool = torch.cuda.graph_pool_handle()
-                # no cyclic GC while a stream is capturing: collecting some OTHER dead graph or
-                # tensor would cudaFree inside the capture and invalidate it
-                gc_was_on = gc.isenabled()
-                gc.collect()
-                gc.disable()
-                try:
-                    for seg, ex in zip(segs, exch):
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, pool=pool):
-                            seg()
-                        self.graph.append(g)
-                        g.replay()
-                        self._exchange(ex)
-                finally:
-                    if gc_was_on:
-                        gc.enable()
+        if self.mode == "full":
+            if not self.use_graph or self._warm_left > 0:
+                # eager (also the warm-up: lazy inits, allocator pools, NCCL communicators)
+                self._warm_left = max(0, self._warm_left - 1)
+                self._iteration()
             else:
+                if self.graph is None:
+                    self._capture([self._iteration])
+                self.graph[0].replay()
+        else:
+            segs = (self._segment_a, self._segment_b, self._segment_c)
+            exch = ((self.oD,), (self.oG, self.oM, self.oS), ())
+            if not self.use_graph or self._warm_left > 0:
+                self._warm_left = max(0, self._warm_left - 1)
+                for seg, ex in zip(segs, exch):
+                    seg()
+                    self._exchange(ex)
+            else:
+                if self.graph is None:
+                    self._capture(segs)
                 for g, ex in zip(self.graph, exch):
                     g.replay()
                     self._exchange(ex)

@@ -37,7 +37,7 @@ def padded_view(t: torch.Tensor, halo: int) -> torch.Tensor:
 
 def conv_fwd(x, wpack, cout, kh, kw, pad, *, x_halo=0, y_halo=0, alpha=1.0, row_scale=None,
              bias=None, act=ACT_NONE, residual=None, out_dtype=None, per_sample=False,
-             path=PATH_AUTO, out=None):
+             path=PATH_AUTO, out=None, post_scale=None):
     n, cin, h, w = x.shape
     ho, wo = h + 2 * pad - kh + 1, w + 2 * pad - kw + 1
     if out is None:
@@ -56,14 +56,16 @@ def conv_fwd(x, wpack, cout, kh, kw, pad, *, x_halo=0, y_halo=0, alpha=1.0, row_
     a.act = act
     a.residual = L.tdesc(residual)
     a.path = path
+    a.post_scale = L.ptr(post_scale)
     L.check(L.lib.otm_conv_fwd(_byref(a), L.stream_ptr()), "otm_conv_fwd")
     return out
 
 
 def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None, path=PATH_AUTO,
-               use_ws=True, wfwd=None, P=None):
-    """P (zeroed [n, Cout] fp32) + wfwd (per-sample forward pack): also accumulate the
-    demodulation term sum_hw dy*y in the epilogue (check wgrad_fuses_P first)."""
+               use_ws=True, wfwd=None, P=None, wfwd_per_sample=True):
+    """P (zeroed [n, Cout] fp32) + wfwd (forward pack: per-sample, or the shared one when x
+    already carries the modulation): also accumulate the demodulation term sum_hw dy*y in the
+    epilogue (check wgrad_fuses_P first)."""
     a = L.ConvWgradArgs()
     a.x = L.tdesc(x)
     a.x_halo = x_halo
@@ -80,6 +82,7 @@ def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None,
     a.ws = L.ptr(ws)
     a.wfwd = L.ptr(wfwd)
     a.P = L.ptr(P)
+    a.wfwd_batch_stride = dw.numel() if (wfwd is not None and wfwd_per_sample) else 0
     L.check(L.lib.otm_conv_wgrad(_byref(a), L.stream_ptr()), "otm_conv_wgrad")
     return dw
 
@@ -153,7 +156,7 @@ def demod(s, q, eps=1e-8):
     return out
 
 
-def mod_bwd(w, alpha, s, sigma_inv, q, P, Q, dw):
+def mod_bwd(w, alpha, s, sigma_inv, q, P, Q, dw, q_scaled=False):
     cout, cin, kh, kw = w.shape
     ds = torch.empty_like(s)
     a = L.ModBwdArgs()
@@ -164,6 +167,7 @@ def mod_bwd(w, alpha, s, sigma_inv, q, P, Q, dw):
     a.nb = s.shape[0]
     a.ds = L.ptr(ds)
     a.dw = L.ptr(dw)
+    a.q_scaled = int(q_scaled)
     L.check(L.lib.otm_mod_bwd(_byref(a), L.stream_ptr()), "otm_mod_bwd")
     return ds
 
@@ -239,23 +243,24 @@ def down_bwd(g, in_hw, g_halo=0):
     return ga
 
 
-def up(x, y_halo=0):
+def up(x, y_halo=0, scale=None):
+    """scale: [n, c] fp32 factor on the result (the consumer modconv's style scale)."""
     n, c, h, w = x.shape
     out = alloc(n, c, 2 * h, 2 * w, x.dtype, x.device, y_halo)
     dx, dy = L.tdesc(x), L.tdesc(out)
-    L.check(L.lib.otm_up(_byref(dx), _byref(dy), y_halo, L.stream_ptr()), "otm_up")
+    L.check(L.lib.otm_up(_byref(dx), _byref(dy), y_halo, L.ptr(scale), L.stream_ptr()), "otm_up")
     return out
 
 
-def up_bwd(g, g_halo=0):
+def up_bwd(g, g_halo=0, scale=None):
     n, c, h, w = g.shape
     gx = alloc(n, c, h // 2, w // 2, g.dtype, g.device)
     dg, dgx = L.tdesc(g), L.tdesc(gx)
-    L.check(L.lib.otm_up_bwd(_byref(dg), g_halo, _byref(dgx), L.stream_ptr()), "otm_up_bwd")
+    L.check(L.lib.otm_up_bwd(_byref(dg), g_halo, _byref(dgx), L.ptr(scale), L.stream_ptr()), "otm_up_bwd")
     return gx
 
 
-def mod_out(g, out, *, g_halo=0, g2=None, res=None, act=ACT_NONE, materialise=True):
+def mod_out(g, out, *, g_halo=0, g2=None, res=None, act=ACT_NONE, materialise=True, gy_scale=None):
     n, c, h, w = out.shape
     gy = alloc(n, c, h, w, out.dtype, out.device) if materialise else None
     P = torch.empty((n, c), dtype=torch.float32, device=out.device)
@@ -268,13 +273,15 @@ def mod_out(g, out, *, g_halo=0, g2=None, res=None, act=ACT_NONE, materialise=Tr
     a.act = act
     a.gy = L.tdesc(gy)
     a.P = L.ptr(P)
+    a.gy_scale = L.ptr(gy_scale)
     L.check(L.lib.otm_mod_out(_byref(a), L.stream_ptr()), "otm_mod_out")
     return gy, P
 
 
-def mod_in(g, x, s, *, g_halo=0, gadd=None, relu_mask=False):
+def mod_in(g, x, s, *, g_halo=0, gadd=None, relu_mask=False, gx_scale=None, want_gx=True):
+    """want_gx=False: only the reduction Q[n,c] = sum_hw fold(g) * x."""
     n, c, h, w = x.shape
-    gx = alloc(n, c, h, w, x.dtype, x.device)
+    gx = alloc(n, c, h, w, x.dtype, x.device) if want_gx else None
     Q = torch.empty((n, c), dtype=torch.float32, device=x.device)
     a = L.ModInArgs()
     a.g = L.tdesc(g)
@@ -285,14 +292,18 @@ def mod_in(g, x, s, *, g_halo=0, gadd=None, relu_mask=False):
     a.gx = L.tdesc(gx)
     a.Q = L.ptr(Q)
     a.relu_mask = int(relu_mask)
+    a.gx_scale = L.ptr(gx_scale)
     L.check(L.lib.otm_mod_in(_byref(a), L.stream_ptr()), "otm_mod_in")
     return gx, Q
 
 
-def channel_sum(g):
-    out = torch.empty((g.shape[1],), dtype=torch.float32, device=g.device)
+def channel_sum(g, out=None):
+    """out given: ACCUMULATE into it (a bias gradient view of the arena)."""
+    acc = out is not None
+    if out is None:
+        out = torch.empty((g.shape[1],), dtype=torch.float32, device=g.device)
     d = L.tdesc(g)
-    L.check(L.lib.otm_channel_sum(_byref(d), L.ptr(out), L.stream_ptr()), "otm_channel_sum")
+    L.check(L.lib.otm_channel_sum(_byref(d), L.ptr(out), int(acc), L.stream_ptr()), "otm_channel_sum")
     return out
 
 
@@ -359,6 +370,95 @@ def loss_path(f1, f2, h, weight, scale, out, want_grad=True, g1=None, g2=None):
     L.check(L.lib.otm_loss_path(_byref(d1), _byref(d2), L.ptr(h), weight, scale, L.ptr(out),
                                 _byref(dg1), _byref(dg2), L.stream_ptr()), "otm_loss_path")
     return g1, g2
+
+
+def _rows(t):
+    """(pointer, row stride) of a [n, k] fp32 tensor whose last stride is 1 (n may be a stride-0
+    broadcast)."""
+    if t.dtype != torch.float32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"expected fp32 [n, k] rows, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+    return L.ptr(t), t.stride(0)
+
+
+def linear_jobs(specs):
+    """specs: dicts with x [n,k], w [o,k], bias|None, and y (forward) or dy + dw/dbias/dx
+    (backward).  Returns a ctypes array of otm_linear_job."""
+    arr = (L.LinearJob * len(specs))()
+    for j, sp in zip(arr, specs):
+        x, w = sp["x"], sp["w"]
+        j.x, j.x_row_stride = _rows(x)
+        j.w = L.ptr(w)
+        j.bias = L.ptr(sp.get("bias"))
+        j.y = L.ptr(sp.get("y"))
+        j.dy = L.ptr(sp.get("dy"))
+        j.dw = L.ptr(sp.get("dw"))
+        j.dbias = L.ptr(sp.get("dbias"))
+        dx = sp.get("dx")
+        if dx is not None:
+            j.dx, j.dx_row_stride = _rows(dx)
+        j.n, j.k, j.o = x.shape[0], x.shape[1], w.shape[0]
+    return arr
+
+
+def linear_fwd(specs):
+    for i in range(0, len(specs), L.MAX_LINEAR_JOBS):
+        chunk = specs[i : i + L.MAX_LINEAR_JOBS]
+        L.check(L.lib.otm_linear_fwd(linear_jobs(chunk), len(chunk), L.stream_ptr()), "otm_linear_fwd")
+
+
+def linear_bwd(specs):
+    for i in range(0, len(specs), L.MAX_LINEAR_JOBS):
+        chunk = specs[i : i + L.MAX_LINEAR_JOBS]
+        L.check(L.lib.otm_linear_bwd(linear_jobs(chunk), len(chunk), L.stream_ptr()), "otm_linear_bwd")
+
+
+def _mapping_args(z1, z2, cross, weights, biases, n_blocks, d, d_const):
+    a = L.MappingArgs()
+    feats = z1.shape[1]
+    if z1.dtype != torch.float32 or not z1.is_contiguous() or (z2 is not None and not z2.is_contiguous()):
+        raise ValueError("mapping: z must be contiguous fp32 [batch, features]")
+    a.z1, a.z2, a.cross = L.ptr(z1), L.ptr(z2), L.ptr(cross)
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        a.w[i], a.b[i] = L.ptr(w), L.ptr(b)
+    a.features, a.n_layers, a.batch, a.n_blocks = feats, len(weights), z1.shape[0], n_blocks
+    for j in range(2):
+        a.d[j] = L.ptr(d[j]) if d[j] is not None else None
+        a.d_const[j] = float(d_const[j])
+    return a
+
+
+def mapping_fwd(z1, z2, cross, weights, biases, n_blocks, d=(None, None), d_const=(1.0, 1.0),
+                n_out=1):
+    """-> list of n_out tensors [n_blocks, batch, features]."""
+    a = _mapping_args(z1, z2, cross, weights, biases, n_blocks, d, d_const)
+    outs = [torch.empty((n_blocks, z1.shape[0], z1.shape[1]), dtype=torch.float32, device=z1.device)
+            for _ in range(n_out)]
+    for j, o in enumerate(outs):
+        a.out[j] = L.ptr(o)
+    L.check(L.lib.otm_mapping_fwd(_byref(a), L.stream_ptr()), "otm_mapping_fwd")
+    return outs
+
+
+def mapping_bwd(z1, z2, cross, weights, biases, n_blocks, d, d_const, douts, dws, dbs):
+    """Accumulates the parameter gradients into dws / dbs."""
+    a = _mapping_args(z1, z2, cross, weights, biases, n_blocks, d, d_const)
+    for i, (dw, db) in enumerate(zip(dws, dbs)):
+        a.dw[i], a.db[i] = L.ptr(dw), L.ptr(db)
+    for j, g in enumerate(douts):
+        a.dout[j] = L.ptr(g) if g is not None else None
+    L.check(L.lib.otm_mapping_bwd(_byref(a), L.stream_ptr()), "otm_mapping_bwd")
+
+
+def loss_style_cycle(a, b, ratio=0.2, scale=1.0, want_grad=(True, True)):
+    """a, b: fp32 [batch, features] rows.  Returns (loss[1], da|None, db|None)."""
+    pa, sa = _rows(a)
+    pb, sb = _rows(b)
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    da = torch.empty(a.shape, dtype=torch.float32, device=a.device) if want_grad[0] else None
+    db = torch.empty(b.shape, dtype=torch.float32, device=a.device) if want_grad[1] else None
+    L.check(L.lib.otm_loss_style_cycle(pa, sa, pb, sb, a.shape[0], a.shape[1], ratio, scale, L.ptr(out),
+                                       L.ptr(da), L.ptr(db), L.stream_ptr()), "otm_loss_style_cycle")
+    return out, da, db
 
 
 def adam(param, grad, m, v, step_dev, lr, beta1, beta2, eps=1e-8, grad_scale=1.0):

@@ -10,7 +10,6 @@ from __future__ import annotations
 import math
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import ops
@@ -40,7 +39,9 @@ class EqualisedLinear(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_features) + bias)
 
     def forward(self, x: torch.Tensor):
-        return F.linear(x, self.weight(), bias=self.bias)
+        lead = x.shape[:-1]
+        y = ops.linear(x.reshape(-1, self.in_features), self)
+        return y.reshape(*lead, self.out_features)
 
     def extra_repr(self):
         return f"in_features={self.in_features}, out_features={self.out_features}"

@@ -24,15 +24,23 @@ ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = K.ACT_NONE, K.ACT_RELU, K.ACT_LRELU, K
 # ---------------------------------------------------------------------------
 # weight staging cache: packs are rebuilt when the parameter changes
 # ---------------------------------------------------------------------------
+# Entries are tagged with the optimiser that owns the weight (FlatAdam marks its parameters), so
+# an optimiser step drops ITS packs only: inside the captured iteration Adam(D) runs in the
+# middle of the generator step and must not throw away the generator's packs.
 _EPOCH = 0
 _PACKS: dict = {}
 
 
-def invalidate_packs() -> None:
-    """Called by the optimiser after it has updated the flat parameter arenas in place."""
+def invalidate_packs(owner=None) -> None:
+    """Called after weights changed in place (optimiser step, checkpoint load, graph replay).
+    owner: only the packs of parameters tagged `_otm_owner == owner`."""
     global _EPOCH
-    _EPOCH += 1
-    _PACKS.clear()
+    if owner is None:
+        _EPOCH += 1
+        _PACKS.clear()
+        return
+    for k in [k for k, v in _PACKS.items() if v[2] == owner]:
+        del _PACKS[k]
 
 
 def eq_scale(weight: torch.Tensor) -> float:
@@ -47,7 +55,7 @@ def _cached(key, weight: torch.Tensor, make):
     if hit is None:
         if len(_PACKS) > 512:
             _PACKS.clear()
-        hit = (make(), weight.detach())
+        hit = (make(), weight.detach(), getattr(weight, "_otm_owner", None))
         _PACKS[key] = hit
     return hit[0]
 
@@ -77,6 +85,15 @@ def _wgrad_buffer(weight: torch.Tensor):
     if DIRECT_WEIGHT_GRADS and g is not None and g.dtype == torch.float32 and g.is_contiguous():
         return g, None
     buf = torch.zeros_like(weight)
+    return buf, buf
+
+
+def _param_grad_buffer(p: torch.Tensor):
+    """Like _wgrad_buffer for any fp32 parameter (biases, to_style / mapping weights)."""
+    g = p.grad
+    if DIRECT_WEIGHT_GRADS and g is not None and g.dtype == torch.float32 and g.is_contiguous():
+        return g, None
+    buf = torch.zeros_like(p)
     return buf, buf
 
 
@@ -120,6 +137,7 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype):
+        ctx.bias = bias
         cout = weight.shape[0]
         wp = _pack(weight, x.dtype, False)
         y = K.conv_fwd(x, wp, cout, k, k, pad, x_halo=x_halo, y_halo=y_halo,
@@ -133,6 +151,7 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, weight, y = ctx.saved_tensors
+        bias = ctx.bias
         k, pad, x_halo, act = ctx.cfg
         cin = weight.shape[1]
         g = nhwc(g)
@@ -143,7 +162,8 @@ class ConvFn(torch.autograd.Function):
             buf, gw = _wgrad_buffer(weight)
             K.conv_wgrad(x, g, buf, k, k, pad, x_halo=x_halo, alpha=eq_scale(weight))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = K.channel_sum(g)
+            buf, gb = _param_grad_buffer(bias)
+            K.channel_sum(g, out=buf)
         if ctx.needs_input_grad[0]:
             wpt = _pack(weight, g.dtype, True)
             gxp = K.conv_fwd(g, wpt, cin, k, k, k - 1 - pad + x_halo, out_dtype=x.dtype)
@@ -344,48 +364,103 @@ def mod_conv(x, s, weight, *, act=ACT_RELU, y_halo=0, pad=1):
     return ModConvFn.apply(x, s, weight, act, y_halo, pad)
 
 
+class UpModConvFn(torch.autograd.Function):
+    """UpSample -> Conv2dWeightModulate(zero pad 1) -> activation (reference builder.py:190-197)
+    with SHARED conv weights: the up-sampling stencil writes x~ = s[b,i] * up(z) (it is per
+    channel, so the style scale commutes), the conv reads the one shared pack and applies
+    sigma_inv as its row scale.  Backward: the activation/P pass stores sigma_inv * gy, so dgrad
+    and wgrad are shared-weight too; Q is reduced against x~ and un-scaled in otm_mod_bwd."""
+
+    @staticmethod
+    def forward(ctx, z, s, weight, act, y_halo):
+        s = s.contiguous().float()
+        cout = weight.shape[0]
+        sig = K.demod(s, _sqsum(weight))
+        xt = K.up(z, scale=s)
+        y = K.conv_fwd(xt, _pack(weight, xt.dtype, False), cout, 3, 3, 1, y_halo=y_halo, row_scale=sig,
+                       act=act)
+        ctx.act = act
+        ctx.save_for_backward(xt, s, weight, sig, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xt, s, weight, sig, y = ctx.saved_tensors
+        c = eq_scale(weight)
+        g = _g(g, y)
+        gu, P = K.mod_out(g, y, act=ctx.act, gy_scale=sig)  # gu = sigma_inv * act'(y) * g
+        dw, dw_ret = _wgrad_buffer(weight)
+        K.conv_wgrad(xt, gu, dw, 3, 3, 1, alpha=c)
+        gxt = K.conv_fwd(gu, _pack(weight, gu.dtype, True), weight.shape[1], 3, 3, 1)
+        _, Qt = K.mod_in(gxt, xt, s, want_gx=False)         # sum_hw gxt * x~  (= s * Q)
+        ds = K.mod_bwd(weight.detach(), c, s, sig, _sqsum(weight), P, Qt, dw, q_scaled=True)
+        gz = K.up_bwd(gxt, scale=s) if ctx.needs_input_grad[0] else None
+        return gz, ds, dw_ret, None, None
+
+
+def up_mod_conv(z, s, weight, *, act=ACT_RELU, y_halo=0):
+    return UpModConvFn.apply(z, s, weight, act, y_halo)
+
+
 class ModResBlockFn(torch.autograd.Function):
     """ModulatedResnetBlock (reference blocks.py:36-68):
     x + modconv2(refl(ReLU(modconv1(refl(x), w))), w); x carries a reflect halo of 1.
 
-    Backward on the tcgen05 path needs only TWO HBM passes besides the four GEMMs: the
-    demodulation terms P = sum_hw dy*y come out of the wgrad epilogues, and the ReLU backward
-    of conv1 is a mask inside conv2's input-side pass (otm_mod_in)."""
+    conv1 runs on per-sample packs cW * s1 (its input is the un-modulated residual stream) and
+    writes h~ = s2 * ReLU(sigma1 * u1): conv2's modulation is conv1's post-activation scale, so
+    conv2 reads ONE shared weight pack.  Backward needs two HBM passes besides the four GEMMs:
+      * conv2's input-side pass (otm_mod_in) folds dgrad2's halo, applies s2, the ReLU mask of
+        h~ and sigma1, i.e. it hands conv1 the gradient w.r.t. its RAW output u1, so conv1's
+        dgrad and wgrad use the shared pack; its reduction Q~2 = sum fold * h~ is at the same
+        time conv1's demodulation term P1 (sum dy1 * y1 = sum s2 * fold * ReLU(y1)) and, divided
+        by s2 in otm_mod_bwd, conv2's direct style term Q2;
+      * conv1's input-side pass adds the residual gradient.
+    conv2's demodulation term P2 comes out of its wgrad epilogue (tcgen05 path)."""
 
     @staticmethod
     def forward(ctx, x, s1, s2, w1, w2, y_halo):
         s1 = s1.contiguous().float()
         s2 = s2.contiguous().float()
-        h, sig1, wp1 = _modconv_fwd(x, s1, w1, 1, 1, ACT_RELU, None, 1)
-        out, sig2, wp2 = _modconv_fwd(h, s2, w2, 1, 1, ACT_NONE, x, y_halo)
-        fused = K.wgrad_fuses_P(x, out, 3, 3, 1, 1)
-        ctx.fused = fused
-        if fused:
-            ctx.save_for_backward(x, s1, s2, w1, w2, h, sig1, sig2, wp1, wp2)
-        else:
-            ctx.save_for_backward(x, s1, s2, w1, w2, h, sig1, sig2, out)
+        n, f = x.shape[0], w1.shape[0]
+        sig1 = K.demod(s1, _sqsum(w1))
+        sig2 = K.demod(s2, _sqsum(w2))
+        wp1 = K.weight_pack(w1.detach(), eq_scale(w1), x.dtype, cs=s1, nb=n)
+        ht = K.conv_fwd(x, wp1, f, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig1, act=ACT_RELU,
+                        post_scale=s2, per_sample=True)
+        out = K.conv_fwd(ht, _pack(w2, x.dtype, False), f, 3, 3, 1, x_halo=1, y_halo=y_halo,
+                         row_scale=sig2, residual=x)
+        ctx.fused = K.wgrad_fuses_P(ht, out, 3, 3, 1, 1)
+        ctx.save_for_backward(x, s1, s2, w1, w2, ht, sig1, sig2, None if ctx.fused else out)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        if ctx.fused:
-            x, s1, s2, w1, w2, h, sig1, sig2, wp1, wp2 = ctx.saved_tensors
-            g = _g(g, x)
-            # conv2 (no activation): gy1 = ReLU'(h) * s2 * fold(dgrad2) comes straight out
-            gy1, ds2, dw2 = _modconv_bwd(g, None, h, s2, sig2, w2, 1, 1, None, True, wfwd=wp2,
-                                         relu_mask=True)
-            gx, ds1, dw1 = _modconv_bwd(gy1, None, x, s1, sig1, w1, 1, 1, g,
-                                        ctx.needs_input_grad[0], wfwd=wp1)
-            return gx, ds1, ds2, dw1, dw2, None
-        x, s1, s2, w1, w2, h, sig1, sig2, out = ctx.saved_tensors
+        x, s1, s2, w1, w2, ht, sig1, sig2, out = ctx.saved_tensors
+        n, f, h, w = x.shape
+        c1, c2 = eq_scale(w1), eq_scale(w2)
         g = _g(g, x)
-        # conv2: y2 = out - x, no activation
-        _, P2 = K.mod_out(g, out, res=x, materialise=False)
-        gh, ds2, dw2 = _modconv_bwd(g, P2, h, s2, sig2, w2, 1, 1, None, True)
-        # conv1: ReLU
-        gy1, P1 = K.mod_out(gh, h, act=ACT_RELU)
-        gx, ds1, dw1 = _modconv_bwd(gy1, P1, x, s1, sig1, w1, 1, 1, g, ctx.needs_input_grad[0])
-        return gx, ds1, ds2, dw1, dw2, None
+        # ---- conv2: dy2 = g, input h~ (already modulated) ------------------------------------
+        dw2, dw2_ret = _wgrad_buffer(w2)
+        if ctx.fused:
+            P2 = torch.zeros((n, f), dtype=torch.float32, device=x.device)
+            K.conv_wgrad(ht, g, dw2, 3, 3, 1, x_halo=1, alpha=c2, rs=sig2,
+                         wfwd=_pack(w2, ht.dtype, False), P=P2, wfwd_per_sample=False)
+        else:
+            _, P2 = K.mod_out(g, out, res=x, materialise=False)
+            K.conv_wgrad(ht, g, dw2, 3, 3, 1, x_halo=1, alpha=c2, rs=sig2)
+        wpt2 = K.weight_pack(w2.detach(), c2, g.dtype, rs=sig2, nb=n, transpose=True)
+        ght_p = K.conv_fwd(g, wpt2, f, 3, 3, 2, per_sample=True)
+        gu1, Qt2 = K.mod_in(ght_p[:, :, 1 : 1 + h, 1 : 1 + w], ht, s2, g_halo=1, relu_mask=True,
+                            gx_scale=sig1)
+        ds2 = K.mod_bwd(w2.detach(), c2, s2, sig2, _sqsum(w2), P2, Qt2, dw2, q_scaled=True)
+        # ---- conv1: dy = gu1 (w.r.t. its raw output), P1 == Qt2 --------------------------------
+        dw1, dw1_ret = _wgrad_buffer(w1)
+        K.conv_wgrad(x, gu1, dw1, 3, 3, 1, x_halo=1, alpha=c1, cs=s1)
+        gxt_p = K.conv_fwd(gu1, _pack(w1, g.dtype, True), f, 3, 3, 2)
+        gx, Q1 = K.mod_in(gxt_p[:, :, 1 : 1 + h, 1 : 1 + w], x, s1, g_halo=1, gadd=g,
+                          want_gx=ctx.needs_input_grad[0])
+        ds1 = K.mod_bwd(w1.detach(), c1, s1, sig1, _sqsum(w1), Qt2, Q1, dw1)
+        return gx, ds1, ds2, dw1_ret, dw2_ret, None
 
 
 def mod_res_block(x, s1, s2, w1, w2, *, y_halo):
@@ -527,3 +602,144 @@ def path(feats, h, weight=1.0):
     """feats: list of [2B,C,H,W] tensors ([f1 ; f2] stacked); h: [B] finite-difference steps.
     Returns (weight * loss, loss)."""
     return PathFn.apply(h.contiguous().float(), float(weight), *feats)
+
+
+# ---------------------------------------------------------------------------
+# small dense layers: EqualisedLinear, MappingNetwork, style-cycle loss (csrc/style.cu)
+# ---------------------------------------------------------------------------
+def _rows32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 [n, k] rows with unit last stride; a stride-0 batch expand is kept as it is."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2:
+        raise ValueError(f"expected [n, k], got {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+class LinearsFn(torch.autograd.Function):
+    """J EqualisedLinear layers (reference layers.py:27-43) in ONE launch each way:
+    y_j = x_j @ (c_j W_j)^T + b_j.  Inputs may alias (the two `to_style` layers of a
+    ModulatedResnetBlock read the same w[i], blocks.py:62-68): their gradients are summed."""
+
+    @staticmethod
+    def forward(ctx, n_jobs, *tensors):
+        xs, ws, bs = tensors[:n_jobs], tensors[n_jobs : 2 * n_jobs], tensors[2 * n_jobs :]
+        xs = [_rows32(x) for x in xs]
+        ys = [torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+              for x, w in zip(xs, ws)]
+        K.linear_fwd([dict(x=x, w=w.detach(), bias=b.detach(), y=y)
+                      for x, w, b, y in zip(xs, ws, bs, ys)])
+        ctx.n_jobs = n_jobs
+        ctx.params = (ws, bs)
+        ctx.save_for_backward(*xs)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *gys):
+        J = ctx.n_jobs
+        xs = ctx.saved_tensors
+        ws, bs = ctx.params
+        specs, gx, gw, gb = [], [None] * J, [None] * J, [None] * J
+        # one zero-filled buffer for every input gradient (dx is accumulated atomically)
+        need = [j for j in range(J) if gys[j] is not None and ctx.needs_input_grad[1 + j]]
+        big = (torch.zeros(sum(xs[j].numel() if xs[j].stride(0) else xs[j].shape[0] * xs[j].shape[1]
+                               for j in need), dtype=torch.float32, device=xs[0].device)
+               if need else None)
+        off = 0
+        for j in range(J):
+            if gys[j] is None:
+                continue
+            sp = dict(x=xs[j], w=ws[j].detach(), dy=gys[j].contiguous().float())
+            if ctx.needs_input_grad[1 + J + j]:
+                sp["dw"], gw[j] = _param_grad_buffer(ws[j])
+            if ctx.needs_input_grad[1 + 2 * J + j]:
+                sp["dbias"], gb[j] = _param_grad_buffer(bs[j])
+            if ctx.needs_input_grad[1 + j]:
+                n, k = xs[j].shape
+                gx[j] = sp["dx"] = big[off : off + n * k].view(n, k)
+                off += n * k
+            specs.append(sp)
+        if specs:
+            K.linear_bwd(specs)
+        return (None, *gx, *gw, *gb)
+
+
+def linears(xs, layers):
+    """layers: EqualisedLinear modules (attributes .weight.weight [o,k], .bias [o])."""
+    return LinearsFn.apply(len(xs), *xs, *[m.weight.weight for m in layers], *[m.bias for m in layers])
+
+
+def linear(x, layer):
+    return LinearsFn.apply(1, x, layer.weight.weight, layer.bias)[0]
+
+
+class MappingFn(torch.autograd.Function):
+    """MappingNetwork.forward (reference builder.py:46-49) with, optionally, the style mixing and
+    domain-variable interpolation of get_single_w / get_two_w fused (builder.py:51-132)."""
+
+    @staticmethod
+    def forward(ctx, z1, z2, cross, n_blocks, d0, d1, d_const, n_out, *params):
+        L = len(params) // 2
+        ws, bs = params[:L], params[L:]
+        z1 = z1.contiguous().float()
+        z2 = None if z2 is None else z2.contiguous().float()
+        d = tuple(None if t is None else t.contiguous().float() for t in (d0, d1))
+        outs = K.mapping_fwd(z1, z2, cross, [w.detach() for w in ws], [b.detach() for b in bs],
+                             n_blocks, d, d_const, n_out)
+        ctx.cfg = (cross, n_blocks, d, d_const, z2 is not None)
+        ctx.params = (ws, bs)
+        ctx.save_for_backward(z1, *([z2] if z2 is not None else []))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        cross, n_blocks, d, d_const, has_z2 = ctx.cfg
+        ws, bs = ctx.params
+        z1 = ctx.saved_tensors[0]
+        z2 = ctx.saved_tensors[1] if has_z2 else None
+        bufs_w, bufs_b, ret_w, ret_b = [], [], [], []
+        for w, b in zip(ws, bs):
+            bw, rw = _param_grad_buffer(w)
+            bb, rb = _param_grad_buffer(b)
+            bufs_w.append(bw), ret_w.append(rw), bufs_b.append(bb), ret_b.append(rb)
+        douts = [None if g is None else g.contiguous().float() for g in gouts]
+        douts += [None] * (2 - len(douts))
+        if any(g is not None for g in douts):
+            K.mapping_bwd(z1, z2, cross, [w.detach() for w in ws], [b.detach() for b in bs], n_blocks,
+                          d, d_const, douts, bufs_w, bufs_b)
+        return (None,) * 8 + (*ret_w, *ret_b)
+
+
+def mapping(net_layers, z1, z2=None, cross=None, *, n_blocks=1, d=(None, None), d_const=(1.0, 1.0),
+            n_out=1):
+    """net_layers: the EqualisedLinear modules of MappingNetwork.net.  Returns n_out tensors
+    [n_blocks, batch, features]."""
+    if any(t is not None and t.requires_grad for t in (z1, z2)):
+        raise ValueError("the mapping kernel does not differentiate w.r.t. z (the reference never does)")
+    return MappingFn.apply(z1, z2, cross, n_blocks, d[0], d[1], tuple(d_const), n_out,
+                           *[m.weight.weight for m in net_layers], *[m.bias for m in net_layers])
+
+
+class StyleCycleFn(torch.autograd.Function):
+    """style_cycle_loss_func (reference loss.py:60-75): scalar and both backward seeds in one
+    single-CTA launch."""
+
+    @staticmethod
+    def forward(ctx, a, b, weight, ratio):
+        a, b = _rows32(a), _rows32(b)
+        out, da, db = K.loss_style_cycle(a, b, ratio, weight, want_grad=tuple(ctx.needs_input_grad[:2]))
+        ctx.save_for_backward(da, db)
+        ctx.mark_non_differentiable(out)
+        return out * weight, out
+
+    @staticmethod
+    def backward(ctx, g, _):
+        da, db = ctx.saved_tensors
+        return _scaled(da, g), _scaled(db, g), None, None
+
+
+def style_cycle(original_w, reconstructed_w, weight=1.0, cos_l2_ratio=0.2):
+    """Returns (weight * loss, loss) as 1-element tensors."""
+    return StyleCycleFn.apply(original_w, reconstructed_w, float(weight), float(cos_l2_ratio))

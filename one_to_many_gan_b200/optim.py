@@ -47,7 +47,10 @@ class GradArena:
                              and dist.get_world_size(process_group) > 1)
         self.data_parallel = data_parallel
         self.world = dist.get_world_size(process_group) if data_parallel else 1
-        self._pending = None
+        self._pending: list = []                   # async NCCL works since the last wait
+        self._issued: list[tuple[int, int]] = []   # their (disjoint) element ranges
+        for p in self.params:
+            p._otm_owner = id(self)  # tags this optimiser's entries of the weight-pack cache
 
     def _attach_grads(self):
         for p, off in zip(self.params, self.offsets):
@@ -62,18 +65,51 @@ class GradArena:
                for p, off in zip(self.params, self.offsets)):
             self._attach_grads()
 
-    def all_reduce_async(self):
-        """Sum-all-reduce the gradient arena (NCCL over NVLink on the GPU box); the 1/world
-        averaging is folded into the Adam kernel's grad_scale."""
-        if self.data_parallel and self._pending is None:
-            self._pending = dist.all_reduce(self.grad_arena, op=dist.ReduceOp.SUM, group=self.group,
-                                            async_op=True)
+    def offset_of(self, param) -> int:
+        """Arena offset (elements) of a parameter: bucket boundaries for the overlapped reduce."""
+        for p, off in zip(self.params, self.offsets):
+            if p is param:
+                return off
+        raise KeyError("parameter is not in this arena")
+
+    def all_reduce_async(self, start: int = 0, end: int | None = None):
+        """Sum-all-reduce elements [start, end) of the gradient arena (NCCL over NVLink on the
+        GPU box) without blocking: a bucket can be launched as soon as its gradients are final,
+        while the rest of backward still runs.  The 1/world averaging is folded into the Adam
+        kernel's grad_scale.  Buckets issued between two waits must not overlap (an in-place sum
+        applied twice would count a gradient twice); re-issuing a covered range is a no-op."""
+        end = self.numel if end is None else end
+        if not self.data_parallel or start >= end:
+            return
+        for lo, hi in self._issued:
+            if lo <= start and end <= hi:
+                return
+            if start < hi and lo < end:
+                raise ValueError(f"all-reduce bucket [{start},{end}) overlaps [{lo},{hi})")
+        self._issued.append((start, end))
+        self._pending.append(dist.all_reduce(self.grad_arena[start:end], op=dist.ReduceOp.SUM,
+                                             group=self.group, async_op=True))
+
+    def _missing(self):
+        gaps, pos = [], 0
+        for lo, hi in sorted(self._issued):
+            if lo > pos:
+                gaps.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < self.numel:
+            gaps.append((pos, self.numel))
+        return gaps
 
     def wait_all_reduce(self):
-        if self.data_parallel:
-            self.all_reduce_async()
-            self._pending.wait()
-            self._pending = None
+        """Reduce whatever part of the arena has not been issued yet, then wait for everything."""
+        if not self.data_parallel:
+            return
+        for lo, hi in self._missing():
+            self.all_reduce_async(lo, hi)
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        self._issued = []
 
 
 class FlatAdam(GradArena):
@@ -99,7 +135,7 @@ class FlatAdam(GradArena):
         self.step_dev += 1
         K.adam(self.param_arena, self.grad_arena, self.exp_avg, self.exp_avg_sq, self.step_dev,
                self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
-        ops.invalidate_packs()
+        ops.invalidate_packs(owner=id(self))  # only THIS network's staged weights are stale
 
     # torch.optim.Adam-compatible checkpoint layout (reference evaluation.py:248-263)
     def state_dict(self):

@@ -105,12 +105,11 @@ class IdentityAugment(torch.nn.Module):
 
 
 def style_cycle_loss_func(original_w, reconstructed_w, *, normalise=True, cos_l2_ratio: float = 0.2):
-    """Reference loss.py:60-75 on [B, w_dim] tensors."""
-    if normalise:
-        original_w = F.normalize(original_w, dim=-1)
-        reconstructed_w = F.normalize(reconstructed_w, dim=-1)
-    cos_loss = 1 - F.cosine_similarity(original_w, reconstructed_w, dim=-1).mean()
-    return cos_loss + cos_l2_ratio * F.mse_loss(original_w, reconstructed_w)
+    """Reference loss.py:60-75 on [B, w_dim] tensors: one kernel writes the scalar and both
+    backward seeds (ops.style_cycle)."""
+    if not normalise:
+        raise ValueError("the B200 path implements normalise=True (all the reference uses)")
+    return ops.style_cycle(original_w, reconstructed_w, 1.0, cos_l2_ratio)[0].reshape(())
 
 
 def _floats(*tensors) -> list[float]:
@@ -157,7 +156,7 @@ def styles_per_input(config) -> int:
 
 def generator_losses(config, generator, discriminator, style_extractor, prints, marks,
                      reconstruct_w, translation_w, w1, w2, cent_fin_diff_h, ada=None,
-                     latent_noise=None):
+                     latent_noise=None, before_discriminator=None, on_latent_grad=None):
     """(reference training.py:158-243) all generator-side losses; each lambda is folded into the
     kernel that writes the term's backward seed.  Returns (total, gan, rec, idt, kl, path, style)
     as 1-element tensors: `total` is the weighted sum that is differentiated, the six terms are
@@ -167,7 +166,13 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     (translation decode, D and S on the translations, both path-length extractions) runs on the
     shoeprint latents broadcast to K styles (image (b, k) at index b*K + k, the
     `latent.expand(K, ...)` of evaluation.py:172-177); the latent gradient is the sum over the
-    K decodes.  Reconstruction (w = 0) and identity stay at B."""
+    K decodes.  Reconstruction (w = 0) and identity stay at B.
+
+    Two scheduling hooks for the data-parallel engine (both optional, no effect on the maths):
+    `before_discriminator()` is called right before the first use of the discriminator (the
+    deferred Adam(D) of the D step goes there); `on_latent_grad()` is called by autograd when the
+    gradient of the latents is complete, i.e. when every decoder / style-extractor gradient is
+    final and only the encoder backward remains."""
     opt = config["optimisation"]
     batch = prints.shape[0]
     nb = generator.n_style_blocks
@@ -175,6 +180,11 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     if translation_w.shape[1] != batch * n_sty or w1.shape[1] != batch * n_sty:
         raise ValueError("style batch must be a multiple of the image batch")
     combined_latents = generator.encode(torch.cat([prints, marks], dim=0))
+    if on_latent_grad is not None and combined_latents.requires_grad:
+        def _latents_ready(_g):
+            on_latent_grad()
+
+        combined_latents.register_hook(_latents_ready)
     kl_loss, kl_raw = ops.kl(combined_latents, opt["kl_loss_lambda"])
     if config["architecture"]["add_latent_noise"]:
         # (training.py:166-167) the caller pre-draws the noise so the device generator is
@@ -198,6 +208,8 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     generated_shoemarks = images[2 * batch :]
 
     # GAN loss (the discriminator's own weight gradients are not needed here)
+    if before_discriminator is not None:
+        before_discriminator()
     d_params = [p for p in discriminator.parameters() if p.requires_grad]
     for p in d_params:
         p.requires_grad_(False)
@@ -210,8 +222,8 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     gan_loss, _, gan_raw = ops.lsgan(fake_shoemark_scores, 1.0, 1.0)
 
     reconstructed_w = style_extractor(generated_shoemarks)
-    style_raw = style_cycle_loss_func(translation_w[-1], reconstructed_w).reshape(1)
-    style_loss = opt["style_cycle_loss_lambda"] * style_raw
+    style_loss, style_raw = ops.style_cycle(translation_w[-1], reconstructed_w,
+                                            opt["style_cycle_loss_lambda"])
 
     # path length: two extractions of the same latent as one 2B batch
     feats = generator.extract(torch.cat([shoeprint_latent_k, shoeprint_latent_k], dim=0),
@@ -219,7 +231,7 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     path_loss, path_raw = ops.path(feats, cent_fin_diff_h, opt["path_loss_lambda"])
 
     total = gan_loss + identity_loss + reconstruction_loss + kl_loss + path_loss + style_loss
-    return total, gan_raw, rec_raw, idt_raw, kl_raw, path_raw, style_raw.detach()
+    return total, gan_raw, rec_raw, idt_raw, kl_raw, path_raw, style_raw
 
 
 def backward_unit(loss):

@@ -90,6 +90,11 @@ def test_train_py_torch_backend_runs_the_reference_path(tmp_path, capsys, monkey
                                ckpt_every=100).replace('backend = "b200"', 'backend = "torch"'))
     import train
 
-    train.main(str(cfg))
+    prec, tf32 = torch.get_float32_matmul_precision(), torch.backends.cudnn.allow_tf32
+    try:
+        train.main(str(cfg))
+    finally:  # the reference's train.py:67-68 settings are process-global
+        torch.set_float32_matmul_precision(prec)
+        torch.backends.cudnn.allow_tf32 = tf32
     out = capsys.readouterr().out
     assert "Step: 2/2, D loss:" in out and "ADA: 0" in out

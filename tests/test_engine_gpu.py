@@ -127,6 +127,7 @@ def test_graph_replay_matches_eager_from_the_same_state(dtype):
     tol = 2e-5 if dtype == torch.float32 else 2e-3  # bf16: a flipped rounding moves a loss 1e-3
     for it in range(iters):
         _copy_state(A, B)
+        B_before = {id(o): o.param_arena.double().clone() for o in (B.oD, B.oG, B.oS)}
         batches = [_images(shape, 10 * (j + 1) + it) for j in range(4)]
         h = torch.tensor([0.11 + 0.01 * it, 0.19 - 0.01 * it])
         outs = []
@@ -139,8 +140,19 @@ def test_graph_replay_matches_eager_from_the_same_state(dtype):
         want = torch.tensor([outs[1][k] for k in A.LOSS_NAMES], dtype=torch.float64)
         torch.testing.assert_close(got, want, rtol=tol, atol=tol, msg=lambda m: f"iteration {it}: {m}")
         for a, b in ((A.oD, B.oD), (A.oG, B.oG), (A.oS, B.oS)):
+            # gradients: a LeakyReLU / ReLU mask flip (fp32 atomics order; in bf16 a flipped
+            # rounding) moves a gradient of this 32x32, batch-2 model (InstanceNorm over 2x4-pixel
+            # planes in D / S) by 3e-3 / up to 0.17 between two EAGER runs of the same state
+            # (measured); the tight gates are the losses above and the weights below
             ga, gb = a.grad_arena.double(), b.grad_arena.double()
-            assert ((ga - gb).norm() / gb.norm()).item() < (1e-3 if dtype == torch.float32 else 3e-2), it
+            assert ((ga - gb).norm() / gb.norm()).item() < (1e-2 if dtype == torch.float32 else 0.5), it
+            # weights after the captured Adam step vs the eager one from the same state: a missing
+            # or doubled update would be an O(lr) = 2e-3 per-element difference on every weight
+            pa, pb = a.param_arena.double(), b.param_arena.double()
+            # (bf16: ~8 % of the weights have a gradient whose SIGN is inside the noise; Adam's early
+            # steps move those by +-lr either way: 3e-4 mean measured; a missing update is 2e-3)
+            assert (pa - pb).abs().mean().item() < (2e-5 if dtype == torch.float32 else 1e-3), it
+            assert not torch.equal(pb, B_before[id(b)]), "the eager step did not update the weights"
         assert torch.equal(A.pool_index.count * torch.ones(1), B.pool_index.count * torch.ones(1))
     assert A.graph is not None and A.iterations == iters
 
@@ -186,3 +198,45 @@ def test_engine_bf16_graph_runs_configs_4_and_5():
         assert out != prev
         prev = out
     assert eng.graph is not None
+
+
+def test_bucket_gradients_are_final():
+    """The overlapped gradient exchange launches the all-reduce of the generator's DECODER slice
+    and of the style extractor when autograd reaches the encoder (hook on the latents).  That is
+    only correct if those gradients are final at that moment: snapshot them in the hook and
+    compare bit for bit with the arenas after backward; the encoder slice must still be
+    incomplete (= there is backward left to overlap with)."""
+    from one_to_many_gan_b200.engine import TrainIteration
+
+    size, batch = (64, 64), 2
+    cfg = _cfg(batch, size, 100)
+    D, G, M, S, (oD, oG, oM, oS) = _build(size, 32, 5, torch.bfloat16)
+    eng = TrainIteration(cfg, torch.device("cuda"), D, G, M, S, oD, oG, oM, oS, use_graph=False)
+    snap = {}
+
+    def grab():
+        snap["dec"] = oG.grad_arena[eng.g_dec_start:].clone()
+        snap["enc"] = oG.grad_arena[: eng.g_dec_start].clone()
+        snap["S"] = oS.grad_arena.clone()
+
+    eng.on_decoder_grads_final = grab
+    torch.manual_seed(3)
+    random.seed(3)
+    shape = (batch, 1, *size)
+    eng.load_inputs(*[_images(shape, 70 + j) for j in range(4)])
+    seen = {}
+    orig = eng._update_gms
+
+    def before_update():
+        seen["dec"] = oG.grad_arena[eng.g_dec_start:].clone()
+        seen["enc"] = oG.grad_arena[: eng.g_dec_start].clone()
+        seen["S"] = oS.grad_arena.clone()
+        orig()
+
+    eng._update_gms = before_update
+    eng.run()
+    assert 0 < eng.g_dec_start < oG.numel
+    assert snap and torch.equal(snap["dec"], seen["dec"]), "decoder gradients changed after the hook"
+    assert torch.equal(snap["S"], seen["S"]), "style-extractor gradients changed after the hook"
+    assert seen["dec"].abs().sum() > 0 and seen["S"].abs().sum() > 0 and seen["enc"].abs().sum() > 0
+    assert not torch.equal(snap["enc"], seen["enc"]), "the encoder backward had already run"

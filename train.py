@@ -215,7 +215,7 @@ def main(config_path: str):
                 "augmentation pipeline; set `[ada] allow_identity = true` to train un-augmented "
                 "(p is then logged and saved as 0), or use backend = 'torch'")
         eng.load_inputs(next(shoeprint_iter), next(shoemark_iter), next(shoeprint_iter), next(shoemark_iter))
-        out = eng.run()
+        out = eng.run(h="host")  # every random draw of the iteration comes from the host generators
         ada_p.update_p(torch.tensor(out["sign_real"]))
         if allow_identity:
             ada_p.p = torch.zeros(())  # what is applied is what is logged and saved
