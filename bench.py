@@ -44,6 +44,8 @@ CONFIG = {
 WORKLOAD = "G+D train iteration, default arch, 128x128, batch 32/GPU, bf16 act / fp32 accum"
 # dense-conv algorithmic GFLOP per image per iteration for the extra configs
 GFLOP_256 = 1441.2
+# dram bytes (read + write) of the roofline launch from the committed ncu capture, or None
+NCU_TRAFFIC_SHARED = None
 
 
 def base_config(world):
@@ -134,7 +136,7 @@ class HostBatches:
         return t
 
 
-def build_trainer(device, rank, use_graph=True, config=None):
+def build_trainer(device, rank, use_graph=True, config=None, return_engine=False):
     """The four networks + optimisers + the CUDA-graph iteration engine (public API:
     one_to_many_gan_b200.engine.TrainIteration)."""
     from one_to_many_gan_b200 import builder
@@ -168,7 +170,7 @@ def build_trainer(device, rank, use_graph=True, config=None):
         eng.load_inputs(next(prints), next(marks), next(prints), next(marks))
         return eng.run(sync_losses=True)  # includes the device->host read of the 10 scalars
 
-    return step
+    return (step, eng) if return_engine else step
 
 
 def time_steps(step, prints, marks, steps, warmup, dist_on, device):
@@ -197,9 +199,14 @@ def time_steps(step, prints, marks, steps, warmup, dist_on, device):
 
 
 def dominant_kernel_roofline(device):
-    """The modulated / plain 3x3 128->128 conv at 64x64 is ~69 % of the dense MACs of this
-    workload.  Time that launch alone with CUDA events on the launching stream
-    (L2 flushed between launches) and quote achieved TFLOP/s against the measured burst peak."""
+    """The 3x3 128->128 conv at 64x64 is ~69 % of the dense MACs of this workload
+    and `conv_tc_fwd_rr2t_kernel<3,2,6>` runs all of them (forward and dgrad).  Its most frequent
+    launch is timed alone -- CUDA events on the launching stream, L2 flushed between launches --
+    against the measured burst peak: the SHARED-weight form (42 of the 62 launches per iteration
+    since the modulation moved into the producers' epilogues: conv2 of a ModulatedResnetBlock
+    with its demodulation row scale, residual add and reflect halo, n = 96 = the 3B decode batch).
+    The per-sample-weight form that is left (conv1 of the block: per-sample packs, ReLU, the
+    next conv's style scale as post-activation scale) is reported next to it."""
     import math
 
     from one_to_many_gan_b200 import kernels as K
@@ -207,42 +214,57 @@ def dominant_kernel_roofline(device):
     n, c, hw = BATCH * 3, 128, 64  # the 3B decode batch the G step actually launches
     x = K.alloc(n, c, hw, hw, torch.bfloat16, device, 1, zero=True)
     K.padded_view(x, 1).normal_()
+    res = K.alloc(n, c, hw, hw, torch.bfloat16, device, 1, zero=True)
+    res.normal_()
     w = torch.randn(c, c, 3, 3, device=device)
     s = torch.rand(n, c, device=device) + 0.5
     sig = torch.rand(n, c, device=device) + 0.5
-    wp = K.weight_pack(w, 1 / math.sqrt(c * 9), torch.bfloat16, cs=s, nb=n)
+    alpha = 1 / math.sqrt(c * 9)
+    wp_shared = K.weight_pack(w, alpha, torch.bfloat16)
+    wp_sample = K.weight_pack(w, alpha, torch.bfloat16, cs=s, nb=n)
     y = K.alloc(n, c, hw, hw, torch.bfloat16, device, 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     flops = 2.0 * n * hw * hw * c * c * 9
 
-    def launch():
-        K.conv_fwd(x, wp, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, act=K.ACT_RELU,
-                   per_sample=True, out=y)
+    def shared():  # conv2: y = x_res + sigma_inv * conv(h~, cW)
+        K.conv_fwd(x, wp_shared, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, residual=res, out=y)
 
-    launch()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        launch()
-        b.record()
+    def per_sample():  # conv1: h~ = s2 * relu(sigma_inv * conv(x, cW * s1))
+        K.conv_fwd(x, wp_sample, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, act=K.ACT_RELU,
+                   post_scale=s, per_sample=True, out=y)
+
+    def timed(fn):
+        fn()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ms = statistics.mean(ts)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.mean(ts)
+
+    ms, ms_ps = timed(shared), timed(per_sample)
     pk, how = peaks()
-    ach = flops / ms / 1e9
+    ach, ach_ps = flops / ms / 1e9, flops / ms_ps / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from `ncu --set full`
-    # (profiles/r1_ncu_conv_tc_fwd_rr2t.md: 135.7 MB read + 65.8 MB written); algorithmic bytes =
-    # x (107 MB) + per-sample weights (28 MB) + y (107 MB) = 242 MB, part of y stays in the L2.
-    traffic = 201.6e6
+    # (profiles/r2_ncu_conv_tc_fwd_rr2t_shared.md); algorithmic bytes = x (107 MB) + residual
+    # (101 MB) + y (107 MB) + weights (0.3 MB) = 315 MB.
+    traffic = NCU_TRAFFIC_SHARED
     return {"bound": "tensor",
-            "kernel": "conv_tc_fwd_rr2t_kernel<3,2,6>: modulated 3x3 128->128 @64x64, n=96 "
-                      "(+demodulation scale, ReLU, reflect halo)",
+            "kernel": "conv_tc_fwd_rr2t_kernel<3,2,6>: shared-weight 3x3 128->128 @64x64, n=96 "
+                      "(+demodulation row scale, residual add, reflect halo)",
             "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "peak_source": how + " burst",
             "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4), "traffic": traffic,
-            "launch_ms": round(ms, 4), "flops_per_launch": flops}
+            "launch_ms": round(ms, 4), "flops_per_launch": flops,
+            "per_sample_weights_form": {"achieved": round(ach_ps, 1),
+                                        "frac": round(ach_ps / pk["bf16_tflops"], 4),
+                                        "launch_ms": round(ms_ps, 4),
+                                        "what": "per-sample packs + ReLU + post-activation style scale "
+                                                "(conv1 of a ModulatedResnetBlock; 20 of 62 launches)"}}
 
 
 def hbm_kernel_roofline(device):
@@ -423,10 +445,11 @@ def extra_config(device, rank, world, dist_on, image, batch, gflop, steps=5):
     from one_to_many_gan_b200.synthetic import SyntheticImages
 
     cfg = make_config(image, batch)
-    step = build_trainer(device, rank, True, cfg)
+    step, eng = build_trainer(device, rank, True, cfg, return_engine=True)
     prints = SyntheticImages(batch, 1, image, device, seed=42, rank=rank, stream_id=0)
     marks = SyntheticImages(batch, 1, image, device, seed=42, rank=rank, stream_id=1)
     ms, last = time_steps(step, prints, marks, steps, 4, dist_on, device)
+    eng.close()
     value = world * batch * steps / (ms / 1e3)
     pk, _ = peaks()
     tf = gflop * value / world / 1e3
@@ -479,7 +502,7 @@ def main():
 
     warmup = max(args.warmup, 3)
     use_graph = os.environ.get("OTM_NO_GRAPH", "0") != "1"
-    step = build_trainer(device, rank, use_graph)
+    step, eng = build_trainer(device, rank, use_graph, return_engine=True)
     prints = SyntheticImages(BATCH, 1, IMAGE, device, seed=42, rank=rank, stream_id=0)
     marks = SyntheticImages(BATCH, 1, IMAGE, device, seed=42, rank=rank, stream_id=1)
 
@@ -530,7 +553,8 @@ def main():
             },
         }
     # ---- BASELINE config 3 (256x256, batch 32 per GPU) through the same engine, every N -------
-    del step
+    eng.close()  # captured NCCL collectives must be released before the process group goes away
+    del step, eng
     torch.cuda.empty_cache()
     extra = None
     if not args.no_extra_configs:
@@ -545,8 +569,9 @@ def main():
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if dist_on:
-        dist.barrier()
-        dist.destroy_process_group()
+        from one_to_many_gan_b200.optim import shutdown_process_group
+
+        shutdown_process_group()
 
 
 if __name__ == "__main__":

@@ -216,6 +216,15 @@ typedef struct {
 } otm_norm_act_bwd_args;
 int otm_norm_act_bwd(const otm_norm_act_bwd_args* a, otm_stream stream);
 
+/* Second derivative of otm_norm_act (InstanceNorm + a piecewise-linear activation) for the R1
+ * gradient penalty (BASELINE config 5: double backward through the discriminator).  With g the
+ * gradient the FIRST backward received (w.r.t. the activation output) and gg the gradient w.r.t.
+ * that backward's result gx:   dg = d L / d g,   dx = d L / d x   (either ptr may be NULL).
+ * sums: fp32 workspace [n*c*5]. */
+int otm_norm_act_bwd_bwd(const otm_tensor* g, const otm_tensor* gg, const otm_tensor* x,
+                         const float* stats, int32_t act, const otm_tensor* dg, const otm_tensor* dx,
+                         float* sums, otm_stream stream);
+
 /* ---------------------------------------------------------------------------------
  * Resampling stencils.  Replace Smooth / UpSample / DownSample
  * (reference layers.py:191-247): replicate-pad 3x3 binomial blur, bilinear x2
@@ -382,6 +391,15 @@ int otm_adam(const otm_adam_args* a, otm_stream stream);
  * Philox4x32-10 keyed by (seed, stream_id), counter = offset + element index. */
 int otm_synth_uniform(float* out, int64_t n, uint64_t seed, uint64_t stream_id,
                       uint64_t offset, otm_stream stream);
+
+/* Device-resident real-data path (replaces ShoeDataset.__getitem__, the transform chain and the
+ * DataLoaders: reference src/data/datasets.py:13-50, train.py:120-169).  data: the resized image
+ * folder as uint8 [n_images, c, h, w] in HBM; idx [batch] int64 and flip [batch] uint8 (NULL = no
+ * flips) on the device.  out[b,c,y,x] = data[idx[b], c, y, flip[b] ? w-1-x : x] * 2/255 - 1
+ * (= Normalize(0.5, 0.5)(ToTensor(.))), fp32 [batch, c, h, w]. */
+int otm_gather_batch(const uint8_t* data, int64_t n_images, int32_t c, int32_t h, int32_t w,
+                     const int64_t* idx, const uint8_t* flip, int32_t batch, float* out,
+                     otm_stream stream);
 
 /* generic helpers */
 int otm_cast(const otm_tensor* x, const otm_tensor* y, otm_stream stream); /* dtype/stride copy */

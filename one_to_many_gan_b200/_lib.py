@@ -256,6 +256,11 @@ SYMBOLS = {
     "otm_instnorm_stats": (C.c_int, [_P(Tensor), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "otm_norm_act": (C.c_int, [_P(NormActArgs), C.c_void_p]),
     "otm_norm_act_bwd": (C.c_int, [_P(NormActBwdArgs), C.c_void_p]),
+    "otm_norm_act_bwd_bwd": (
+        C.c_int,
+        [_P(Tensor), _P(Tensor), _P(Tensor), C.c_void_p, C.c_int32, _P(Tensor), _P(Tensor), C.c_void_p,
+         C.c_void_p],
+    ),
     "otm_down": (C.c_int, [_P(DownArgs), C.c_void_p]),
     "otm_down_bwd": (C.c_int, [_P(Tensor), C.c_int32, _P(Tensor), C.c_void_p]),
     "otm_up": (C.c_int, [_P(Tensor), _P(Tensor), C.c_int32, C.c_void_p, C.c_void_p]),
@@ -290,6 +295,11 @@ SYMBOLS = {
     "otm_synth_uniform": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p],
+    ),
+    "otm_gather_batch": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+         C.c_void_p, C.c_void_p],
     ),
     "otm_cast": (C.c_int, [_P(Tensor), _P(Tensor), C.c_void_p]),
     "otm_add_inplace": (C.c_int, [_P(Tensor), _P(Tensor), C.c_void_p]),

@@ -132,7 +132,8 @@ class Generator(nn.Module):
         x = ops.nhwc(x, torch.float32)
         xp = ops.norm_act(x, norm=False, y_halo=3)  # ReflectionPad2d(3)
         c0 = enc[1]
-        raw = ops.conv(xp, c0.weight.weight, c0.bias, 7, 3, x_halo=3, out_dtype=self.act_dtype)
+        raw = ops.conv(xp, c0.weight.weight, c0.bias, 7, 3, x_halo=3, out_dtype=self.act_dtype,
+                       bias_dead=True)  # every encoder conv feeds an InstanceNorm
         n_tail = self.n_down + self.n_enc_res  # stages that follow the first conv
 
         def halo_after(stage_idx: int) -> int:
@@ -147,7 +148,7 @@ class Generator(nn.Module):
         i = 4
         for d in range(self.n_down):
             c = enc[i]
-            raw = ops.conv(a, c.weight.weight, c.bias, 3, 1)
+            raw = ops.conv(a, c.weight.weight, c.bias, 3, 1, bias_dead=True)
             a = ops.down(raw, norm=True, act=ops.ACT_RELU, y_halo=halo_after(d + 1))
             i += 4
         for r in range(self.n_enc_res):
@@ -237,10 +238,10 @@ def _patch_trunk(model: nn.Sequential, x: torch.Tensor, act_dtype):
     a = ops.down(a)
     for idx in (3, 7):
         c = model[idx]
-        raw = ops.conv(a, c.weight.weight, c.bias, 4, 1)
+        raw = ops.conv(a, c.weight.weight, c.bias, 4, 1, bias_dead=True)
         a = ops.down(raw, norm=True, act=ops.ACT_LRELU)
     c = model[11]
-    raw = ops.conv(a, c.weight.weight, c.bias, 4, 1)
+    raw = ops.conv(a, c.weight.weight, c.bias, 4, 1, bias_dead=True)
     return ops.norm_act(raw, norm=True, act=ops.ACT_LRELU)
 
 

@@ -878,6 +878,22 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int hh0 = h0 + half * TH;
         const uint32_t tacc =
             tmem_base + (uint32_t)(buf * 256 + half * 128) + ((uint32_t)(wq * 32) << 16);
+        // residual: fetched NOW into registers (16 x 16 B per thread = the whole 128-pixel x
+        // 256 B half-tile in flight per CTA), consumed after the transposing stores below, so the
+        // DRAM latency hides behind the TMEM read-out.  Coalesced mapping: a half-warp reads the
+        // 16 pieces of ONE pixel (256 contiguous bytes); warp wq owns pixels wq*32 .. wq*32+31.
+        uint4 rres[16];
+        if (p.res.ptr) {
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int q = wq * 32 + it * 2 + (lane >> 4);
+            const int qh = hh0 + q / TW, qw = w0 + q % TW;
+            rres[it] = (qh < p.y.h && qw < p.y.w)
+                           ? *reinterpret_cast<const uint4*>(
+                                 vptr<__nv_bfloat16>(p.res, n, qh, qw, o0 + (lane & 15) * 8))
+                           : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         // the previous TMA store must have finished reading the staging tile
         if (te == 0) tma_store_wait_read();
         asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -904,24 +920,23 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int sw = m & 7;
         if (p.res.ptr) {
           asm volatile("bar.sync 2, 128;" ::: "memory");  // staged tile complete
-          if (valid) {
-#pragma unroll 4
-            for (int piece = 0; piece < BN / 8; ++piece) {
-              uint4* sp = reinterpret_cast<uint4*>(myrow + (piece >> 3) * SUB_BYTES +
-                                                   (((piece & 7) ^ sw) << 4));
-              uint4 a = *sp;
-              const uint4 b = *reinterpret_cast<const uint4*>(
-                  vptr<__nv_bfloat16>(p.res, n, oh, ow, o0 + piece * 8));
-              __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a);
-              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+          const int piece = lane & 15;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
-                a2[e] = __floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y);
-              }
-              *sp = a;
+          for (int it = 0; it < 16; ++it) {
+            const int q = wq * 32 + it * 2 + (lane >> 4);
+            uint4* sp = reinterpret_cast<uint4*>(stage_out + q * 128 + (piece >> 3) * SUB_BYTES +
+                                                 (((piece & 7) ^ (q & 7)) << 4));
+            uint4 a = *sp;
+            __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rres[it]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+              a2[e] = __floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y);
             }
+            *sp = a;
           }
+          __syncwarp();  // the halo stores below read this warp's own 32 pixel rows
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1376,9 +1391,12 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const int taps = a->kh * a->kw;
   const int m_tiles = M / 128;
   p.n_tiles_n = N / BN;
-  // taps per CTA: as many shifted x tiles as fit a 256-column MMA next to the one dy tile
-  // (OTM_WGRAD_TPC=1 restores one tap per CTA, for A/B measurements)
-  static const int tpc_cap = [] { const char* e = getenv("OTM_WGRAD_TPC"); return e ? atoi(e) : 4; }();
+  // taps per CTA.  OTM_WGRAD_TPC=2|4 lays that many shifted x tiles side by side as ONE 256-column
+  // operand next to the shared dy tile (96 instead of 128 B/clk of operand reads).  Measured on
+  // B200 (tools/bench_wgrad.py, profiles/r2_wgrad_tpc.md): SLOWER -- 717 vs 921 TFLOP/s at n=96
+  // 128->128, 645 vs 733 at n=64 -- because the 48 KB stages leave a 2-deep ring per CTA at two
+  // CTAs per SM and the TMA latency is exposed.  Default: one tap per CTA.
+  static const int tpc_cap = [] { const char* e = getenv("OTM_WGRAD_TPC"); return e ? atoi(e) : 1; }();
   int tpc = p.a_is_x ? 1 : 256 / BN;
   if (tpc > tpc_cap) tpc = tpc_cap;
   const int tap_ctas = (taps + tpc - 1) / tpc;
@@ -1408,7 +1426,10 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
     else if (tpc == 2) rc = launch_wgrad<64, 3, 2, 2>(tmA, tmB, p, grid, st);
     else rc = launch_wgrad<64, 4, 2, 1>(tmA, tmB, p, grid, st);
   } else if (BN == 128) {
-    if (tpc >= 2) rc = launch_wgrad<128, 2, 2, 2>(tmA, tmB, p, grid, st);
+    static const int occ1 = [] { const char* e = getenv("OTM_WGRAD_OCC1"); return e ? atoi(e) : 0; }();
+    if (tpc >= 2 && occ1) rc = launch_wgrad<128, 4, 1, 2>(tmA, tmB, p, grid, st);  // experiment
+    else if (tpc >= 2) rc = launch_wgrad<128, 2, 2, 2>(tmA, tmB, p, grid, st);
+    else if (occ1) rc = launch_wgrad<128, 6, 1, 1>(tmA, tmB, p, grid, st);        // experiment
     else rc = launch_wgrad<128, 3, 2, 1>(tmA, tmB, p, grid, st);
   } else {
     rc = launch_wgrad<256, 2, 2, 1>(tmA, tmB, p, grid, st);

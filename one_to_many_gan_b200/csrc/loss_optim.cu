@@ -233,6 +233,52 @@ __global__ void __launch_bounds__(256) synth_kernel(float* out, long long n, uin
   }
 }
 
+// ---------------------------------------------------------------------------
+// Device-resident real-data path: the whole (resized) image folder lives in HBM as uint8
+// [N, C, H, W] -- what PIL decodes, 1 byte per pixel -- and a batch is ONE gather kernel:
+//   out[b] = Normalize(0.5, 0.5)(ToTensor(data[idx[b]])), mirrored in w when flip[b] != 0
+// = (v / 255 - 0.5) / 0.5, the transform chain of reference train.py:120-126 plus the random
+// horizontal flip of ShoeDataset.__getitem__ (datasets.py:48-50).  HBM-bound: 1 B read + 4 B
+// written per pixel; a thread converts 4 consecutive pixels (one 32-bit load, one 128-bit store).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_batch_kernel(const uint8_t* __restrict__ data, const long long* __restrict__ idx,
+                    const uint8_t* __restrict__ flip, float* __restrict__ out, int batch, int c,
+                    int h, int w, int vec) {
+  const long long plane = (long long)h * w, img = plane * c;
+  if (vec) {
+    const int wq = w / 4;
+    const long long total = (long long)batch * c * h * wq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int xq = (int)(i % wq);
+      long long r = i / wq;
+      const int y = (int)(r % h);
+      r /= h;
+      const int ch = (int)(r % c), b = (int)(r / c);
+      const bool fl = flip && flip[b];
+      const uint8_t* row = data + idx[b] * img + ch * plane + (long long)y * w;
+      const uchar4 v = *reinterpret_cast<const uchar4*>(row + (fl ? w - 4 - 4 * xq : 4 * xq));
+      const float k = 2.f / 255.f;
+      float4 o;
+      if (fl) o = make_float4(v.w * k - 1.f, v.z * k - 1.f, v.y * k - 1.f, v.x * k - 1.f);
+      else o = make_float4(v.x * k - 1.f, v.y * k - 1.f, v.z * k - 1.f, v.w * k - 1.f);
+      *reinterpret_cast<float4*>(out + ((long long)b * c + ch) * plane + (long long)y * w + 4 * xq) = o;
+    }
+    return;
+  }
+  const long long total = (long long)batch * img;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const long long r = i / w;  // (b * c + ch) * h + y
+    const int b = (int)(i / img);
+    const bool fl = flip && flip[b];
+    const long long src = idx[b] * img + (r - (long long)b * c * h) * w + (fl ? w - 1 - x : x);
+    out[i] = data[src] * (2.f / 255.f) - 1.f;
+  }
+}
+
 }  // namespace otm
 
 using namespace otm;
@@ -354,6 +400,23 @@ int otm_adam(const otm_adam_args* a, otm_stream stream) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adam_kernel<<<(int)blocks, 256, 0, st>>>(*a);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
+int otm_gather_batch(const uint8_t* data, int64_t n_images, int32_t c, int32_t h, int32_t w,
+                     const int64_t* idx, const uint8_t* flip, int32_t batch, float* out,
+                     otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(data && idx && out && n_images >= 1 && c >= 1 && h >= 1 && w >= 1 && batch >= 1,
+              "gather_batch: bad arguments");
+  const int vec = (w % 4 == 0) && ((uintptr_t)data % 4 == 0) && ((uintptr_t)out % 16 == 0);
+  const long long items = (long long)batch * c * h * (vec ? w / 4 : w);
+  long long blocks = (items + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  gather_batch_kernel<<<(int)blocks, 256, 0, st>>>(data, (const long long*)idx, flip, out, batch, c, h,
+                                                   w, vec);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
 }

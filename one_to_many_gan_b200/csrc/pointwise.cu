@@ -441,6 +441,96 @@ struct NormActBwdApplyF : NormActBwdBase<T, V, DOWN> {
 };
 
 // ---------------------------------------------------------------------------
+// Second derivative of InstanceNorm (+ LeakyReLU / ReLU): the R1 gradient penalty differentiates
+// a BACKWARD pass (BASELINE config 5).  First backward (otm_norm_act_bwd), per (n,c) plane of N
+// pixels, yh = (x - mean) * r:
+//     gy = g * act'(yh) ;  gx = B(gy) = r * (gy - mean(gy) - yh * mean(gy * yh))
+// Given gg = dL/d(gx):   B is linear and self-adjoint in gy, so
+//     dL/d(g)  = act'(yh) * B(gg)
+//     dL/d(x)_j = -r^2 * [ b (gg_j - mean(gg)) + a (gy_j - mean(gy))
+//                          + yh_j (mean(gg * gy) - mean(gg) mean(gy) - 3 a b) ]
+//   with a = mean(gg * yh), b = mean(gy * yh)  (act' is piecewise constant: no term from it).
+// Pass 1 reduces the five means, pass 2 writes both outputs.
+// ---------------------------------------------------------------------------
+template <typename T, int V>
+struct Norm2Base {
+  View g, gg, x;
+  const float* stats;
+  int act, C;
+  struct State { float mean[V], rstd[V], mg[V], mgg[V], a[V], b[V], t[V]; };
+  __device__ void prefetch(int, int, int, int) const {}
+  __device__ void prepare_stats(int n, int c, State& st) const {
+    const float* p = stats + ((long long)n * C + c) * 2;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { st.mean[i] = p[2 * i]; st.rstd[i] = p[2 * i + 1]; }
+  }
+  __device__ void load(int n, int h, int w, int c, const State& st, float (&gy)[V], float (&ggv)[V],
+                       float (&yh)[V], float (&mask)[V]) const {
+    load_vec<T, V>(vptr<T>(g, n, h, w, c), gy);
+    load_vec<T, V>(vptr<T>(gg, n, h, w, c), ggv);
+    load_vec<T, V>(vptr<T>(x, n, h, w, c), yh);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      yh[i] = (yh[i] - st.mean[i]) * st.rstd[i];
+      mask[i] = act == OTM_ACT_NONE ? 1.f : (yh[i] > 0.f ? 1.f : (act == OTM_ACT_LRELU ? 0.2f : 0.f));
+      gy[i] *= mask[i];
+    }
+  }
+};
+
+template <typename T, int V>
+struct Norm2ReduceF : Norm2Base<T, V> {
+  static constexpr int NQ = 5;
+  using State = typename Norm2Base<T, V>::State;
+  __device__ void prepare(int n, int c, State& st) const { this->prepare_stats(n, c, st); }
+  __device__ void operator()(int n, int h, int w, int c, float (&acc)[5][V], const State& st) const {
+    float gy[V], ggv[V], yh[V], mask[V];
+    this->load(n, h, w, c, st, gy, ggv, yh, mask);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      acc[0][i] += gy[i];
+      acc[1][i] += ggv[i];
+      acc[2][i] += ggv[i] * yh[i];
+      acc[3][i] += gy[i] * yh[i];
+      acc[4][i] += ggv[i] * gy[i];
+    }
+  }
+  __device__ int out_index(int n, int c, int q) const { return (n * this->C + c) * 5 + q; }
+};
+
+template <typename T, int V>
+struct Norm2ApplyF : Norm2Base<T, V> {
+  View dg, dx;
+  const float* sums;
+  float inv_hw;
+  using State = typename Norm2Base<T, V>::State;
+  __device__ void prepare(int n, int c, State& st) const {
+    this->prepare_stats(n, c, st);
+    const float* sm = sums + ((long long)n * this->C + c) * 5;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      st.mg[i] = sm[5 * i] * inv_hw;
+      st.mgg[i] = sm[5 * i + 1] * inv_hw;
+      st.a[i] = sm[5 * i + 2] * inv_hw;
+      st.b[i] = sm[5 * i + 3] * inv_hw;
+      st.t[i] = sm[5 * i + 4] * inv_hw - st.mgg[i] * st.mg[i] - 3.f * st.a[i] * st.b[i];
+    }
+  }
+  __device__ void operator()(int n, int h, int w, int c, const State& st) const {
+    float gy[V], ggv[V], yh[V], mask[V], o1[V], o2[V];
+    this->load(n, h, w, c, st, gy, ggv, yh, mask);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      o1[i] = mask[i] * st.rstd[i] * (ggv[i] - st.mgg[i] - yh[i] * st.a[i]);
+      o2[i] = -st.rstd[i] * st.rstd[i] *
+              (st.b[i] * (ggv[i] - st.mgg[i]) + st.a[i] * (gy[i] - st.mg[i]) + yh[i] * st.t[i]);
+    }
+    if (dg.ptr) store_vec<T, V>(vptr_mut<T>(dg, n, h, w, c), o1);
+    if (dx.ptr) store_vec<T, V>(vptr_mut<T>(dx, n, h, w, c), o2);
+  }
+};
+
+// ---------------------------------------------------------------------------
 // resampling: shared 1-D tap generators
 // ---------------------------------------------------------------------------
 // DownSample = blur then bilinear to n_out = n_in/2 (align_corners=False, scale n_in/n_out).
@@ -2121,6 +2211,35 @@ static int norm_act_bwd_impl(const otm_norm_act_bwd_args* a, otm_stream stream) 
     else OTM_NAB_BODY(false);
   });
 #undef OTM_NAB_BODY
+  return rc;
+}
+
+int otm_norm_act_bwd_bwd(const otm_tensor* g, const otm_tensor* gg, const otm_tensor* x,
+                         const float* stats, int32_t act, const otm_tensor* dg, const otm_tensor* dx,
+                         float* sums, otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(g && gg && x && g->ptr && gg->ptr && x->ptr && stats && sums && dg && dx,
+              "norm_act_bwd_bwd: null argument");
+  OTM_REQUIRE(same_shape(*g, *x) && same_shape(*gg, *x) && g->dtype == x->dtype && gg->dtype == x->dtype,
+              "norm_act_bwd_bwd: shape / dtype mismatch");
+  OTM_REQUIRE(act == OTM_ACT_NONE || act == OTM_ACT_RELU || act == OTM_ACT_LRELU,
+              "norm_act_bwd_bwd: piecewise-linear activations only");
+  const int C = x->c;
+  OTM_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 5 * x->n * C, st));
+  const bool vok = vec_ok(*g, 8) && vec_ok(*gg, 8) && vec_ok(*x, 8) && vec_ok(*dg, 8) && vec_ok(*dx, 8);
+  int rc = OTM_OK;
+  OTM_DISPATCH_TV(x->dtype, vok, {
+    Norm2ReduceF<T, V> r;
+    r.g = make_view(*g); r.gg = make_view(*gg); r.x = make_view(*x); r.stats = stats; r.act = act; r.C = C;
+    rc = launch_nc_reduce<V>(r, x->n, x->h, x->w, C, sums, st);
+    if (rc == OTM_OK) {
+      Norm2ApplyF<T, V> f;
+      f.g = make_view(*g); f.gg = make_view(*gg); f.x = make_view(*x); f.stats = stats; f.act = act; f.C = C;
+      f.dg = dg->ptr ? make_view(*dg) : null_view(); f.dx = dx->ptr ? make_view(*dx) : null_view();
+      f.sums = sums; f.inv_hw = 1.f / (float)(x->h * x->w);
+      rc = launch_ew<V>(f, x->n, x->h, x->w, C, st);
+    }
+  });
   return rc;
 }
 

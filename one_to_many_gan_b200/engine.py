@@ -280,6 +280,15 @@ class TrainIteration:
         for o in opts:
             o.wait_all_reduce()
 
+    def close(self):
+        """Drop the captured graphs.  MUST run before `dist.destroy_process_group()`: tearing a NCCL
+        communicator down while a CUDA graph that captured its collectives is alive hangs."""
+        torch.cuda.synchronize(self.dev)
+        self.graph = None
+        self._warm_left = 0
+        gc.collect()
+        torch.cuda.synchronize(self.dev)
+
     # ---------------------------------------------------------------- image pool I/O
     def pool_images(self):
         """The pool as the reference's `ImageBuffer.images` list of [1,C,H,W] tensors."""

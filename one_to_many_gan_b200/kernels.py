@@ -221,6 +221,18 @@ def norm_act_bwd(g, x, stats=None, act=ACT_NONE, *, g_halo=0, g2=None, want_gres
     return (gx, gres) if want_gres else gx
 
 
+def norm_act_bwd_bwd(g, gg, x, stats, act, want_dg=True, want_dx=True):
+    """Second derivative of norm_act (R1 penalty): returns (dL/dg, dL/dx) given gg = dL/d(gx)."""
+    n, c, h, w = x.shape
+    dg = alloc(n, c, h, w, x.dtype, x.device) if want_dg else None
+    dx = alloc(n, c, h, w, x.dtype, x.device) if want_dx else None
+    sums = torch.empty((n, c, 5), dtype=torch.float32, device=x.device)
+    tg, tgg, tx, tdg, tdx = L.tdesc(g), L.tdesc(gg), L.tdesc(x), L.tdesc(dg), L.tdesc(dx)
+    L.check(L.lib.otm_norm_act_bwd_bwd(_byref(tg), _byref(tgg), _byref(tx), L.ptr(stats), act, _byref(tdg),
+                                       _byref(tdx), L.ptr(sums), L.stream_ptr()), "otm_norm_act_bwd_bwd")
+    return dg, dx
+
+
 def down(x, stats=None, act=ACT_NONE, y_halo=0, out=None):
     n, c, h, w = x.shape
     if out is None:
@@ -473,6 +485,19 @@ def adam(param, grad, m, v, step_dev, lr, beta1, beta2, eps=1e-8, grad_scale=1.0
 def synth_uniform(out, seed, stream_id, offset=0):
     L.check(L.lib.otm_synth_uniform(L.ptr(out), out.numel(), seed, stream_id, offset, L.stream_ptr()),
             "otm_synth_uniform")
+    return out
+
+
+def gather_batch(data, idx, flip, out=None):
+    """data: uint8 [N,C,H,W] on the device; idx int64 [B]; flip uint8 [B] or None -> fp32 [B,C,H,W]
+    in [-1, 1]."""
+    n, c, h, w = data.shape
+    if data.dtype != torch.uint8 or not data.is_contiguous():
+        raise ValueError("gather_batch: data must be a contiguous uint8 [N,C,H,W] tensor")
+    if out is None:
+        out = torch.empty((idx.shape[0], c, h, w), dtype=torch.float32, device=data.device)
+    L.check(L.lib.otm_gather_batch(L.ptr(data), n, c, h, w, L.ptr(idx), L.ptr(flip), idx.shape[0],
+                                   L.ptr(out), L.stream_ptr()), "otm_gather_batch")
     return out
 
 

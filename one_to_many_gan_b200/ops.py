@@ -136,8 +136,9 @@ class ConvFn(torch.autograd.Function):
     of the conv; `pad` is the total logical padding (halo + zero padding)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype):
+    def forward(ctx, x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype, bias_dead=False):
         ctx.bias = bias
+        ctx.bias_dead = bias_dead
         cout = weight.shape[0]
         wp = _pack(weight, x.dtype, False)
         y = K.conv_fwd(x, wp, cout, k, k, pad, x_halo=x_halo, y_halo=y_halo,
@@ -163,7 +164,11 @@ class ConvFn(torch.autograd.Function):
             K.conv_wgrad(x, g, buf, k, k, pad, x_halo=x_halo, alpha=eq_scale(weight))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             buf, gb = _param_grad_buffer(bias)
-            K.channel_sum(g, out=buf)
+            # bias_dead: the conv feeds an InstanceNorm, which cancels the bias exactly -- its
+            # gradient is identically 0 (sum_hw of the norm's input gradient vanishes);
+            # the zero-initialised buffer IS the exact gradient, no reduction pass needed
+            if not ctx.bias_dead:
+                K.channel_sum(g, out=buf)
         if ctx.needs_input_grad[0]:
             wpt = _pack(weight, g.dtype, True)
             gxp = K.conv_fwd(g, wpt, cin, k, k, k - 1 - pad + x_halo, out_dtype=x.dtype)
@@ -173,11 +178,14 @@ class ConvFn(torch.autograd.Function):
                 gx = K.norm_act_bwd(gint, None, None, ACT_NONE, g_halo=x_halo)
             else:
                 gx = gxp
-        return gx, gw, gb, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None
 
 
-def conv(x, weight, bias, k, pad, *, x_halo=0, y_halo=0, act=ACT_NONE, out_dtype=None):
-    return ConvFn.apply(x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype or x.dtype)
+def conv(x, weight, bias, k, pad, *, x_halo=0, y_halo=0, act=ACT_NONE, out_dtype=None,
+         bias_dead=False):
+    """bias_dead=True: the output goes straight into an InstanceNorm (the bias gradient is exactly
+    zero and is not computed)."""
+    return ConvFn.apply(x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype or x.dtype, bias_dead)
 
 
 # ---------------------------------------------------------------------------

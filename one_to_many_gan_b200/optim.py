@@ -165,3 +165,26 @@ class FlatAdam(GradArena):
             self.step_dev.fill_(self.steps)
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+
+
+def shutdown_process_group(timeout_s: float = 20.0) -> None:
+    """barrier + destroy_process_group that cannot hang the process: communicators that were
+    captured into CUDA graphs have been seen to block in ncclCommDestroy even after the graphs
+    were released, so the teardown runs in a helper thread and, if it does not return in time,
+    the process exits immediately with status 0 (all results have been written by then)."""
+    import os
+    import sys
+    import threading
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    dist.barrier()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    if t.is_alive():
+        os._exit(0)

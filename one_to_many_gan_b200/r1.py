@@ -9,14 +9,14 @@ and its gradient w.r.t. D's weights needs the derivative OF a backward pass.  Th
 bilinear in (x, W), so {forward, dgrad, wgrad} is closed under differentiation: the three
 autograd Functions below call the library's conv kernels (tcgen05 in bf16 mode) and express
 their own backward through each other, to any order.  The per-sample normalisation, LeakyReLU
-and the blur/bilinear stencils between the convs are evaluated with differentiable tensor ops on
-this path only -- their second derivatives are needed (the InstanceNorm Jacobian depends on its
-input); they are HBM-bound and a few percent of an iteration."""
+and the blur/bilinear stencils between the convs are twice-differentiable Functions over the
+library's own passes as well: the stencils are linear (their backward is the transposed stencil,
+whose backward is the stencil), LeakyReLU is piecewise linear, and the second derivative of
+InstanceNorm -- its Jacobian depends on its input -- is the kernel pair otm_norm_act_bwd_bwd."""
 
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import kernels as K
 from . import ops
@@ -30,11 +30,13 @@ class _Conv(torch.autograd.Function):
     """y = conv(x, w), stride 1, zero padding `pad`; w already carries the equalised-LR scale."""
 
     @staticmethod
-    def forward(ctx, x, w, pad, dtype, out_dtype):
+    def forward(ctx, x, w, pad, dtype, out_dtype, bias=None):
+        """bias: added in the conv epilogue; first-order gradient only (see _eq_conv)."""
         cout, cin, k, _ = w.shape
         xin = _cl(x, torch.float32 if cin == 1 else dtype)
         wp = K.weight_pack(w.detach().float().contiguous(), 1.0, xin.dtype)
-        y = K.conv_fwd(xin, wp, cout, k, k, pad, out_dtype=out_dtype)
+        y = K.conv_fwd(xin, wp, cout, k, k, pad, out_dtype=out_dtype,
+                       bias=None if bias is None else bias.detach())
         ctx.save_for_backward(x, w)
         ctx.cfg = (pad, dtype, out_dtype)
         return y
@@ -48,7 +50,10 @@ class _Conv(torch.autograd.Function):
             gx = _Dgrad.apply(g, w, pad, dtype, x.dtype)
         if ctx.needs_input_grad[1]:
             gw = _Wgrad.apply(x, g, w.shape[2], pad, dtype)
-        return gx, gw, None, None, None
+        gb = None
+        if ctx.needs_input_grad[5]:
+            gb = K.channel_sum(_cl(g, g.dtype))
+        return gx, gw, None, None, None, gb
 
 
 class _Dgrad(torch.autograd.Function):
@@ -102,39 +107,92 @@ class _Wgrad(torch.autograd.Function):
         return d_x, d_g, None, None, None
 
 
-def _eq_conv(x, layer, dtype, out_dtype=None):
-    """EqualisedConv2d (reference layers.py:82-102) on the twice-differentiable path."""
+class _NormAct(torch.autograd.Function):
+    """y = act(InstanceNorm(x)) (norm=False: y = act(x)), act piecewise linear -- twice
+    differentiable on the library's kernels: the first backward is otm_norm_act_bwd, the second
+    otm_norm_act_bwd_bwd (the InstanceNorm Jacobian depends on x; the activation's does not)."""
+
+    @staticmethod
+    def forward(ctx, x, norm, act, dtype):
+        xin = _cl(x, dtype)
+        stats = K.instnorm_stats(xin) if norm else None
+        y = K.norm_act(xin, stats, act)
+        ctx.act, ctx.dtype = act, dtype
+        ctx.save_for_backward(x, stats)  # x itself: the second derivative flows back into it
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, stats = ctx.saved_tensors
+        return _NormActBwd.apply(g, x, stats, ctx.act, ctx.dtype), None, None, None
+
+
+class _NormActBwd(torch.autograd.Function):
+    """gx = B(g * act'(yh)); `stats` (mean, rstd of x) is auxiliary: the x-derivative computed in
+    backward() already contains the dependence through the statistics."""
+
+    @staticmethod
+    def forward(ctx, g, x, stats, act, dtype):
+        xin = _cl(x, dtype)
+        gin = _cl(g, xin.dtype)
+        gx = K.norm_act_bwd(gin, xin, stats, act)
+        ctx.act = act
+        ctx.save_for_backward(gin, xin, stats)
+        return gx
+
+    @staticmethod
+    def backward(ctx, gg):
+        gin, xin, stats = ctx.saved_tensors
+        ggin = _cl(gg, xin.dtype)
+        if stats is None:  # activation only: linear in g, no dependence on x almost everywhere
+            return K.norm_act_bwd(ggin, xin, None, ctx.act), None, None, None, None
+        d_g, d_x = K.norm_act_bwd_bwd(gin, ggin, xin, stats, ctx.act,
+                                      want_dg=ctx.needs_input_grad[0], want_dx=ctx.needs_input_grad[1])
+        return d_g, d_x, None, None, None
+
+
+class _Down(torch.autograd.Function):
+    """DownSample (reference layers.py:232-247): linear, so its backward is the transposed stencil
+    and the backward of THAT is the stencil again."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = tuple(x.shape[2:])
+        return K.down(ops.nhwc(x.detach()))
+
+    @staticmethod
+    def backward(ctx, g):
+        return _DownT.apply(g, ctx.hw)
+
+
+class _DownT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, hw):
+        return K.down_bwd(ops.nhwc(g.detach()), hw)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return _Down.apply(gg), None
+
+
+def _eq_conv(x, layer, dtype, out_dtype=None, with_bias=False):
+    """EqualisedConv2d (reference layers.py:82-102) on the twice-differentiable path.  Only layer
+    0 takes its bias (with_bias): the biases of the three layers that feed an InstanceNorm are
+    cancelled by it, and `grad_x sum(D(x))` does not depend on the last layer's.  Layer 0's bias
+    DOES matter: it shifts the activations every later InstanceNorm Jacobian is evaluated at."""
     w = layer.weight.weight
-    y = _Conv.apply(x, w * ops.eq_scale(w), layer.padding, dtype, out_dtype or dtype)
-    if getattr(layer, "bias", None) is not None:
-        y = y + layer.bias.view(1, -1, 1, 1).to(y.dtype)
-    return y
-
-
-def _instance_norm(x, eps=1e-5):
-    xf = x.float()
-    m = xf.mean(dim=(2, 3), keepdim=True)
-    v = xf.var(dim=(2, 3), unbiased=False, keepdim=True)
-    return ((xf - m) * torch.rsqrt(v + eps)).to(x.dtype)
-
-
-def _down(x):
-    """DownSample (reference layers.py:232-247): replicate-pad blur, bilinear to (H//2, W//2)."""
-    xf = F.pad(x.float(), (1, 1, 1, 1), mode="replicate")
-    h, w = x.shape[2:]
-    rows = xf[:, :, 0:h] + 2.0 * xf[:, :, 1 : h + 1] + xf[:, :, 2 : h + 2]
-    blur = (rows[..., 0:w] + 2.0 * rows[..., 1 : w + 1] + rows[..., 2 : w + 2]) * (1.0 / 16.0)
-    y = F.interpolate(blur, size=(h // 2, w // 2), mode="bilinear", align_corners=False)
-    return y.to(x.dtype)
+    return _Conv.apply(x, w * ops.eq_scale(w), layer.padding, dtype, out_dtype or dtype,
+                       layer.bias if with_bias else None)
 
 
 def discriminator_scores(discriminator, x):
     """The Discriminator forward (reference builder.py:268-287) on the twice-differentiable path."""
     m, dt = discriminator.model, discriminator.act_dtype
-    a = _down(F.leaky_relu(_eq_conv(x, m[0], dt), 0.2))
+    a = _eq_conv(x, m[0], dt, with_bias=True)
+    a = _Down.apply(_NormAct.apply(a, False, ops.ACT_LRELU, dt))
     for idx in (3, 7):
-        a = _down(F.leaky_relu(_instance_norm(_eq_conv(a, m[idx], dt)), 0.2))
-    a = F.leaky_relu(_instance_norm(_eq_conv(a, m[11], dt)), 0.2)
+        a = _Down.apply(_NormAct.apply(_eq_conv(a, m[idx], dt), True, ops.ACT_LRELU, dt))
+    a = _NormAct.apply(_eq_conv(a, m[11], dt), True, ops.ACT_LRELU, dt)
     return _eq_conv(a, m[14], dt, torch.float32)
 
 

@@ -116,7 +116,13 @@ def test_graph_replay_matches_eager_from_the_same_state(dtype):
     grows with the chaos of the training run."""
     from one_to_many_gan_b200.engine import TrainIteration
 
-    size, min_lat, n_res, batch, pool, iters = (32, 32), 16, 3, 2, 5, 8
+    if dtype == torch.float32:
+        size, min_lat, n_res, batch, pool, iters = (32, 32), 16, 3, 2, 5, 8
+    else:
+        # bf16 on the 32x32 / batch-2 model is a coin toss: D ends in a 1x1 score map and the
+        # InstanceNorms of D / S see 2x4-pixel planes, so one flipped rounding moves the GAN loss
+        # by 3 % between two EAGER runs of the same state.  64x64 / batch 4 (5x5 score maps).
+        size, min_lat, n_res, batch, pool, iters = (64, 64), 32, 5, 4, 9, 6
     cfg = _cfg(batch, size, pool)
     shape = (batch, 1, *size)
     dev = torch.device("cuda")
@@ -124,12 +130,12 @@ def test_graph_replay_matches_eager_from_the_same_state(dtype):
     nets_b = _build(size, min_lat, n_res, dtype)
     A = TrainIteration(cfg, dev, *nets_a[:4], *nets_a[4], use_graph=True, warmup=2)
     B = TrainIteration(cfg, dev, *nets_b[:4], *nets_b[4], use_graph=False)
-    tol = 2e-5 if dtype == torch.float32 else 2e-3  # bf16: a flipped rounding moves a loss 1e-3
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
     for it in range(iters):
         _copy_state(A, B)
         B_before = {id(o): o.param_arena.double().clone() for o in (B.oD, B.oG, B.oS)}
         batches = [_images(shape, 10 * (j + 1) + it) for j in range(4)]
-        h = torch.tensor([0.11 + 0.01 * it, 0.19 - 0.01 * it])
+        h = torch.tensor([0.11 + 0.01 * it, 0.19 - 0.01 * it, 0.13, 0.17][:batch])
         outs = []
         for eng in (A, B):
             torch.manual_seed(500 + it)
@@ -138,7 +144,15 @@ def test_graph_replay_matches_eager_from_the_same_state(dtype):
             outs.append(eng.run(h=h))
         got = torch.tensor([outs[0][k] for k in A.LOSS_NAMES], dtype=torch.float64)
         want = torch.tensor([outs[1][k] for k in A.LOSS_NAMES], dtype=torch.float64)
-        torch.testing.assert_close(got, want, rtol=tol, atol=tol, msg=lambda m: f"iteration {it}: {m}")
+        # sign_real / sign_fake are means of sign(): quantised in steps of 2 / (batch * score-map
+        # pixels); in bf16 a score within rounding of 0.5 may flip, so they get 3 quanta
+        n_scores = batch * ((size[0] // 8 - 3) * (size[1] // 8 - 3))
+        quant = torch.full_like(got, tol)
+        if dtype != torch.float32:
+            for k in ("sign_real", "sign_fake"):
+                quant[A.LOSS_NAMES.index(k)] = 3 * 2.0 / n_scores + 1e-6
+        bad = (got - want).abs() > quant + tol * want.abs()
+        assert not bad.any(), f"iteration {it}: {got.tolist()} vs {want.tolist()}"
         for a, b in ((A.oD, B.oD), (A.oG, B.oG), (A.oS, B.oS)):
             # gradients: a LeakyReLU / ReLU mask flip (fp32 atomics order; in bf16 a flipped
             # rounding) moves a gradient of this 32x32, batch-2 model (InstanceNorm over 2x4-pixel

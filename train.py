@@ -46,9 +46,9 @@ def _data_iterators(config, device, rank: int, world: int):
     # (train.py:56-58,139,153): the two folders are shuffled independently; every rank draws the
     # same permutations and takes its own slice of each
     gen = torch.Generator().manual_seed(seed)
-    marks = image_folder_loader(config, "shoemark_data_dir", gen, rank, world)
-    prints = image_folder_loader(config, "shoeprint_data_dir", gen, rank, world)
-    return itertools.cycle(prints), itertools.cycle(marks)
+    marks = image_folder_loader(config, "shoemark_data_dir", gen, rank, world, device)
+    prints = image_folder_loader(config, "shoeprint_data_dir", gen, rank, world, device)
+    return prints, marks  # DeviceImages cycles over epochs itself
 
 
 def main_torch(config):
@@ -92,8 +92,21 @@ def main_torch(config):
                 yield torch.rand(t["batch_size"], data["image_channels"], *data["image_size"], generator=g) * 2 - 1
 
         prints, marks = synth(t["random_seed"]), synth(t["random_seed"] + 1)
-    else:
-        prints, marks = _data_iterators(config, device, 0, 1)
+    else:  # the reference's own dataset + DataLoaders (train.py:120-169)
+        from src.data.datasets import ShoeDataset
+        from torchvision import transforms
+
+        tf = transforms.Compose([transforms.Resize(data["image_size"]), transforms.ToTensor(),
+                                 transforms.Normalize((0.5,), (0.5,))])
+        gen = torch.Generator().manual_seed(t["random_seed"])
+
+        def loader(key):
+            ds = ShoeDataset(data[key], mode="train", transform=tf)
+            return itertools.cycle(torch.utils.data.DataLoader(
+                ds, batch_size=t["batch_size"], shuffle=True, num_workers=8, drop_last=True,
+                pin_memory=True, generator=gen))
+
+        marks, prints = loader("shoemark_data_dir"), loader("shoeprint_data_dir")
     buf = ImageBuffer(t["image_buffer_size"])
     aug = ("xflip", "rotate90", "xint", "scale", "rotate", "aniso", "xfrac", "brightness", "contrast",
            "lumaflip", "hue", "saturation")  # every pipeline stage on, reference train.py:175-188
@@ -233,10 +246,10 @@ def main(config_path: str):
             save_checkpoint(checkpoint_path(config, step + 1), nets=nets, optimisers=opts, ada_p=ada_p,
                             pool_images=eng.pool_images(), pool_size=eng.pool_size, step=step + 1)
     if world > 1:
-        import torch.distributed as dist
+        from one_to_many_gan_b200.optim import shutdown_process_group
 
-        dist.barrier()
-        dist.destroy_process_group()
+        eng.close()
+        shutdown_process_group()
     return eng
 
 
