@@ -93,6 +93,9 @@ __device__ __forceinline__ void tma_store_commit() {
 __device__ __forceinline__ void tma_store_wait_read() {  // staged smem may be overwritten
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_wait_read1() {  // all but the newest group were read
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -157,6 +160,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 16 lanes x 32 columns in the mma C-fragment layout: thread t receives, for every 8-column
+// block k, r[4k+0..1] = (lane t/4, columns 8k + 2(t%4) + {0,1}) and r[4k+2..3] = the same
+// columns of lane t/4 + 8 -- exactly the register layout stmatrix stores, so an accumulator
+// that is TRANSPOSED in TMEM (lane = channel, column = pixel) goes to a pixel-major shared
+// tile with one stmatrix.trans per 4 (8 channel x 8 pixel) blocks instead of 2-byte stores.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.x4.trans.m8n8.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// four transposed 8x8 b16 matrices; lanes 8j .. 8j+7 give the row addresses of matrix j
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c,
+                                                  uint32_t d) {
+  asm volatile("stmatrix.sync.aligned.x4.trans.m8n8.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(saddr),
+               "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
 }
 
 // shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
@@ -685,15 +730,16 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
           const int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
           if (nh * nw > 1) {
-            for (int piece = 0; piece < BN / 8; ++piece) {
-              const uint4 val = *reinterpret_cast<const uint4*>(
-                  myrow + (piece >> 3) * SUB_BYTES + (((piece & 7) ^ sw) << 4));
-              for (int a = 0; a < nh; ++a)
-                for (int b = 0; b < nw; ++b)
-                  if (a + b > 0)
-                    *reinterpret_cast<uint4*>(
-                        vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + piece * 8)) = val;
-            }
+            for (int a = 0; a < nh; ++a)
+              for (int b = 0; b < nw; ++b)
+                if (a + b > 0) {
+                  uint4* dst = reinterpret_cast<uint4*>(
+                      vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0));
+#pragma unroll 4
+                  for (int piece = 0; piece < BN / 8; ++piece)
+                    dst[piece] = *reinterpret_cast<const uint4*>(
+                        myrow + (piece >> 3) * SUB_BYTES + (((piece & 7) ^ sw) << 4));
+                }
           }
         }
       }
@@ -724,7 +770,8 @@ conv_tc_fwd_rr2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 template <int KS, int NA, int NB>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                        const __grid_constant__ CUtensorMap tmY, TcFwdPP pp) {
+                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                        TcFwdPP pp) {
   const TcFwdP& p = pp.p;
   constexpr int BN = 128;  // output channels per tile (the MMA's M)
   constexpr int TW = 8, TH = 16;
@@ -736,18 +783,20 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ringA = smem;
   uint8_t* ringB = ringA + NA * A_SLOT;
-  uint8_t* stage_out = ringB + NB * B_SLOT;
-  uint64_t* bars = (uint64_t*)(stage_out + TILE_BYTES);
+  uint8_t* stage_base = ringB + NB * B_SLOT;  // TWO staging tiles: half-tiles alternate
+  uint64_t* bars = (uint64_t*)(stage_base + 2 * TILE_BYTES);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + NA;
   uint64_t* fullB = emptyA + NA;
   uint64_t* emptyB = fullB + NB;
   uint64_t* tmem_full = emptyB + NB;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;  // [2]
-  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;   // [2] residual half-tile landed in staging tile x
+  uint32_t* tmem_ptr = (uint32_t*)(res_full + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int cin_chunks = p.cin / 64;
+  const bool has_res = p.res.ptr != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -760,6 +809,7 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tmem_full[b]), 1);
       mbar_init(smem_u32(&tmem_empty[b]), 128);
+      mbar_init(smem_u32(&res_full[b]), 1);
     }
     fence_barrier_init();
   }
@@ -855,116 +905,192 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue ----------------
+    // ---------------- epilogue warps: TMEM -> scale/bias/activation -> staged bf16 tile -----
+    // Named barriers (count 192 = 4 epilogue warps + the 2 finishing warps):
+    //   2 + x   stage x is free again (finishing warps arrive, epilogue warps wait)
+    //   4 + x   stage x holds a finished half-tile (epilogue warps arrive, finishing warps wait)
     const int wq = warp - 4;
-    const int te = threadIdx.x - 128;
-    const int m = wq * 32 + lane;  // output channel (TMEM lane) in phase 1, pixel in phase 2
-    int lt = 0;
+    int lt = 0, hc = 0;  // tiles / half-tiles done by this CTA
     for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
       int n, h0, w0, o0;
       decode(t, n, h0, w0, o0);
       const int buf = lt & 1;
-      const float scale = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + o0 + m] : 1.f);
-      const float bias = p.bias ? p.bias[o0 + m] : 0.f;
-      const float post = p.post_scale ? p.post_scale[(long long)n * p.cout + o0 + m] : 1.f;
+      // fragment layout: this thread holds channels wq*32 + 8j + lane/4, j = 0..3
+      float scale[4], bias[4], post[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = o0 + wq * 32 + 8 * j + (lane >> 2);
+        scale[j] = p.alpha * (p.row_scale ? p.row_scale[(long long)n * p.cout + ch] : 1.f);
+        bias[j] = p.bias ? p.bias[ch] : 0.f;
+        post[j] = p.post_scale ? p.post_scale[(long long)n * p.cout + ch] : 1.f;
+      }
       mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
       tc_fence_after();
       const int nhalf = (h0 + TH) < p.y.h ? 2 : 1;
-      // staging address pieces of this thread's channel: [sub-tile of 64 ch][pixel][128 B]
-      uint8_t* const chan_base = stage_out + (m >> 6) * SUB_BYTES + (m & 7) * 2;
-      const int chunk = (m & 63) >> 3;
 #pragma unroll 1
-      for (int half = 0; half < nhalf; ++half) {
-        const int hh0 = h0 + half * TH;
+      for (int half = 0; half < nhalf; ++half, ++hc) {
+        const int x = hc & 1;
+        uint8_t* const stage_out = stage_base + x * TILE_BYTES;
+        // staging tile [sub-tile of 64 ch][pixel][128 B, 16-byte chunks XOR-swizzled by pixel & 7]:
+        // lane = 8j + i addresses row i of matrix j = channels wq*32 + 8j .. + 7 of pixel 8k + i
+        const uint32_t st_base = smem_u32(stage_out) + (uint32_t)((wq >> 1) * SUB_BYTES) +
+                                 (uint32_t)((lane & 7) * 128) +
+                                 (uint32_t)(((((wq & 1) * 4 + (lane >> 3)) ^ (lane & 7))) << 4);
         const uint32_t tacc =
             tmem_base + (uint32_t)(buf * 256 + half * 128) + ((uint32_t)(wq * 32) << 16);
-        // residual: fetched NOW into registers (16 x 16 B per thread = the whole 128-pixel x
-        // 256 B half-tile in flight per CTA), consumed after the transposing stores below, so the
-        // DRAM latency hides behind the TMEM read-out.  Coalesced mapping: a half-warp reads the
-        // 16 pieces of ONE pixel (256 contiguous bytes); warp wq owns pixels wq*32 .. wq*32+31.
-        uint4 rres[16];
-        if (p.res.ptr) {
+        // 32 pixels (TMEM columns) x this warp's 32 channels per step; the next step's TMEM
+        // read is in flight while this one is scaled, packed and stored
+        float va[2][16], vb[2][16];  // lanes +0..15 / +16..31 of the warp's TMEM window
+        tmem_ld_16x256b_x4(tacc, va[0]);
+        tmem_ld_16x256b_x4(tacc + (16u << 16), vb[0]);
+        // the finishing warps are done with this staging tile (its TMA store has read it) ...
+        asm volatile("bar.sync %0, 192;" ::"r"(2 + x) : "memory");
+        // ... and this half-tile's residual has been bulk-copied into it
+        if (has_res) mbar_wait(smem_u32(&res_full[x]), (hc >> 1) & 1);
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            const int q = wq * 32 + it * 2 + (lane >> 4);
-            const int qh = hh0 + q / TW, qw = w0 + q % TW;
-            rres[it] = (qh < p.y.h && qw < p.y.w)
-                           ? *reinterpret_cast<const uint4*>(
-                                 vptr<__nv_bfloat16>(p.res, n, qh, qw, o0 + (lane & 15) * 8))
-                           : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-        // the previous TMA store must have finished reading the staging tile
-        if (te == 0) tma_store_wait_read();
-        asm volatile("bar.sync 3, 128;" ::: "memory");
-#pragma unroll 1
         for (int j2 = 0; j2 < 4; ++j2) {
-          float v[32];
-          tmem_ld32(tacc + (uint32_t)(j2 * 32), v);
+          float (&xa)[16] = va[j2 & 1];
+          float (&xb)[16] = vb[j2 & 1];
+          tmem_ld_wait();
+          if (j2 < 3) {
+            tmem_ld_16x256b_x4(tacc + (uint32_t)((j2 + 1) * 32), va[(j2 + 1) & 1]);
+            tmem_ld_16x256b_x4(tacc + (uint32_t)((j2 + 1) * 32) + (16u << 16), vb[(j2 + 1) & 1]);
+          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], scale, bias);
-          act_fwd_vec<32>(v, p.act);
+          for (int k = 0; k < 4; ++k) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int q = j2 * 32 + i;  // pixel of this half-tile
-            *reinterpret_cast<__nv_bfloat16*>(chan_base + q * 128 + ((chunk ^ (q & 7)) << 4)) =
-                __float2bfloat16_rn(v[i] * post);
+            for (int e = 0; e < 2; ++e) {
+              xa[4 * k + e] = fmaf(xa[4 * k + e], scale[0], bias[0]);
+              xa[4 * k + 2 + e] = fmaf(xa[4 * k + 2 + e], scale[1], bias[1]);
+              xb[4 * k + e] = fmaf(xb[4 * k + e], scale[2], bias[2]);
+              xb[4 * k + 2 + e] = fmaf(xb[4 * k + 2 + e], scale[3], bias[3]);
+            }
+          }
+          act_fwd_vec<16>(xa, p.act);
+          act_fwd_vec<16>(xb, p.act);
+          if (p.post_scale) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                xa[4 * k + e] *= post[0];
+                xa[4 * k + 2 + e] *= post[1];
+                xb[4 * k + e] *= post[2];
+                xb[4 * k + 2 + e] *= post[3];
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t sa = st_base + (uint32_t)((j2 * 32 + k * 8) * 128);
+            uint32_t o[4] = {pack_bf16x2(xa[4 * k], xa[4 * k + 1]), pack_bf16x2(xa[4 * k + 2], xa[4 * k + 3]),
+                             pack_bf16x2(xb[4 * k], xb[4 * k + 1]), pack_bf16x2(xb[4 * k + 2], xb[4 * k + 3])};
+            if (has_res) {
+              // the staged residual comes back in the very fragment layout that is stored:
+              // same warp, same addresses, read before written
+              uint32_t rr[4];
+              ldmatrix_x4_trans(sa, rr);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = hadd2_bf16(o[e], rr[e]);  // one rounding
+            }
+            stmatrix_x4_trans(sa, o[0], o[1], o[2], o[3]);
           }
         }
+        // the TMA store (async proxy) is issued by a finishing warp after this barrier
+        fence_proxy_async();
+        asm volatile("bar.arrive %0, 192;" ::"r"(4 + x) : "memory");
         tc_fence_before();
         if (half == nhalf - 1) mbar_arrive(smem_u32(&tmem_empty[buf]));  // accumulator drained
-        // phase 2: thread = pixel row of the staged tile
-        const int oh = hh0 + m / TW, ow = w0 + m % TW;
-        const bool valid = (oh < p.y.h) && (ow < p.y.w);
-        uint8_t* myrow = stage_out + m * 128;
-        const int sw = m & 7;
-        if (p.res.ptr) {
-          asm volatile("bar.sync 2, 128;" ::: "memory");  // staged tile complete
-          const int piece = lane & 15;
+      }
+    }
+  } else if (warp >= 2) {
+    // ---------------- finishing warps (2 and 3): TMA store, reflect halo, residual load -------
+    // They run one staging tile behind the epilogue warps and off its critical path.  The
+    // residual of half-tile hc + 2 is bulk-copied (TMA, same SWIZZLE_128B box as the store) into
+    // staging tile x as soon as half-tile hc's store has read it: it has a whole half-tile period
+    // to arrive, costs no registers and no LSU traffic, and the epilogue warps add it with
+    // ldmatrix / packed-bf16 add / stmatrix in place.
+    const int ht = threadIdx.x - 64;  // 0 .. 63
+    // (tile, half) of the residual to load next: two half-tiles ahead of the one being finished
+    int rt = blockIdx.x, rhalf = 0;
+    auto load_residual = [&](int x) {  // one thread
+      if (rt >= pp.total_tiles) return;
+      int n, h0, w0, o0;
+      decode(rt, n, h0, w0, o0);
+      const uint32_t bar = smem_u32(&res_full[x]);
+      mbar_expect_tx(bar, TILE_BYTES);
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            const int q = wq * 32 + it * 2 + (lane >> 4);
-            uint4* sp = reinterpret_cast<uint4*>(stage_out + q * 128 + (piece >> 3) * SUB_BYTES +
-                                                 (((piece & 7) ^ (q & 7)) << 4));
-            uint4 a = *sp;
-            __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a);
-            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rres[it]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
-              a2[e] = __floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y);
-            }
-            *sp = a;
-          }
-          __syncwarp();  // the halo stores below read this warp's own 32 pixel rows
-        }
-        fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (te == 0 && hh0 < p.y.h) {
+      for (int sb = 0; sb < BN / 64; ++sb)
+        tma_load_4d(smem_u32(stage_base + x * TILE_BYTES + sb * SUB_BYTES), &tmR, bar, o0 + sb * 64, w0,
+                    h0 + rhalf * TH, n);
+      if (rhalf == 0 && (h0 + TH) < p.y.h) rhalf = 1;
+      else { rhalf = 0; rt += gridDim.x; }
+    };
+    if (has_res && ht == 0) {
+      tma_prefetch_desc(&tmR);
+      load_residual(0);
+      load_residual(1);
+    }
+    __syncwarp();
+    // both staging tiles start out free
+    asm volatile("bar.arrive 2, 192;" ::: "memory");
+    asm volatile("bar.arrive 3, 192;" ::: "memory");
+    int hc = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+      int n, h0, w0, o0;
+      decode(t, n, h0, w0, o0);
+      const int nhalf = (h0 + TH) < p.y.h ? 2 : 1;
+#pragma unroll 1
+      for (int half = 0; half < nhalf; ++half, ++hc) {
+        const int x = hc & 1;
+        const int hh0 = h0 + half * TH;
+        uint8_t* const stage_out = stage_base + x * TILE_BYTES;
+        asm volatile("bar.sync %0, 192;" ::"r"(4 + x) : "memory");  // half-tile staged
+        if (ht == 0) {
 #pragma unroll
           for (int sb = 0; sb < BN / 64; ++sb)
             tma_store_4d(&tmY, smem_u32(stage_out + sb * SUB_BYTES), o0 + sb * 64, w0, hh0, n);
           tma_store_commit();
         }
-        if (p.y_halo > 0 && valid) {
-          int hs[3], ws[3];
-          const int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
-          const int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
-          if (nh * nw > 1) {
-            for (int piece = 0; piece < BN / 8; ++piece) {
-              const uint4 val = *reinterpret_cast<const uint4*>(
-                  myrow + (piece >> 3) * SUB_BYTES + (((piece & 7) ^ sw) << 4));
-              for (int a = 0; a < nh; ++a)
-                for (int b = 0; b < nw; ++b)
-                  if (a + b > 0)
-                    *reinterpret_cast<uint4*>(
-                        vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0 + piece * 8)) = val;
+        if (p.y_halo > 0) {
+          // reflect border: staged pixel rows ht and ht + 64 (second stores of interior pixels)
+#pragma unroll 1
+          for (int r = 0; r < 2; ++r) {
+            const int m = ht + 64 * r;
+            const int oh = hh0 + m / TW, ow = w0 + m % TW;
+            if (oh < p.y.h && ow < p.y.w) {
+              int hs[3], ws[3];
+              const int nh = mirror_set(oh, p.y.h, p.y_halo, hs);
+              const int nw = mirror_set(ow, p.y.w, p.y_halo, ws);
+              if (nh * nw > 1) {
+                const uint8_t* myrow = stage_out + m * 128;
+                const int sw = m & 7;
+                for (int a = 0; a < nh; ++a)
+                  for (int b = 0; b < nw; ++b)
+                    if (a + b > 0) {
+                      uint4* dst = reinterpret_cast<uint4*>(
+                          vptr_mut<__nv_bfloat16>(p.y, n, hs[a], ws[b], o0));
+#pragma unroll 4
+                      for (int pc = 0; pc < BN / 8; ++pc)
+                        dst[pc] = *reinterpret_cast<const uint4*>(
+                            myrow + (pc >> 3) * SUB_BYTES + (((pc & 7) ^ sw) << 4));
+                    }
+              }
             }
           }
         }
+        // both warps are done reading the staged rows; once the TMA store has read the tile too
+        // it takes the residual of half-tile hc + 2 and is handed back to the epilogue warps
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (ht == 0) {
+          tma_store_wait_read();
+          if (has_res) load_residual(x);
+        }
+        __syncwarp();
+        asm volatile("bar.arrive %0, 192;" ::"r"(2 + x) : "memory");
       }
     }
-    if (te == 0) tma_store_wait_all();
+    if (ht == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -1270,12 +1396,12 @@ static int launch_fwd_rr2(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 
 template <int KS, int NA, int NB>
 static int launch_fwd_rr2t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
-                           const TcFwdPP& pp, int ctas, cudaStream_t st) {
-  constexpr int smem = NA * (32 + KS - 1) * 8 * 128 + NB * 128 * 128 + 2 * 128 * 128 + 1024 + 512;
+                           const CUtensorMap& tmR, const TcFwdPP& pp, int ctas, cudaStream_t st) {
+  constexpr int smem = NA * (32 + KS - 1) * 8 * 128 + NB * 128 * 128 + 2 * (2 * 128 * 128) + 1024 + 512;
   static_assert(smem <= 227 * 1024, "transposed pair conv kernel exceeds shared memory");
   auto kern = conv_tc_fwd_rr2t_kernel<KS, NA, NB>;
   OTM_ENSURE_SMEM(kern, smem);
-  kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, pp);
+  kern<<<ctas, 256, smem, st>>>(tmA, tmB, tmY, tmR, pp);
   OTM_LAUNCH_CHECK();
   return OTM_OK;
 }
@@ -1325,8 +1451,13 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
       CUtensorMap tmA2;
       rc = make_act_map(&tmA2, a->x, a->x_halo, TW, 2 * TH + KS - 1);
       if (rc) return rc;
-      if (KS == 3) return launch_fwd_rr2t<3, 2, 6>(tmA2, tmB, tmY, pp, ctas, st);
-      return launch_fwd_rr2t<4, 2, 6>(tmA2, tmB, tmY, pp, ctas, st);
+      CUtensorMap tmR = tmY;  // residual: same boxes as the output tile, its own strides
+      if (a->residual.ptr) {
+        rc = make_act_map(&tmR, a->residual, 0, TW, TH);
+        if (rc) return rc;
+      }
+      if (KS == 3) return launch_fwd_rr2t<3, 2, 4>(tmA2, tmB, tmY, tmR, pp, ctas, st);
+      return launch_fwd_rr2t<4, 2, 4>(tmA2, tmB, tmY, tmR, pp, ctas, st);
     }
     if (KS == 3) return launch_fwd_rr2<64, 3, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
     return launch_fwd_rr2<64, 4, 3, 8>(tmA, tmB, tmY, pp, ctas, st);
