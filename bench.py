@@ -45,7 +45,7 @@ WORKLOAD = "G+D train iteration, default arch, 128x128, batch 32/GPU, bf16 act /
 # dense-conv algorithmic GFLOP per image per iteration for the extra configs
 GFLOP_256 = 1441.2
 # dram bytes (read + write) of the roofline launch from the committed ncu capture, or None
-NCU_TRAFFIC_SHARED = None
+NCU_TRAFFIC_RESIDUAL = None
 
 
 def base_config(world):
@@ -200,13 +200,13 @@ def time_steps(step, prints, marks, steps, warmup, dist_on, device):
 
 def dominant_kernel_roofline(device):
     """The 3x3 128->128 conv at 64x64 is ~69 % of the dense MACs of this workload
-    and `conv_tc_fwd_rr2t_kernel<3,2,6>` runs all of them (forward and dgrad).  Its most frequent
-    launch is timed alone -- CUDA events on the launching stream, L2 flushed between launches --
-    against the measured burst peak: the SHARED-weight form (42 of the 62 launches per iteration
-    since the modulation moved into the producers' epilogues: conv2 of a ModulatedResnetBlock
-    with its demodulation row scale, residual add and reflect halo, n = 96 = the 3B decode batch).
-    The per-sample-weight form that is left (conv1 of the block: per-sample packs, ReLU, the
-    next conv's style scale as post-activation scale) is reported next to it."""
+    and `conv_tc_fwd_rr2t_kernel<3,2,4>` runs all of them (forward and dgrad, 62 launches per
+    iteration).  Its heaviest form is timed alone -- CUDA events on the launching stream, L2
+    flushed between launches -- against the measured burst peak: conv2 of a ModulatedResnetBlock
+    (shared weights, demodulation row scale, residual add, reflect halo) at n = 96 = the 3B decode
+    batch.  The other two forms it is launched in are timed the same way and reported next to it
+    with their launch counts: conv1 of the block (per-sample weight packs, ReLU, the next conv's
+    style scale as post-activation scale, halo) and the bare shared-weight form (dgrad)."""
     import math
 
     from one_to_many_gan_b200 import kernels as K
@@ -226,12 +226,15 @@ def dominant_kernel_roofline(device):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     flops = 2.0 * n * hw * hw * c * c * 9
 
-    def shared():  # conv2: y = x_res + sigma_inv * conv(h~, cW)
+    def residual():  # conv2: y = x_res + sigma_inv * conv(h~, cW)
         K.conv_fwd(x, wp_shared, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, residual=res, out=y)
 
     def per_sample():  # conv1: h~ = s2 * relu(sigma_inv * conv(x, cW * s1))
         K.conv_fwd(x, wp_sample, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, act=K.ACT_RELU,
                    post_scale=s, per_sample=True, out=y)
+
+    def plain():  # dgrad: shared flipped pack, no epilogue work
+        K.conv_fwd(x, wp_shared, c, 3, 3, 1, x_halo=1, out=y)
 
     def timed(fn):
         fn()
@@ -247,24 +250,26 @@ def dominant_kernel_roofline(device):
             ts.append(a.elapsed_time(b))
         return statistics.mean(ts)
 
-    ms, ms_ps = timed(shared), timed(per_sample)
     pk, how = peaks()
-    ach, ach_ps = flops / ms / 1e9, flops / ms_ps / 1e9
+    peak = pk["bf16_tflops"]
+    ms = timed(residual)
+    ach = flops / ms / 1e9
+    forms = {}
+    for name, fn, cnt in (("per_sample_weights_relu_poststyle_halo", per_sample, 20),
+                          ("shared_weights_bare", plain, 30)):
+        t = timed(fn)
+        forms[name] = {"achieved": round(flops / t / 1e9, 1), "frac": round(flops / t / 1e9 / peak, 4),
+                       "launch_ms": round(t, 4), "launches_per_iteration": cnt}
     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from `ncu --set full`
-    # (profiles/r2_ncu_conv_tc_fwd_rr2t_shared.md); algorithmic bytes = x (107 MB) + residual
+    # (profiles/r2_ncu_conv_tc_fwd_rr2t_residual.md); algorithmic bytes = x (107 MB) + residual
     # (101 MB) + y (107 MB) + weights (0.3 MB) = 315 MB.
-    traffic = NCU_TRAFFIC_SHARED
     return {"bound": "tensor",
-            "kernel": "conv_tc_fwd_rr2t_kernel<3,2,6>: shared-weight 3x3 128->128 @64x64, n=96 "
+            "kernel": "conv_tc_fwd_rr2t_kernel<3,2,4>: shared-weight 3x3 128->128 @64x64, n=96 "
                       "(+demodulation row scale, residual add, reflect halo)",
-            "achieved": round(ach, 1), "peak": pk["bf16_tflops"], "peak_source": how + " burst",
-            "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops"], 4), "traffic": traffic,
-            "launch_ms": round(ms, 4), "flops_per_launch": flops,
-            "per_sample_weights_form": {"achieved": round(ach_ps, 1),
-                                        "frac": round(ach_ps / pk["bf16_tflops"], 4),
-                                        "launch_ms": round(ms_ps, 4),
-                                        "what": "per-sample packs + ReLU + post-activation style scale "
-                                                "(conv1 of a ModulatedResnetBlock; 20 of 62 launches)"}}
+            "achieved": round(ach, 1), "peak": peak, "peak_source": how + " burst",
+            "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": NCU_TRAFFIC_RESIDUAL,
+            "launch_ms": round(ms, 4), "flops_per_launch": flops, "launches_per_iteration": 12,
+            "other_forms": forms}
 
 
 def hbm_kernel_roofline(device):

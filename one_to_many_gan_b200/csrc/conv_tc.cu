@@ -1294,6 +1294,266 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
 }
 
 // ---------------------------------------------------------------------------
+// wgrad, filter-column form (3x3, Cout % 128 == 0, Cin % 128 == 0): the heavy weight gradients
+// ---------------------------------------------------------------------------
+// The one-tap-per-CTA kernel above uses every operand byte it stages exactly once: per K = 64
+// pixels it WRITES 32 KB into shared memory (TMA) and READS 32 KB (four 128x128x16 MMAs), 256
+// B/clk against the SM's 128 B/clk -- ncu shows the tensor pipe at 51 %.  Here a CTA owns one
+// FILTER COLUMN s of a (128 cout x 128 cin) block, i.e. the three taps (r, s), r = 0..2:
+//   * a K-group of 8 pixels is one image-row segment = one 1024-byte swizzle atom, the 8 rows of
+//     a pixel tile are consecutive atoms (the layout the one-tap kernel already uses);
+//   * the x box holds 10 rows x 8 columns; tap r reads pixel rows r .. r+7, i.e. the SAME bytes
+//     at an atom-aligned offset of r KB.  With LBO = SBO = 1024 the three taps are the three
+//     64-channel "chunks" of ONE MN-major B operand: a 128 x 192 x 16 MMA per 64 input channels
+//     computes all three taps and the dy tile is read once for them;
+//   * accumulators: 2 channel chunks x 192 columns in TMEM.
+// Per 64 pixels: 36 KB staged, 80 KB read by eight 96-cycle MMAs = 151 B/clk (was 256).
+// Persistent, stream-K: the (sample, block, filter column) items x pixel tiles are one sequence
+// cut into equal ranges, one per CTA; a CTA flushes its accumulator (per-sample row / column
+// factors, fused P term, bulk reduce-add into the fp32 workspace) whenever the item changes, so
+// any batch size balances.  Measured (n = 96, 128 -> 128 @ 64x64): 116 us = 1.0 PFLOP/s; the
+// main loop alone 1.25-1.3.  A double-buffered 192-column variant (64 input channels per CTA, the
+// flush hidden) stages 45 % more bytes per MMA and ran at 152 us: the staging traffic, not the
+// flush, is what binds.
+struct TcWgRowP {
+  float* ws;                  // [tap][cout][cin] fp32
+  const __nv_bfloat16* wfwd;  // forward pack [n | 1][cout][taps][cin] (fused P term) or NULL
+  float* P;                   // [n][cout]
+  const float* rs;            // [n][cout] or NULL
+  const float* cs;            // [n][cin] or NULL
+  float alpha;
+  int cin, cout;
+  int x_coord_off;            // x_halo - pad
+  int tiles_w, tiles_total;   // 8x8 pixel tiles of the dy image
+  int m_tiles, n_tiles;       // cout / 128, cin / 128
+  long long units_total;      // items * tiles_total
+  long long wfwd_n_stride;
+};
+
+constexpr int WGR_STAGES = 4;
+constexpr int WGR_A_BYTES = 2 * 8 * 1024;        // dy: 2 chunks x 8 pixel rows x 1 KB
+constexpr int WGR_B_CHUNK = 10 * 1024;           // x: 10 pixel rows x 1 KB per 64 channels
+constexpr int WGR_STAGE_BYTES = WGR_A_BYTES + 2 * WGR_B_CHUNK;
+constexpr int WGR_RED_PITCH = 256 + 16;          // one thread's 64 fp32 partial sums (+ bank skew)
+constexpr int WGR_RED_BYTES = 256 * WGR_RED_PITCH;  // one row per epilogue thread
+
+__global__ void __launch_bounds__(384, 1)
+conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDy,
+                         const __grid_constant__ CUtensorMap tmX, TcWgRowP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_red = smem + WGR_STAGES * WGR_STAGE_BYTES;  // staging rows + cs_s[128]
+  uint64_t* bars = (uint64_t*)(stage_red + WGR_RED_BYTES + 512);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + WGR_STAGES;
+  uint64_t* accum_full = bars + 2 * WGR_STAGES;
+  uint64_t* accum_empty = accum_full + 1;
+  uint32_t* tmem_ptr = (uint32_t*)(accum_empty + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int st = 0; st < WGR_STAGES; ++st) {
+      mbar_init(smem_u32(&full[st]), 1);
+      mbar_init(smem_u32(&empty[st]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    mbar_init(smem_u32(accum_empty), 256);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // this CTA's range of (item, tile) units; item = ((n * m_tiles + mt) * n_tiles + nt) * 3 + fs
+  const long long u_beg = p.units_total * blockIdx.x / gridDim.x;
+  const long long u_end = p.units_total * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    int it = 0;
+    long long u = u_beg;
+    while (u < u_end) {
+      const long long item = u / p.tiles_total;
+      const int t0 = (int)(u - item * p.tiles_total);
+      const int t1 = (int)min((long long)p.tiles_total, t0 + (u_end - u));
+      const int fs = (int)(item % 3);  // filter column
+      long long rest = item / 3;
+      const int nt = (int)(rest % p.n_tiles); rest /= p.n_tiles;
+      const int mt = (int)(rest % p.m_tiles);
+      const int n = (int)(rest / p.m_tiles);
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int stage = it % WGR_STAGES;
+        mbar_wait(smem_u32(&empty[stage]), ((it / WGR_STAGES) & 1) ^ 1);
+        if (lane == 0) {
+          const int h0 = (t / p.tiles_w) * 8, w0 = (t % p.tiles_w) * 8;
+          const uint32_t bar = smem_u32(&full[stage]);
+          const uint32_t sa = smem_u32(smem + stage * WGR_STAGE_BYTES);
+          mbar_expect_tx(bar, WGR_STAGE_BYTES);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            tma_load_4d(sa + c * (WGR_A_BYTES / 2), &tmDy, bar, mt * 128 + c * 64, w0, h0, n);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)  // 8 pixel columns from w0 + fs, 10 pixel rows from h0
+            tma_load_4d(sa + WGR_A_BYTES + c * WGR_B_CHUNK, &tmX, bar, nt * 128 + c * 64,
+                        w0 + fs + p.x_coord_off, h0 + p.x_coord_off, n);
+        }
+        __syncwarp();
+      }
+      u += t1 - t0;
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = make_idesc(128, 192, 1, 1);
+    int it = 0, seg = 0;
+    long long u = u_beg;
+    while (u < u_end) {
+      const long long item = u / p.tiles_total;
+      const int t0 = (int)(u - item * p.tiles_total);
+      const int t1 = (int)min((long long)p.tiles_total, t0 + (u_end - u));
+      mbar_wait(smem_u32(accum_empty), (seg & 1) ^ 1);  // previous segment flushed
+      tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int stage = it % WGR_STAGES;
+        mbar_wait(smem_u32(&full[stage]), (it / WGR_STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * WGR_STAGE_BYTES);
+          // MN-major SW128.  A: LBO = next 64 couts (8 KB), SBO = next 8 pixels (1 KB).
+          // B: LBO = next TAP (the same pixels one row down = 1 KB), SBO = next 8 pixels (1 KB).
+          const uint64_t da = make_desc(sa, WGR_A_BYTES / 2, 1024);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint64_t db = make_desc(sa + WGR_A_BYTES + c * WGR_B_CHUNK, 1024, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 16 pixels (K) = 2 pixel rows = 2048 B per step
+              umma_bf16(tmem_base + (uint32_t)(c * 192), da + (uint64_t)(k * 128),
+                        db + (uint64_t)(k * 128), idesc, (t > t0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty[stage]));
+          if (t == t1 - 1) umma_commit(smem_u32(accum_full));
+        }
+        __syncwarp();
+      }
+      u += t1 - t0;
+      ++seg;
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: flush one segment (8 warps) ----------------
+    // Warps 4-7 drain channel chunk 0 (TMEM columns 0..191), warps 8-11 chunk 1; thread =
+    // output channel (TMEM lane).  Per filter row the 64 scaled partial sums of a thread go to
+    // ITS OWN 256-byte row of a staging tile, one 128-byte half at a time, and from there to the
+    // fp32 workspace with bulk reduce-adds (cp.reduce.async.bulk .add.f32: the L2 adds whole
+    // sectors) instead of scattered 16-byte reds through the LSU; the two halves alternate, so a
+    // half is rewritten only after its reduce has read it.  The per-sample column factors come
+    // from shared memory and the forward weights of the fused P term are fetched one filter row
+    // ahead: no global-load latency sits between the TMEM reads.
+    const int te = threadIdx.x - 128;   // 0 .. 255
+    const int c = te >> 7;              // channel chunk of this warpgroup
+    const int lane_m = te & 127;        // TMEM lane
+    const int wq = warp & 3;
+    float* cs_s = reinterpret_cast<float*>(stage_red + WGR_RED_BYTES);  // [128]
+    uint8_t* row = stage_red + te * WGR_RED_PITCH;
+    int seg = 0;
+    long long u = u_beg;
+    while (u < u_end) {
+      const long long item = u / p.tiles_total;
+      const int t0 = (int)(u - item * p.tiles_total);
+      const int t1 = (int)min((long long)p.tiles_total, t0 + (u_end - u));
+      const int fs = (int)(item % 3);
+      long long rest = item / 3;
+      const int nt = (int)(rest % p.n_tiles); rest /= p.n_tiles;
+      const int mt = (int)(rest % p.m_tiles);
+      const int n = (int)(rest / p.m_tiles);
+      const int m = mt * 128 + lane_m;  // cout
+      const float rsv = p.rs ? p.rs[(long long)n * p.cout + m] : 1.f;
+      const float rowf = p.alpha * rsv;
+      // the previous segment's flush has read cs_s (barrier at its end)
+      if (te < 128) cs_s[te] = p.cs ? p.cs[(long long)n * p.cin + nt * 128 + te] : 1.f;
+      const __nv_bfloat16* wbase =
+          p.P ? p.wfwd + (long long)n * p.wfwd_n_stride + (long long)m * 9 * p.cin + nt * 128 + c * 64
+              : nullptr;
+      uint4 wnext[8];
+      if (wbase) {  // filter row 0: tap fs
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          wnext[i] = *reinterpret_cast<const uint4*>(wbase + (long long)fs * p.cin + i * 8);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // cs_s complete
+      mbar_wait(smem_u32(accum_full), seg & 1);
+      tc_fence_after();
+      float pacc = 0.f;  // sum_i G[o,i,tap] * wfwd[n][o][tap][i] over this thread's columns
+#pragma unroll 1
+      for (int fr = 0; fr < 3; ++fr) {  // filter row of this accumulator group
+        const int tap = fr * 3 + fs;
+        uint4 wcur[8];
+        if (wbase) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wcur[i] = wnext[i];
+          if (fr < 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              wnext[i] = *reinterpret_cast<const uint4*>(wbase + (long long)((fr + 1) * 3 + fs) * p.cin + i * 8);
+          }
+        }
+        float* dst = p.ws + ((long long)tap * p.cout + m) * p.cin + nt * 128 + c * 64;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {  // 32 columns = one 128-byte half row
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c * 192 + fr * 64 + hf * 32), v);
+          if (wbase) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __nv_bfloat162* wp2 = reinterpret_cast<const __nv_bfloat162*>(&wcur[4 * hf + k]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 wf = __bfloat1622float2(wp2[i]);
+                pacc = fmaf(v[8 * k + 2 * i], wf.x, fmaf(v[8 * k + 2 * i + 1], wf.y, pacc));
+              }
+            }
+          }
+          // the bulk reduce issued from this half row one filter row ago has read it
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          const float4* cp = reinterpret_cast<const float4*>(cs_s + c * 64 + hf * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 tq = cp[q];
+            reinterpret_cast<float4*>(row + hf * 128)[q] =
+                make_float4(v[4 * q] * tq.x * rowf, v[4 * q + 1] * tq.y * rowf,
+                            v[4 * q + 2] * tq.z * rowf, v[4 * q + 3] * tq.w * rowf);
+          }
+          fence_proxy_async();  // this thread's half row: generic writes -> read by the bulk reduce
+          asm volatile(
+              "cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(
+                  dst + hf * 32),
+              "r"(smem_u32(row + hf * 128))
+              : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(accum_empty));  // accumulator drained: the next segment may start
+      if (p.P) atomicAdd(p.P + (long long)n * p.cout + m, pacc * rsv);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // everybody has read cs_s
+      u += t1 - t0;
+      ++seg;
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1507,7 +1767,46 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
   return OTM_OK;
 }
 
+static void launch_wgrad_fold(float* ws, float* dw, int cout, int cin, int taps, int a_is_x,
+                              cudaStream_t st);
+
+// filter-row kernel: 3x3, both channel counts multiples of 128, a workspace to reduce into
+static bool wgrad_row_eligible(const otm_conv_wgrad_args* a) {
+  return a->kh == 3 && a->kw == 3 && a->x.c % 128 == 0 && a->dy.c % 128 == 0 && a->ws != nullptr;
+}
+
+static int conv_wgrad_tc_row(const otm_conv_wgrad_args* a, cudaStream_t st) {
+  const int cin = a->x.c, cout = a->dy.c;
+  TcWgRowP p;
+  p.ws = a->ws; p.wfwd = (const __nv_bfloat16*)a->wfwd; p.P = a->P; p.rs = a->rs; p.cs = a->cs;
+  p.alpha = a->alpha; p.cin = cin; p.cout = cout;
+  p.x_coord_off = a->x_halo - a->pad;
+  p.tiles_w = (a->dy.w + 7) / 8;
+  p.tiles_total = p.tiles_w * ((a->dy.h + 7) / 8);
+  p.m_tiles = cout / 128; p.n_tiles = cin / 128;
+  p.units_total = (long long)a->dy.n * p.m_tiles * p.n_tiles * 3 * p.tiles_total;
+  p.wfwd_n_stride = a->wfwd_batch_stride;
+  if (p.P) OTM_REQUIRE(p.wfwd, "conv_wgrad: fused P needs wfwd");
+  CUtensorMap tmX, tmDy;
+  int rc = make_act_map(&tmX, a->x, a->x_halo, 8, 10);
+  if (rc) return rc;
+  rc = make_act_map(&tmDy, a->dy, 0, 8, 8);
+  if (rc) return rc;
+  OTM_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, sizeof(float) * (size_t)9 * cin * cout, st));
+  constexpr int smem = WGR_STAGES * WGR_STAGE_BYTES + WGR_RED_BYTES + 512 + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "filter-column wgrad ring exceeds shared memory");
+  auto kern = conv_tc_wgrad_row_kernel;
+  OTM_ENSURE_SMEM(kern, smem);
+  long long ctas = num_sms();
+  if (ctas > p.units_total) ctas = p.units_total;
+  kern<<<(int)ctas, 384, smem, st>>>(tmDy, tmX, p);
+  OTM_LAUNCH_CHECK();
+  launch_wgrad_fold(p.ws, a->dw, cout, cin, 9, 0, st);
+  return OTM_OK;
+}
+
 int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
+  if (wgrad_row_eligible(a)) return conv_wgrad_tc_row(a, st);
   const int cin = a->x.c, cout = a->dy.c;
   TcWgP p;
   p.dw = a->dw; p.rs = a->rs; p.cs = a->cs; p.alpha = a->alpha;
@@ -1566,14 +1865,17 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
     rc = launch_wgrad<256, 2, 2, 1>(tmA, tmB, p, grid, st);
   }
   if (rc) return rc;
-  if (p.ws) {
-    const long long total = (long long)taps * cin * cout;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    wgrad_fold_kernel<<<blocks, 256, 0, st>>>(p.ws, p.dw, cout, cin, taps, p.a_is_x);
-    OTM_LAUNCH_CHECK();
-  }
+  if (p.ws) launch_wgrad_fold(p.ws, p.dw, cout, cin, taps, p.a_is_x, st);
   return OTM_OK;
+}
+
+static void launch_wgrad_fold(float* ws, float* dw, int cout, int cin, int taps, int a_is_x,
+                              cudaStream_t st) {
+  const long long total = (long long)taps * cin * cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  wgrad_fold_kernel<<<blocks, 256, 0, st>>>(ws, dw, cout, cin, taps, a_is_x);
+  g_launches.fetch_add(1);
 }
 
 int conv_fwd_simt(const otm_conv_fwd_args* a, cudaStream_t st);
