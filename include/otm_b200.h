@@ -89,10 +89,17 @@ typedef struct {
   otm_tensor residual;    /* ptr NULL = none */
   int32_t path;           /* otm_path */
   const float* post_scale; /* [n, Cout] or NULL */
+  float* stat_sums;       /* [n, Cout, 2] fp32 or NULL: the epilogue also accumulates sum(y) and
+                           * sum(y^2) per (n, channel) -- the InstanceNorm statistics of the
+                           * consumer (reference blocks.py:23,27; nn.InstanceNorm2d) without a
+                           * separate read of y.  Zeroed by this call.  Only when
+                           * otm_conv_fwd_fuses_stats() says so; finish with otm_instnorm_finalize. */
 } otm_conv_fwd_args;
 int otm_conv_fwd(const otm_conv_fwd_args* a, otm_stream stream);
 /* 1 if the tcgen05 path would be used for these arguments, 0 if SIMT */
 int otm_conv_fwd_uses_tcgen05(const otm_conv_fwd_args* a);
+/* 1 if this call would run on the kernel whose epilogue can accumulate stat_sums */
+int otm_conv_fwd_fuses_stats(const otm_conv_fwd_args* a);
 
 /* wgrad:  dw[o][i][r][s] (fp32, torch parameter layout [Cout,Cin,kh,kw], ACCUMULATED into)
  *   += alpha * sum_{n,h,w} rs[n,o] * cs[n,i] * dy[n,h,w,o] * x[n, h+r-pad, w+s-pad, i]
@@ -180,6 +187,10 @@ int otm_mod_bwd(const otm_mod_bwd_args* a, otm_stream stream);
  * builder.py:161-176,268-284.
  * --------------------------------------------------------------------------------- */
 /* stats[n,c,0..1] = (mean, rstd) over h*w of x.  ws: fp32 workspace [n*c*2], zeroed here. */
+/* stats[i,0..1] = (mean, rstd) from sums[i,0..1] = (sum, sum of squares) over hw elements,
+ * i < count = n * c (the sums a conv epilogue accumulated, otm_conv_fwd_args.stat_sums). */
+int otm_instnorm_finalize(const float* sums, float* stats, int32_t count, int32_t hw, float eps,
+                          otm_stream stream);
 int otm_instnorm_stats(const otm_tensor* x, float eps, float* ws, float* stats,
                        otm_stream stream);
 /* y = act((x - mean) * rstd) + residual, optional reflect halo of width y_halo around y.

@@ -52,6 +52,7 @@ class ConvFwdArgs(C.Structure):
         ("residual", Tensor),
         ("path", C.c_int32),
         ("post_scale", C.c_void_p),
+        ("stat_sums", C.c_void_p),
     ]
 
 
@@ -240,6 +241,7 @@ SYMBOLS = {
     "otm_launch_count": (C.c_int64, []),
     "otm_conv_fwd": (C.c_int, [_P(ConvFwdArgs), C.c_void_p]),
     "otm_conv_fwd_uses_tcgen05": (C.c_int, [_P(ConvFwdArgs)]),
+    "otm_conv_fwd_fuses_stats": (C.c_int, [_P(ConvFwdArgs)]),
     "otm_conv_wgrad": (C.c_int, [_P(ConvWgradArgs), C.c_void_p]),
     "otm_conv_wgrad_uses_tcgen05": (C.c_int, [_P(ConvWgradArgs)]),
     "otm_conv_wgrad_fuses_P": (C.c_int, [_P(ConvWgradArgs)]),
@@ -253,6 +255,7 @@ SYMBOLS = {
         [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p],
     ),
     "otm_mod_bwd": (C.c_int, [_P(ModBwdArgs), C.c_void_p]),
+    "otm_instnorm_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "otm_instnorm_stats": (C.c_int, [_P(Tensor), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "otm_norm_act": (C.c_int, [_P(NormActArgs), C.c_void_p]),
     "otm_norm_act_bwd": (C.c_int, [_P(NormActBwdArgs), C.c_void_p]),

@@ -148,8 +148,8 @@ class Generator(nn.Module):
         i = 4
         for d in range(self.n_down):
             c = enc[i]
-            raw = ops.conv(a, c.weight.weight, c.bias, 3, 1, bias_dead=True)
-            a = ops.down(raw, norm=True, act=ops.ACT_RELU, y_halo=halo_after(d + 1))
+            raw, st = ops.conv(a, c.weight.weight, c.bias, 3, 1, bias_dead=True, want_stats=True)
+            a = ops.down(raw, norm=True, act=ops.ACT_RELU, y_halo=halo_after(d + 1), stats=st)
             i += 4
         for r in range(self.n_enc_res):
             blk = enc[i]
@@ -238,11 +238,11 @@ def _patch_trunk(model: nn.Sequential, x: torch.Tensor, act_dtype):
     a = ops.down(a)
     for idx in (3, 7):
         c = model[idx]
-        raw = ops.conv(a, c.weight.weight, c.bias, 4, 1, bias_dead=True)
-        a = ops.down(raw, norm=True, act=ops.ACT_LRELU)
+        raw, st = ops.conv(a, c.weight.weight, c.bias, 4, 1, bias_dead=True, want_stats=True)
+        a = ops.down(raw, norm=True, act=ops.ACT_LRELU, stats=st)
     c = model[11]
-    raw = ops.conv(a, c.weight.weight, c.bias, 4, 1, bias_dead=True)
-    return ops.norm_act(raw, norm=True, act=ops.ACT_LRELU)
+    raw, st = ops.conv(a, c.weight.weight, c.bias, 4, 1, bias_dead=True, want_stats=True)
+    return ops.norm_act(raw, norm=True, act=ops.ACT_LRELU, stats=st)
 
 
 class Discriminator(nn.Module):

@@ -228,6 +228,7 @@ struct TcFwdP {
   View y, res;
   const float* row_scale;
   const float* post_scale;  // [n, cout] applied AFTER the activation (NULL = 1)
+  float* stat_sums;         // [n, cout, 2] sum / sum of squares of the stored values, or NULL
   const float* bias;
   float alpha;
   int act, y_halo;
@@ -927,6 +928,9 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
       tc_fence_after();
       const int nhalf = (h0 + TH) < p.y.h ? 2 : 1;
+      // InstanceNorm statistics of the consumer: per-thread sums of its 4 channels over the tile
+      float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool col_ok0 = w0 + 2 * (lane & 3) < p.y.w, col_ok1 = w0 + 2 * (lane & 3) + 1 < p.y.w;
 #pragma unroll 1
       for (int half = 0; half < nhalf; ++half, ++hc) {
         const int x = hc & 1;
@@ -980,6 +984,23 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
               }
             }
           }
+          if (p.stat_sums) {
+            // fragment element (k, e): pixel row hh0 + 4 j2 + k, pixel column w0 + 2 (lane % 4) + e
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const bool rok = h0 + half * TH + 4 * j2 + k < p.y.h;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const bool ok = rok && (e ? col_ok1 : col_ok0);
+                const float a0 = ok ? xa[4 * k + e] : 0.f, a1 = ok ? xa[4 * k + 2 + e] : 0.f;
+                const float b0 = ok ? xb[4 * k + e] : 0.f, b1 = ok ? xb[4 * k + 2 + e] : 0.f;
+                ssum[0] += a0; ssq[0] = fmaf(a0, a0, ssq[0]);
+                ssum[1] += a1; ssq[1] = fmaf(a1, a1, ssq[1]);
+                ssum[2] += b0; ssq[2] = fmaf(b0, b0, ssq[2]);
+                ssum[3] += b1; ssq[3] = fmaf(b1, b1, ssq[3]);
+              }
+            }
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t sa = st_base + (uint32_t)((j2 * 32 + k * 8) * 128);
@@ -1001,6 +1022,24 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         asm volatile("bar.arrive %0, 192;" ::"r"(4 + x) : "memory");
         tc_fence_before();
         if (half == nhalf - 1) mbar_arrive(smem_u32(&tmem_empty[buf]));  // accumulator drained
+      }
+      if (p.stat_sums) {
+        // the 4 lanes of a quad hold the same channels (different pixel columns)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 1);
+          ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 1);
+          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 2);
+          ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 2);
+        }
+        if ((lane & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float* dst = p.stat_sums + ((long long)n * p.cout + o0 + wq * 32 + 8 * j + (lane >> 2)) * 2;
+            atomicAdd(dst, ssum[j]);
+            atomicAdd(dst + 1, ssq[j]);
+          }
+        }
       }
     }
   } else if (warp >= 2) {
@@ -1666,6 +1705,15 @@ static int launch_fwd_rr2t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   return OTM_OK;
 }
 
+// would conv_fwd_tc run these arguments on the transposed pair kernel? (the one whose epilogue
+// can accumulate the consumer's InstanceNorm statistics); mirrors the choice made below
+bool conv_fwd_tc_uses_rr2t(const otm_conv_fwd_args* a) {
+  const int cout = a->y.c;
+  if (cout % 128 != 0) return false;
+  const int tile_rows = (a->y.h + 15) / 16, tiles_w = (a->y.w + 7) / 8;
+  return (long long)((tile_rows + 1) / 2) * tiles_w * (cout / 128) * a->y.n >= 2LL * num_sms();
+}
+
 int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   const int Ho = a->y.h, Wo = a->y.w, cout = a->y.c, cin = a->x.c;
   const int KS = a->kh;  // 3 or 4 (conv_fwd_tc_eligible)
@@ -1673,9 +1721,16 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   constexpr int TW = 8, TH = 16;
   const int tile_rows = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
   const int tiles = tile_rows * tiles_w;
+  // 128-channel tiles go to the transposed pair kernel whenever there are enough tile pairs to
+  // fill the SMs twice -- also for 256 / 512 output channels (two / four weight tiles per pixel
+  // pair: measured 1465-1580 vs 1260-1350 TFLOP/s for the 256-wide tile at 256 -> 256 @64x64);
+  // the 256-wide tile is kept for the small layers
   int BN = 128;
   if (cout % 128 != 0) BN = 64;
-  else if (cout % 256 == 0 && (long long)tiles * a->y.n * (cout / 256) >= 2 * num_sms()) BN = 256;
+  else if (cout % 256 == 0 &&
+           (long long)((tile_rows + 1) / 2) * tiles_w * (cout / 128) * a->y.n < 2LL * num_sms() &&
+           (long long)tiles * a->y.n * (cout / 256) >= 2 * num_sms())
+    BN = 256;
 
   CUtensorMap tmA, tmB, tmY;
   int rc = make_act_map(&tmA, a->x, a->x_halo, TW, TH + KS - 1);
@@ -1692,6 +1747,7 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   p.y = make_view(a->y);
   p.res = a->residual.ptr ? make_view(a->residual) : null_view();
   p.row_scale = a->row_scale; p.post_scale = a->post_scale; p.bias = a->bias; p.alpha = a->alpha;
+  p.stat_sums = nullptr;
   p.act = a->act;
   p.y_halo = a->y_halo; p.cin = cin; p.cout = cout; p.kh = KS; p.kw = KS;
   p.coord_off = a->x_halo - a->pad;
@@ -1711,6 +1767,10 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
       CUtensorMap tmA2;
       rc = make_act_map(&tmA2, a->x, a->x_halo, TW, 2 * TH + KS - 1);
       if (rc) return rc;
+      if (a->stat_sums) {
+        p.stat_sums = a->stat_sums;
+        OTM_CHECK_CUDA(cudaMemsetAsync(a->stat_sums, 0, sizeof(float) * 2 * (size_t)a->y.n * cout, st));
+      }
       CUtensorMap tmR = tmY;  // residual: same boxes as the output tile, its own strides
       if (a->residual.ptr) {
         rc = make_act_map(&tmR, a->residual, 0, TW, TH);
@@ -1821,12 +1881,11 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const int taps = a->kh * a->kw;
   const int m_tiles = M / 128;
   p.n_tiles_n = N / BN;
-  // taps per CTA.  OTM_WGRAD_TPC=2|4 lays that many shifted x tiles side by side as ONE 256-column
-  // operand next to the shared dy tile (96 instead of 128 B/clk of operand reads).  Measured on
-  // B200 (tools/bench_wgrad.py, profiles/r2_wgrad_tpc.md): SLOWER -- 717 vs 921 TFLOP/s at n=96
-  // 128->128, 645 vs 733 at n=64 -- because the 48 KB stages leave a 2-deep ring per CTA at two
-  // CTAs per SM and the TMA latency is exposed.  Default: one tap per CTA.
-  static const int tpc_cap = [] { const char* e = getenv("OTM_WGRAD_TPC"); return e ? atoi(e) : 1; }();
+  // taps per CTA: laying 2 / 4 shifted x tiles side by side as ONE 256-column operand next to the
+  // shared dy tile was measured SLOWER here (717 vs 921 TFLOP/s at n=96 128->128: the 48 KB
+  // stages leave a 2-deep ring at two CTAs per SM); the filter-column kernel above is the form
+  // of that idea that works.  One tap per CTA.
+  constexpr int tpc_cap = 1;
   int tpc = p.a_is_x ? 1 : 256 / BN;
   if (tpc > tpc_cap) tpc = tpc_cap;
   const int tap_ctas = (taps + tpc - 1) / tpc;
@@ -1852,15 +1911,9 @@ int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   dim3 grid(tap_ctas, m_tiles * p.n_tiles_n, a->dy.n * splits);
   if (p.ws) OTM_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, sizeof(float) * (size_t)taps * cin * cout, st));
   if (BN == 64) {
-    if (tpc == 4) rc = launch_wgrad<64, 2, 2, 4>(tmA, tmB, p, grid, st);
-    else if (tpc == 2) rc = launch_wgrad<64, 3, 2, 2>(tmA, tmB, p, grid, st);
-    else rc = launch_wgrad<64, 4, 2, 1>(tmA, tmB, p, grid, st);
+    rc = launch_wgrad<64, 4, 2, 1>(tmA, tmB, p, grid, st);
   } else if (BN == 128) {
-    static const int occ1 = [] { const char* e = getenv("OTM_WGRAD_OCC1"); return e ? atoi(e) : 0; }();
-    if (tpc >= 2 && occ1) rc = launch_wgrad<128, 4, 1, 2>(tmA, tmB, p, grid, st);  // experiment
-    else if (tpc >= 2) rc = launch_wgrad<128, 2, 2, 2>(tmA, tmB, p, grid, st);
-    else if (occ1) rc = launch_wgrad<128, 6, 1, 1>(tmA, tmB, p, grid, st);        // experiment
-    else rc = launch_wgrad<128, 3, 2, 1>(tmA, tmB, p, grid, st);
+    rc = launch_wgrad<128, 3, 2, 1>(tmA, tmB, p, grid, st);
   } else {
     rc = launch_wgrad<256, 2, 2, 1>(tmA, tmB, p, grid, st);
   }
@@ -1910,11 +1963,20 @@ int otm_conv_fwd_uses_tcgen05(const otm_conv_fwd_args* a) {
   return conv_fwd_tc_eligible(a) ? 1 : 0;
 }
 
+int otm_conv_fwd_fuses_stats(const otm_conv_fwd_args* a) {
+  if (!a || a->path == OTM_PATH_SIMT || !conv_fwd_tc_eligible(a)) return 0;
+  return conv_fwd_tc_uses_rr2t(a) ? 1 : 0;
+}
+
 int otm_conv_fwd(const otm_conv_fwd_args* a, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int rc = validate_fwd(a);
   if (rc) return rc;
   const bool tc = conv_fwd_tc_eligible(a);
+  if (a->stat_sums)
+    OTM_REQUIRE(tc && a->path != OTM_PATH_SIMT && conv_fwd_tc_uses_rr2t(a),
+                "conv_fwd: stat_sums given but this launch cannot accumulate them "
+                "(ask otm_conv_fwd_fuses_stats first)");
   if (a->path == OTM_PATH_TCGEN05 && !tc)
     return fail(OTM_ERR_UNSUPPORTED, "conv_fwd: tcgen05 path not available for this shape/dtype");
   if (tc && a->path != OTM_PATH_SIMT) return conv_fwd_tc(a, st);

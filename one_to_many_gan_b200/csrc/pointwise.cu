@@ -137,14 +137,14 @@ static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
   int cv_shift = -1;
   if ((CV & (CV - 1)) == 0) { cv_shift = 0; while ((1 << cv_shift) < CV) ++cv_shift; }
   const int nrows = N * H;
-  static const int mode = [] { const char* e = getenv("OTM_EW_MODE"); return e ? atoi(e) : 1; }();
+  constexpr int mode = 1;  // persistent CTAs (the one-shot grid below serves item counts >= 2^30)
   if (mode == 1) {
     const int nblk = (W * CV + 255) / 256;
     const long long items = (long long)nrows * nblk;
     if (items < (1ll << 30)) {
       long long grid = (long long)num_sms() * ew_occ<F>::value;
       if (grid > items) grid = items;
-      static const int chunk = [] { const char* e = getenv("OTM_EW_CHUNK"); return e ? atoi(e) : 0; }();
+      constexpr int chunk = 0;
       ew_persist_kernel<V, F><<<(int)grid, 256, 0, st>>>(f, N, H, W, C, cv_shift, nblk, (int)items,
                                                          chunk);
       OTM_LAUNCH_CHECK();
@@ -152,8 +152,8 @@ static int launch_ew(F f, int N, int H, int W, int C, cudaStream_t st) {
     }
   }
   // enough CTAs for ~8 per SM; a bounded number of rows per CTA
-  static const int rows_cap = [] { const char* e = getenv("OTM_EW_ROWS"); return e ? atoi(e) : 8; }();
-  static const int ctas_per_sm = [] { const char* e = getenv("OTM_EW_CTAS"); return e ? atoi(e) : 8; }();
+  constexpr int rows_cap = 8;
+  constexpr int ctas_per_sm = 8;
   int rows = nrows / (num_sms() * ctas_per_sm);
   if (rows < 1) rows = 1;
   if (rows > rows_cap) rows = rows_cap;
@@ -237,7 +237,7 @@ static int launch_nc_reduce(F f, int N, int H, int W, int C, float* out, cudaStr
   int rows = 256 / lanes;
   // all CTAs co-resident (4 per SM at 64 registers): chunks * N <= 4 * SMs, so there is no
   // partial second wave; at least `rows*4` pixels per CTA
-  static const int mode = [] { const char* e = getenv("OTM_EW_MODE"); return e ? atoi(e) : 1; }();
+  constexpr int mode = 1;  // persistent CTAs (the one-shot grid below serves item counts >= 2^30)
   int want_chunks = mode == 1 ? (num_sms() * OTM_RED_OCC) / N : (num_sms() * 4 + N - 1) / N;
   if (want_chunks < 1) want_chunks = 1;
   int pix = (HW + want_chunks - 1) / want_chunks;
@@ -288,6 +288,17 @@ __global__ void stats_finalize_kernel(const float* ws, float* stats, View x, int
   float dm = s * inv_n;
   float var = fmaxf(ss * inv_n - dm * dm, 0.f);
   stats[2 * i] = k + dm;
+  stats[2 * i + 1] = rsqrtf(var + eps);
+}
+
+// (mean, rstd) from plain sums accumulated by a conv epilogue (otm_conv_fwd_args.stat_sums)
+__global__ void stats_from_sums_kernel(const float* __restrict__ sums, float* __restrict__ stats,
+                                       int count, float inv_n, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float m = sums[2 * i] * inv_n;
+  const float var = fmaxf(sums[2 * i + 1] * inv_n - m * m, 0.f);
+  stats[2 * i] = m;
   stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
@@ -1638,14 +1649,11 @@ struct ChannelSumRowOp {
 // must fit in shared memory.  Returns the number of stages (0 = not eligible) and the ring size.
 static int row_stream_plan(const otm_tensor& A, int a_halo, const otm_tensor* B, const otm_tensor* Cc,
                            const otm_tensor* o1, const otm_tensor* o2, size_t* smem_bytes) {
-  static const int use_stream = [] { const char* e = getenv("OTM_ROW_STREAM"); return e ? atoi(e) : 1; }();
+  constexpr int use_stream = 1;
   if (!use_stream || a_halo > 3 || A.c % 8 != 0 || A.h < 2 * a_halo + 2 || A.w < 2 * a_halo + 2) return 0;
   // small tensors: the 148 x 288-thread persistent launch with its ring set-up costs more than
   // the register-file kernels
-  static const long long min_bytes = [] {
-    const char* e = getenv("OTM_ROW_STREAM_MIN_MB");
-    return (long long)(e ? atoi(e) : 8) << 20;
-  }();
+  constexpr long long min_bytes = 8ll << 20;
   if ((long long)A.n * A.h * A.w * A.c * (long long)dtype_size(A.dtype) < min_bytes) return 0;
   const int C = A.c, CV = C / 8;
   if (CV < 1 || 256 % CV != 0 || A.h < 4 || A.w < 4) return 0;
@@ -1959,17 +1967,14 @@ down_bwd_stream_kernel(View g, View ga, float sch, float scw, int C, int S) {
 }
 
 static int down_stream_slots(const otm_down_args* a, size_t* smem_bytes) {
-  static const int use_stream = [] { const char* e = getenv("OTM_DOWN_STREAM"); return e ? atoi(e) : 1; }();
+  constexpr int use_stream = 1;
   const otm_tensor& x = a->x;
   if (!use_stream || x.c % 8 != 0) return 0;
   const int C = x.c, CV = C / 8;
   if (CV < 1 || 256 % CV != 0 || a->y.h < 2 || a->y.w < 2) return 0;
   if (x.sw != C || x.sh % 8 || x.sn % 8 || ((uintptr_t)x.ptr % 16)) return 0;
   const size_t es = dtype_size(x.dtype);
-  static const long long min_bytes = [] {
-    const char* e = getenv("OTM_ROW_STREAM_MIN_MB");
-    return (long long)(e ? atoi(e) : 8) << 20;
-  }();
+  constexpr long long min_bytes = 8ll << 20;
   if ((long long)x.n * x.h * x.w * C * (long long)es < min_bytes) return 0;
   const size_t row = ((size_t)x.w * C * es + 127) & ~(size_t)127;
   if (((size_t)x.w * C * es) % 16) return 0;
@@ -2008,6 +2013,15 @@ const char* otm_last_error(void) { return g_err; }
 int otm_version(void) { return 1; }
 int64_t otm_launch_count(void) { return g_launches.load(); }
 
+int otm_instnorm_finalize(const float* sums, float* stats, int32_t count, int32_t hw, float eps,
+                          otm_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  OTM_REQUIRE(sums && stats && count > 0 && hw > 0, "instnorm_finalize: bad argument");
+  stats_from_sums_kernel<<<(count + 255) / 256, 256, 0, st>>>(sums, stats, count, 1.f / (float)hw, eps);
+  OTM_LAUNCH_CHECK();
+  return OTM_OK;
+}
+
 int otm_instnorm_stats(const otm_tensor* x, float eps, float* ws, float* stats,
                        otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -2020,7 +2034,7 @@ int otm_instnorm_stats(const otm_tensor* x, float eps, float* ws, float* stats,
   // pure read reductions through the row-streaming kernel: 31.7 vs 33.8 us on [64,128,64,64], 70.7
   // vs 80.9 us on [64,128,128,128] once the flush goes through shared memory (with one atomic per
   // thread it was slower); OTM_STREAM_REDUCE=0 selects the register-file reduction
-  static const int stream_red = [] { const char* e = getenv("OTM_STREAM_REDUCE"); return e ? atoi(e) : 1; }();
+  constexpr int stream_red = 1;
   const int rs_stages = (vok && stream_red)
                             ? row_stream_plan(*x, 0, nullptr, nullptr, nullptr, nullptr, &rs_smem_bytes) : 0;
   if (rs_stages) {
@@ -2104,10 +2118,7 @@ static otm_tensor slice_n(const otm_tensor& t, int n0, int cnt) {
 // 1034 vs 1059 img/s) -- the 2-4x smaller launches lose more to their prologues and tails than
 // the L2 hits give back.  Off by default; kept as a knob for the larger configs.
 int otm_norm_act_bwd(const otm_norm_act_bwd_args* a, otm_stream stream) {
-  static const long long block_bytes = [] {
-    const char* e = getenv("OTM_L2_BLOCK_MB");
-    return (long long)(e ? atoi(e) : 0) << 20;
-  }();
+  constexpr long long block_bytes = 0;  // L2-blocked variant measured slower; kept for reference
   if (a && a->stats && a->gx.ptr && a->x.ptr && a->g.ptr && block_bytes > 0) {
     const long long per_sample =
         (long long)a->gx.h * a->gx.w * a->gx.c * (long long)dtype_size(a->gx.dtype) *
@@ -2277,7 +2288,7 @@ int otm_down(const otm_down_args* a, otm_stream stream) {
       return OTM_OK;
     }
   }
-  static const int blk = [] { const char* e = getenv("OTM_DOWN_FWD_BLOCK"); return e ? atoi(e) : 0; }();
+  constexpr int blk = 0;  // the 2x2-block form measured slower (occupancy), DESIGN.md
   const bool even = a->x.h == 2 * a->y.h && a->x.w == 2 * a->y.w && a->y.h >= 4 && a->y.w >= 4;
   OTM_DISPATCH_TV(a->x.dtype, vok, {
     if (blk && V == 8 && even) {
@@ -2302,11 +2313,8 @@ int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_
   int rc = OTM_OK;
   {
     // windowed row streaming (odd and even sizes): g rows are small, the pass is write-bound
-    static const int use_stream = [] { const char* e = getenv("OTM_DOWN_BWD_STREAM"); return e ? atoi(e) : 1; }();
-    static const long long min_bytes = [] {
-      const char* e = getenv("OTM_ROW_STREAM_MIN_MB");
-      return (long long)(e ? atoi(e) : 8) << 20;
-    }();
+    constexpr int use_stream = 1;
+    constexpr long long min_bytes = 8ll << 20;
     const int C = g->c, CV = C / 8;
     const size_t es = dtype_size(g->dtype);
     const size_t row = ((size_t)g->w * C * es + 127) & ~(size_t)127;
@@ -2333,7 +2341,7 @@ int otm_down_bwd(const otm_tensor* g, int32_t g_halo, const otm_tensor* ga, otm_
       return OTM_OK;
     }
   }
-  static const int blk = [] { const char* e = getenv("OTM_DOWN_BLOCK"); return e ? atoi(e) : 1; }();
+  constexpr int blk = 1;
   const bool even = ga->h == 2 * g->h && ga->w == 2 * g->w && g->h >= 4 && g->w >= 4;
   OTM_DISPATCH_TV(g->dtype, vok, {
     if (blk && V == 8 && even && g_halo == 0) {
@@ -2454,7 +2462,7 @@ int otm_channel_sum(const otm_tensor* g, float* out, int32_t accumulate, otm_str
   int rc = OTM_OK;
   {
     size_t smem = 0;
-    static const int stream_red = [] { const char* e = getenv("OTM_STREAM_REDUCE"); return e ? atoi(e) : 1; }();
+    constexpr int stream_red = 1;
     const int stages = (vok && stream_red) ? row_stream_plan(*g, 0, nullptr, nullptr, nullptr, nullptr, &smem) : 0;
     if (stages) {
       if (g->dtype == OTM_BF16) {

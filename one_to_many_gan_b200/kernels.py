@@ -37,7 +37,9 @@ def padded_view(t: torch.Tensor, halo: int) -> torch.Tensor:
 
 def conv_fwd(x, wpack, cout, kh, kw, pad, *, x_halo=0, y_halo=0, alpha=1.0, row_scale=None,
              bias=None, act=ACT_NONE, residual=None, out_dtype=None, per_sample=False,
-             path=PATH_AUTO, out=None, post_scale=None):
+             path=PATH_AUTO, out=None, post_scale=None, want_stats=False, eps=1e-5):
+    """want_stats: also return the InstanceNorm statistics (mean, rstd) [n, cout, 2] of the output
+    -- accumulated in the conv epilogue when the launch supports it, else by a separate pass."""
     n, cin, h, w = x.shape
     ho, wo = h + 2 * pad - kh + 1, w + 2 * pad - kw + 1
     if out is None:
@@ -57,8 +59,19 @@ def conv_fwd(x, wpack, cout, kh, kw, pad, *, x_halo=0, y_halo=0, alpha=1.0, row_
     a.residual = L.tdesc(residual)
     a.path = path
     a.post_scale = L.ptr(post_scale)
+    if not want_stats:
+        L.check(L.lib.otm_conv_fwd(_byref(a), L.stream_ptr()), "otm_conv_fwd")
+        return out
+    if y_halo == 0 and L.lib.otm_conv_fwd_fuses_stats(_byref(a)):
+        sums = torch.empty((n, cout, 2), dtype=torch.float32, device=x.device)
+        stats = torch.empty((n, cout, 2), dtype=torch.float32, device=x.device)
+        a.stat_sums = L.ptr(sums)
+        L.check(L.lib.otm_conv_fwd(_byref(a), L.stream_ptr()), "otm_conv_fwd")
+        L.check(L.lib.otm_instnorm_finalize(L.ptr(sums), L.ptr(stats), n * cout, ho * wo, eps,
+                                            L.stream_ptr()), "otm_instnorm_finalize")
+        return out, stats
     L.check(L.lib.otm_conv_fwd(_byref(a), L.stream_ptr()), "otm_conv_fwd")
-    return out
+    return out, instnorm_stats(out, eps)
 
 
 def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None, path=PATH_AUTO,

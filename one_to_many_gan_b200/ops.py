@@ -136,21 +136,28 @@ class ConvFn(torch.autograd.Function):
     of the conv; `pad` is the total logical padding (halo + zero padding)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype, bias_dead=False):
+    def forward(ctx, x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype, bias_dead=False,
+                want_stats=False):
         ctx.bias = bias
         ctx.bias_dead = bias_dead
         cout = weight.shape[0]
         wp = _pack(weight, x.dtype, False)
         y = K.conv_fwd(x, wp, cout, k, k, pad, x_halo=x_halo, y_halo=y_halo,
                        bias=bias.detach() if bias is not None else None, act=act,
-                       out_dtype=out_dtype)
+                       out_dtype=out_dtype, want_stats=want_stats)
+        stats = None
+        if want_stats:
+            y, stats = y
         ctx.cfg = (k, pad, x_halo, act)
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
         return y
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gstats=None):
         x, weight, y = ctx.saved_tensors
         bias = ctx.bias
         k, pad, x_halo, act = ctx.cfg
@@ -178,14 +185,17 @@ class ConvFn(torch.autograd.Function):
                 gx = K.norm_act_bwd(gint, None, None, ACT_NONE, g_halo=x_halo)
             else:
                 gx = gxp
-        return gx, gw, gb, None, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None, None
 
 
 def conv(x, weight, bias, k, pad, *, x_halo=0, y_halo=0, act=ACT_NONE, out_dtype=None,
-         bias_dead=False):
+         bias_dead=False, want_stats=False):
     """bias_dead=True: the output goes straight into an InstanceNorm (the bias gradient is exactly
-    zero and is not computed)."""
-    return ConvFn.apply(x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype or x.dtype, bias_dead)
+    zero and is not computed).  want_stats=True: returns (y, stats) with the InstanceNorm
+    statistics of y -- from the conv epilogue where the kernel supports it -- to hand to
+    `norm_act(..., stats=)` / `down(..., stats=)`."""
+    return ConvFn.apply(x, weight, bias, k, pad, x_halo, y_halo, act, out_dtype or x.dtype, bias_dead,
+                        want_stats)
 
 
 # ---------------------------------------------------------------------------
@@ -196,8 +206,11 @@ class NormActFn(torch.autograd.Function):
     (reference blocks.py:20-33, builder.py:161-165)."""
 
     @staticmethod
-    def forward(ctx, x, residual, norm, act, y_halo):
-        stats = K.instnorm_stats(x) if norm else None
+    def forward(ctx, x, residual, norm, act, y_halo, stats=None):
+        if not norm:
+            stats = None
+        elif stats is None:
+            stats = K.instnorm_stats(x)
         y = K.norm_act(x, stats, act, residual=residual, y_halo=y_halo)
         ctx.act = act
         ctx.has_res = residual is not None
@@ -211,19 +224,22 @@ class NormActFn(torch.autograd.Function):
         want_res = ctx.has_res and ctx.needs_input_grad[1]
         r = K.norm_act_bwd(g, x, stats, ctx.act, want_gres=want_res)
         gx, gres = (r if want_res else (r, None))
-        return gx, gres, None, None, None
+        return gx, gres, None, None, None, None
 
 
-def norm_act(x, *, norm=True, act=ACT_NONE, residual=None, y_halo=0):
-    return NormActFn.apply(x, residual, norm, act, y_halo)
+def norm_act(x, *, norm=True, act=ACT_NONE, residual=None, y_halo=0, stats=None):
+    return NormActFn.apply(x, residual, norm, act, y_halo, stats)
 
 
 class DownFn(torch.autograd.Function):
     """(InstanceNorm -> activation ->) DownSample (reference layers.py:232-247) in one pass."""
 
     @staticmethod
-    def forward(ctx, x, norm, act, y_halo):
-        stats = K.instnorm_stats(x) if norm else None
+    def forward(ctx, x, norm, act, y_halo, stats=None):
+        if not norm:
+            stats = None
+        elif stats is None:
+            stats = K.instnorm_stats(x)
         y = K.down(x, stats, act, y_halo)
         ctx.act = act
         ctx.save_for_backward(x, stats)
@@ -234,16 +250,16 @@ class DownFn(torch.autograd.Function):
         x, stats = ctx.saved_tensors
         g = _g(g, x)
         if stats is None and ctx.act == ACT_NONE:
-            return K.down_bwd(g, x.shape[2:]), None, None, None
+            return K.down_bwd(g, x.shape[2:]), None, None, None, None
         # (otm_norm_act_bwd can apply the stencil transpose on load (g_down=1) and skip this
         # temporary, but gathering 4-16 taps in both of its passes measured 0.6 ms/iteration
         # slower than materialising `ga` once, so the two-kernel form is used.)
         ga = K.down_bwd(g, x.shape[2:])
-        return K.norm_act_bwd(ga, x, stats, ctx.act), None, None, None
+        return K.norm_act_bwd(ga, x, stats, ctx.act), None, None, None, None
 
 
-def down(x, *, norm=False, act=ACT_NONE, y_halo=0):
-    return DownFn.apply(x, norm, act, y_halo)
+def down(x, *, norm=False, act=ACT_NONE, y_halo=0, stats=None):
+    return DownFn.apply(x, norm, act, y_halo, stats)
 
 
 class UpFn(torch.autograd.Function):
@@ -269,11 +285,9 @@ class ResBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, w2, y_halo):
         f = w1.shape[0]
-        raw1 = K.conv_fwd(x, _pack(w1, x.dtype, False), f, 3, 3, 1, x_halo=1)
-        st1 = K.instnorm_stats(raw1)
+        raw1, st1 = K.conv_fwd(x, _pack(w1, x.dtype, False), f, 3, 3, 1, x_halo=1, want_stats=True)
         t = K.norm_act(raw1, st1, ACT_RELU, y_halo=1)
-        raw2 = K.conv_fwd(t, _pack(w2, x.dtype, False), f, 3, 3, 1, x_halo=1)
-        st2 = K.instnorm_stats(raw2)
+        raw2, st2 = K.conv_fwd(t, _pack(w2, x.dtype, False), f, 3, 3, 1, x_halo=1, want_stats=True)
         out = K.norm_act(raw2, st2, ACT_NONE, residual=x, y_halo=y_halo)
         ctx.save_for_backward(x, w1, w2, raw1, st1, t, raw2, st2)
         return out
