@@ -1363,7 +1363,11 @@ constexpr int RS_THREADS = OTM_RS_THREADS;
 
 template <typename T, typename OP>
 __global__ void __launch_bounds__(RS_THREADS + 32, 1)
-row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out) {
+row_stream_kernel(OP op, int N, int H, int W, int C, int stages_nseg, float* red_out) {
+  // rows too long for a multi-stage ring are streamed as `nseg` column segments (one item = one
+  // segment of one image row; the reflect-halo columns travel with the first / last segment)
+  const int stages = stages_nseg & 0xff, nseg = stages_nseg >> 8;
+  const int Wseg = W / nseg;
   constexpr int V = 8;
   constexpr int NQ = OP::NQ;
   constexpr int NA = NQ > 0 ? NQ : 1;
@@ -1371,8 +1375,9 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
   const View va = op.in_a(), vb = op.in_b(), vc = op.in_c();
   const int p = op.a_halo();
   const int CV = C / V;
-  const uint32_t a_row_bytes = (uint32_t)(W + 2 * p) * C * sizeof(T);
-  const uint32_t x_row_bytes = (uint32_t)W * C * sizeof(T);
+  const uint32_t a_row_bytes = (uint32_t)(Wseg + 2 * p) * C * sizeof(T);  // slot size (largest segment)
+  const uint32_t x_row_bytes = (uint32_t)Wseg * C * sizeof(T);
+  const uint32_t px_bytes = (uint32_t)C * sizeof(T);
   const bool has_b = vb.ptr != nullptr, has_c = vc.ptr != nullptr;
   const uint32_t off_alias = a_row_bytes, off_b = off_alias + (p ? a_row_bytes : 0);
   const uint32_t off_c = off_b + (has_b ? x_row_bytes : 0);
@@ -1386,7 +1391,7 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int rows = N * H;
+  const int rows = N * H * nseg;  // items
   const int r0 = (int)((long long)rows * blockIdx.x / gridDim.x);
   const int r1 = (int)((long long)rows * (blockIdx.x + 1) / gridDim.x);
   if (warp == RS_THREADS / 32) {
@@ -1395,17 +1400,22 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
       for (int r = r0, k = 0; r < r1; ++r, ++k) {
         const int st = k % stages;
         sb_mbar_wait(sb_smem(&empty[st]), ((k / stages) & 1) ^ 1);
-        const int n = r / H, h = r - n * H;
+        const int row = r / nseg, seg = r - row * nseg;
+        const int n = row / H, h = row - n * H;
+        const int w_lo = seg * Wseg;
+        // A columns [a0, a1): the segment plus the halo columns at the row ends
+        const int a0 = seg == 0 ? -p : w_lo, a1 = w_lo + Wseg + (seg == nseg - 1 ? p : 0);
+        const uint32_t a_bytes = (uint32_t)(a1 - a0) * px_bytes;
         const int alias = reflect_alias(h, H, p);
         const uint32_t bar = sb_smem(&full[st]);
         const uint32_t base = sb_smem(rs_smem + (size_t)st * stage_bytes);
-        const uint32_t bytes = a_row_bytes + (alias != NO_ALIAS ? a_row_bytes : 0) + (has_b ? x_row_bytes : 0) +
+        const uint32_t bytes = a_bytes + (alias != NO_ALIAS ? a_bytes : 0) + (has_b ? x_row_bytes : 0) +
                                (has_c ? x_row_bytes : 0);
         sb_mbar_expect_tx(bar, bytes);
-        sb_bulk_load(base, vptr<T>(va, n, h, -p, 0), a_row_bytes, bar);
-        if (alias != NO_ALIAS) sb_bulk_load(base + off_alias, vptr<T>(va, n, alias, -p, 0), a_row_bytes, bar);
-        if (has_b) sb_bulk_load(base + off_b, vptr<T>(vb, n, h, 0, 0), x_row_bytes, bar);
-        if (has_c) sb_bulk_load(base + off_c, vptr<T>(vc, n, h, 0, 0), x_row_bytes, bar);
+        sb_bulk_load(base, vptr<T>(va, n, h, a0, 0), a_bytes, bar);
+        if (alias != NO_ALIAS) sb_bulk_load(base + off_alias, vptr<T>(va, n, alias, a0, 0), a_bytes, bar);
+        if (has_b) sb_bulk_load(base + off_b, vptr<T>(vb, n, h, w_lo, 0), x_row_bytes, bar);
+        if (has_c) sb_bulk_load(base + off_c, vptr<T>(vc, n, h, w_lo, 0), x_row_bytes, bar);
       }
     }
     return;
@@ -1446,7 +1456,10 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
   };
   for (int r = r0, k = 0; r < r1; ++r, ++k) {
     const int stg = k % stages;
-    const int n = r / H, h = r - n * H;
+    const int row = r / nseg, seg = r - row * nseg;
+    const int n = row / H, h = row - n * H;
+    const int w_lo = seg * Wseg;
+    const int a0 = seg == 0 ? -p : w_lo;  // first A column of the slot
     if (n != cur_n) {
       flush(cur_n);
       op.prepare(n, cv * V, st);
@@ -1459,38 +1472,39 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages, float* red_out)
     const T* brow = reinterpret_cast<const T*>(base + off_b);
     const T* crow = reinterpret_cast<const T*>(base + off_c);
     const bool row_alias = reflect_alias(h, H, p) != NO_ALIAS;
-    for (int i = tid; i < W * CV; i += RS_THREADS) {
-      const int w = i >> cv_sh;
+    for (int i = tid; i < Wseg * CV; i += RS_THREADS) {
+      const int wl = i >> cv_sh;  // column within the segment
+      const int w = w_lo + wl;
       float a[V], b[V], c[V];
-      load_vec<T, V>(arow + (size_t)(w + p) * C + cv * V, a);
+      load_vec<T, V>(arow + (size_t)(w - a0) * C + cv * V, a);
       if (p) {
-        const int wa = reflect_alias(w, W, p);
+        const int wa = reflect_alias(w, W, p);  // lies in the same slot (first / last segment)
         if (wa != NO_ALIAS) {
           float t[V];
-          load_vec<T, V>(arow + (size_t)(wa + p) * C + cv * V, t);
+          load_vec<T, V>(arow + (size_t)(wa - a0) * C + cv * V, t);
 #pragma unroll
           for (int e = 0; e < V; ++e) a[e] += t[e];
         }
         if (row_alias) {
           float t[V];
-          load_vec<T, V>(alrow + (size_t)(w + p) * C + cv * V, t);
+          load_vec<T, V>(alrow + (size_t)(w - a0) * C + cv * V, t);
 #pragma unroll
           for (int e = 0; e < V; ++e) a[e] += t[e];
           if (wa != NO_ALIAS) {
-            load_vec<T, V>(alrow + (size_t)(wa + p) * C + cv * V, t);
+            load_vec<T, V>(alrow + (size_t)(wa - a0) * C + cv * V, t);
 #pragma unroll
             for (int e = 0; e < V; ++e) a[e] += t[e];
           }
         }
       }
       if (has_b) {
-        load_vec<T, V>(brow + (size_t)w * C + cv * V, b);
+        load_vec<T, V>(brow + (size_t)wl * C + cv * V, b);
       } else {
 #pragma unroll
         for (int e = 0; e < V; ++e) b[e] = 0.f;
       }
       if (has_c) {
-        load_vec<T, V>(crow + (size_t)w * C + cv * V, c);
+        load_vec<T, V>(crow + (size_t)wl * C + cv * V, c);
       } else {
 #pragma unroll
         for (int e = 0; e < V; ++e) c[e] = 0.f;
@@ -1664,16 +1678,25 @@ static int row_stream_plan(const otm_tensor& A, int a_halo, const otm_tensor* B,
   };
   if (!dense(&A) || !dense(B) || !dense(Cc) || !dense(o1) || !dense(o2)) return 0;
   const size_t es = dtype_size(A.dtype);
-  const size_t arow = (size_t)(A.w + 2 * a_halo) * C * es, xrow = (size_t)A.w * C * es;
-  if (arow % 16 || xrow % 16) return 0;
-  const size_t stage = (arow * (a_halo ? 2 : 1) + ((B && B->ptr) ? xrow : 0) + ((Cc && Cc->ptr) ? xrow : 0) + 127) &
-                       ~(size_t)127;
   const size_t scratch = 2 * 8 * RS_THREADS * sizeof(float);  // reduction flush scratch [NQ * V][threads]
-  int stages = (int)((200 * 1024 - 256 - scratch) / stage);
-  if (stages < 2) return 0;
-  if (stages > 8) stages = 8;
-  *smem_bytes = stage * stages + 2 * 8 * stages + scratch + 64;
-  return stages;
+  // whole rows if at least 3 stages fit, else 2 / 4 / 8 column segments per row (the 256- and
+  // 512-channel tensors of the 256x256 / 512x512 configurations)
+  for (int nseg = 1; nseg <= 8; nseg *= 2) {
+    if (A.w % nseg != 0) break;
+    const int wseg = A.w / nseg;
+    if (wseg < 2 * a_halo + 2) break;
+    const size_t arow = (size_t)(wseg + 2 * a_halo) * C * es, xrow = (size_t)wseg * C * es;
+    if (arow % 16 || xrow % 16) return 0;
+    const size_t stage =
+        (arow * (a_halo ? 2 : 1) + ((B && B->ptr) ? xrow : 0) + ((Cc && Cc->ptr) ? xrow : 0) + 127) & ~(size_t)127;
+    int stages = (int)((200 * 1024 - 256 - scratch) / stage);
+    if (stages < 3 && nseg < 8 && A.w % (2 * nseg) == 0 && A.w / (2 * nseg) >= 2 * a_halo + 2) continue;
+    if (stages < 2) return 0;
+    if (stages > 8) stages = 8;
+    *smem_bytes = stage * stages + 2 * 8 * stages + scratch + 64;
+    return stages | (nseg << 8);
+  }
+  return 0;
 }
 
 template <typename T, typename OP>
@@ -1681,7 +1704,7 @@ static int launch_row_stream(const OP& op, int N, int H, int W, int C, int stage
                              float* red_out, cudaStream_t st) {
   auto kern = row_stream_kernel<T, OP>;
   OTM_ENSURE_SMEM(kern, 200 * 1024);
-  int grid = num_sms();
+  int grid = num_sms();  // `stages` = stages | nseg << 8 as row_stream_plan returns it
   if (grid > N * H) grid = N * H;
   kern<<<grid, RS_THREADS + 32, smem, st>>>(op, N, H, W, C, stages, red_out);
   OTM_LAUNCH_CHECK();

@@ -1,7 +1,9 @@
 """The TMA row-streaming kernels (row_stream_kernel ops, down_stream_kernel) only engage on tensors
 of >= 8 MB, above the shapes of test_kernels_gpu.py: here they run on 17-33 MB tensors against
 fp32 torch autograd on the same (storage-rounded) inputs, including the reflect-halo folds of
-width 1 and 3 and an odd-size DownSample."""
+width 1 and 3 and an odd-size DownSample.  The (8, 256, 64, 64) / (4, 512, 64, 64) shapes are the
+256- and 512-channel latents of BASELINE configs 3 and 5: their rows (32-64 KB) do not fit a
+multi-stage ring, so they are streamed as 2-8 column segments per row."""
 
 import pytest
 import torch
@@ -43,10 +45,14 @@ def padded_grad(K, gp):
     return buf
 
 
+SHAPES = [(16, 128, 64, 64), (8, 256, 64, 64), (4, 512, 64, 64), (4, 64, 256, 256)]  # >= 16.8 MB each
+
+
+@pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("halo", [0, 1, 3])
 @pytest.mark.parametrize("act", ["none", "relu"])
-def test_stream_norm_act_bwd(K, halo, act):
-    n, c, h, w = 16, 128, 64, 64  # 16.8 MB per bf16 tensor
+def test_stream_norm_act_bwd(K, halo, act, shape):
+    n, c, h, w = shape
     x = rnd(n, c, h, w, seed=1).bfloat16().float()
     gp = rnd(n, c, h + 2 * halo, w + 2 * halo, seed=2).bfloat16().float()
     g2 = rnd(n, c, h, w, seed=3).bfloat16().float()
@@ -66,8 +72,9 @@ def test_stream_norm_act_bwd(K, halo, act):
     assert relerr(gx.float(), xr.grad) < TOL[torch.bfloat16], (halo, act)
 
 
-def test_stream_fold_add_and_gres(K):
-    n, c, h, w, halo = 16, 128, 64, 64, 1
+@pytest.mark.parametrize("shape", SHAPES)
+def test_stream_fold_add_and_gres(K, shape):
+    (n, c, h, w), halo = shape, 1
     gp = rnd(n, c, h + 2, w + 2, seed=4).bfloat16().float()
     g2 = rnd(n, c, h, w, seed=5).bfloat16().float()
     z = torch.zeros(n, c, h, w, device="cuda", requires_grad=True)
@@ -78,8 +85,9 @@ def test_stream_fold_add_and_gres(K):
     assert relerr(gx.float(), z.grad) < 1e-2
 
 
-def test_stream_mod_in(K):
-    n, c, h, w = 16, 128, 64, 64
+@pytest.mark.parametrize("shape", SHAPES)
+def test_stream_mod_in(K, shape):
+    n, c, h, w = shape
     x = F.relu(rnd(n, c, h, w, seed=6)).bfloat16().float()
     gp = rnd(n, c, h + 2, w + 2, seed=7).bfloat16().float()
     gadd = rnd(n, c, h, w, seed=8).bfloat16().float()
@@ -96,8 +104,9 @@ def test_stream_mod_in(K):
     assert relerr(Q, want_q) < 5e-3
 
 
-def test_stream_norm_act_fwd_and_channel_sum(K):
-    n, c, h, w = 16, 128, 64, 64
+@pytest.mark.parametrize("shape", SHAPES)
+def test_stream_norm_act_fwd_and_channel_sum(K, shape):
+    n, c, h, w = shape
     x = rnd(n, c, h, w, seed=9).bfloat16().float()
     res = rnd(n, c, h, w, seed=10).bfloat16().float()
     xt = to_nhwc(K, x)
