@@ -133,6 +133,9 @@ typedef struct {
 int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream);
 int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a);
 int otm_conv_wgrad_fuses_P(const otm_conv_wgrad_args* a);
+/* bytes of the fp32 workspace `ws` this call wants (0: none, e.g. the FFMA path): the caller
+ * allocates it -- the library never owns memory ("otm_query_workspace"). */
+int64_t otm_conv_wgrad_workspace_bytes(const otm_conv_wgrad_args* a);
 
 /* Weight staging.  Replaces EqualisedWeight.forward (layers.py:23-24) and the per-sample
  * `weights * s` materialisation (layers.py:152-161).

@@ -1988,6 +1988,11 @@ int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a) {
   return conv_wgrad_tc_eligible(a) ? 1 : 0;
 }
 
+int64_t otm_conv_wgrad_workspace_bytes(const otm_conv_wgrad_args* a) {
+  if (!a || a->path == OTM_PATH_SIMT || !conv_wgrad_tc_eligible(a)) return 0;
+  return (int64_t)sizeof(float) * a->kh * a->kw * a->x.c * a->dy.c;
+}
+
 int otm_conv_wgrad_fuses_P(const otm_conv_wgrad_args* a) {
   if (!a || a->path == OTM_PATH_SIMT || !conv_wgrad_tc_eligible(a)) return 0;
   return (a->dy.c % 128 == 0) ? 1 : 0;

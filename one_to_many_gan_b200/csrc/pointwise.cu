@@ -1360,13 +1360,21 @@ __device__ __forceinline__ int reflect_alias(int i, int n, int p) {
 #define OTM_RS_THREADS 512
 #endif
 constexpr int RS_THREADS = OTM_RS_THREADS;
+#ifndef OTM_RS_GROUPS
+#define OTM_RS_GROUPS 1
+#endif
+// consumer warp groups (when the ring has a multiple of it in stages).  Measured with 4 groups at
+// 128x128 b32: InstanceNorm backward 1.79 -> 1.85 ms, mod_in 1.11 -> 1.19 ms, norm+act 0.49 -> 0.44
+// ms per iteration -- the per-stage barrier round trip is NOT what holds these passes at ~3.7 TB/s;
+// default 1 (every warp on every stage), the grouped path stays compiled and tested.
+constexpr int RS_GROUPS = OTM_RS_GROUPS;
 
 template <typename T, typename OP>
 __global__ void __launch_bounds__(RS_THREADS + 32, 1)
 row_stream_kernel(OP op, int N, int H, int W, int C, int stages_nseg, float* red_out) {
   // rows too long for a multi-stage ring are streamed as `nseg` column segments (one item = one
   // segment of one image row; the reflect-halo columns travel with the first / last segment)
-  const int stages = stages_nseg & 0xff, nseg = stages_nseg >> 8;
+  const int stages = stages_nseg & 0xff, nseg = (stages_nseg >> 8) & 0xff, ngroups = stages_nseg >> 16;
   const int Wseg = W / nseg;
   constexpr int V = 8;
   constexpr int NQ = OP::NQ;
@@ -1387,7 +1395,7 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages_nseg, float* red
   uint64_t* empty = bars + stages;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (threadIdx.x == 0) {
-    for (int s2 = 0; s2 < stages; ++s2) { sb_mbar_init(sb_smem(&full[s2]), 1); sb_mbar_init(sb_smem(&empty[s2]), RS_THREADS / 32); }
+    for (int s2 = 0; s2 < stages; ++s2) { sb_mbar_init(sb_smem(&full[s2]), 1); sb_mbar_init(sb_smem(&empty[s2]), RS_THREADS / 32 / ngroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1420,22 +1428,29 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages_nseg, float* red
     }
     return;
   }
-  // ---------------- consumers (RS_THREADS / 32 warps) ----------------
+  // ---------------- consumers (RS_THREADS / 32 warps in `ngroups` groups) ----------------
+  // The warps work in groups; group j consumes the items j, j + ngroups, ... of the CTA's range,
+  // so a thread handles ngroups times more vectors per stage it waits for (one image row of 64
+  // pixels x 128 channels is only 2 vectors per thread when all 512 threads share it: the barrier
+  // round trip and the row bookkeeping were a third of the work per row).  `stages` is a multiple
+  // of `ngroups`, so a ring stage always belongs to the same group and that group sees every phase
+  // of its mbarriers (a parity wait must never be more than one phase behind).
   const int tid = threadIdx.x;  // 0..RS_THREADS-1
-  const int cv = tid % CV;      // constant per thread: CV divides 256 (so it is a power of two)
+  const int GSZ = RS_THREADS / ngroups;
+  const int grp = tid / GSZ, gt = tid % GSZ;
+  const int cv = gt % CV;       // constant per thread: CV divides GSZ (a power of two)
   const int cv_sh = 31 - __clz(CV);
   typename OP::State st;
-  int cur_n = -1;
   float acc[NA][V];
 #pragma unroll
   for (int q = 0; q < NA; ++q)
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
-  // per-sample flush of the register accumulators: the 256 / CV threads that share a channel
-  // vector meet in shared memory first, so one atomic per (n, c, q) and CTA reaches L2
+  // per-sample flush of the register accumulators: the RS_THREADS / CV threads that share a
+  // channel vector meet in shared memory first, so one atomic per (n, c, q) and CTA reaches L2
   float* red_sm = reinterpret_cast<float*>(bars + 2 * stages);  // [NQ * V][RS_THREADS]
   auto flush = [&](int n) {
-    if (NQ > 0 && n >= 0) {  // n and the call sites are uniform over the consumer warps
+    if (NQ > 0) {  // every consumer thread calls this once per sample of the CTA's range
 #pragma unroll
       for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -1454,67 +1469,69 @@ row_stream_kernel(OP op, int N, int H, int W, int C, int stages_nseg, float* red
       asm volatile("bar.sync 1, %0;" ::"n"(RS_THREADS) : "memory");
     }
   };
-  for (int r = r0, k = 0; r < r1; ++r, ++k) {
-    const int stg = k % stages;
-    const int row = r / nseg, seg = r - row * nseg;
-    const int n = row / H, h = row - n * H;
-    const int w_lo = seg * Wseg;
-    const int a0 = seg == 0 ? -p : w_lo;  // first A column of the slot
-    if (n != cur_n) {
-      flush(cur_n);
-      op.prepare(n, cv * V, st);
-      cur_n = n;
-    }
-    sb_mbar_wait(sb_smem(&full[stg]), (k / stages) & 1);
-    const unsigned char* base = rs_smem + (size_t)stg * stage_bytes;
-    const T* arow = reinterpret_cast<const T*>(base);
-    const T* alrow = reinterpret_cast<const T*>(base + off_alias);
-    const T* brow = reinterpret_cast<const T*>(base + off_b);
-    const T* crow = reinterpret_cast<const T*>(base + off_c);
-    const bool row_alias = reflect_alias(h, H, p) != NO_ALIAS;
-    for (int i = tid; i < Wseg * CV; i += RS_THREADS) {
-      const int wl = i >> cv_sh;  // column within the segment
-      const int w = w_lo + wl;
-      float a[V], b[V], c[V];
-      load_vec<T, V>(arow + (size_t)(w - a0) * C + cv * V, a);
-      if (p) {
-        const int wa = reflect_alias(w, W, p);  // lies in the same slot (first / last segment)
-        if (wa != NO_ALIAS) {
-          float t[V];
-          load_vec<T, V>(arow + (size_t)(wa - a0) * C + cv * V, t);
-#pragma unroll
-          for (int e = 0; e < V; ++e) a[e] += t[e];
-        }
-        if (row_alias) {
-          float t[V];
-          load_vec<T, V>(alrow + (size_t)(w - a0) * C + cv * V, t);
-#pragma unroll
-          for (int e = 0; e < V; ++e) a[e] += t[e];
+  const int ips = nseg * H;  // items per sample
+  for (int n = r0 / ips; n <= (r1 - 1) / ips; ++n) {
+    const int lo = max(r0, n * ips), hi = min(r1, (n + 1) * ips);
+    op.prepare(n, cv * V, st);
+    // this group's items of the sample: ring positions k = r - r0 with k % ngroups == grp
+    for (int r = lo + ((grp - (lo - r0)) % ngroups + ngroups) % ngroups; r < hi; r += ngroups) {
+      const int k = r - r0;
+      const int stg = k % stages;
+      const int row = r / nseg, seg = r - row * nseg;
+      const int h = row - n * H;
+      const int w_lo = seg * Wseg;
+      const int a0 = seg == 0 ? -p : w_lo;  // first A column of the slot
+      sb_mbar_wait(sb_smem(&full[stg]), (k / stages) & 1);
+      const unsigned char* base = rs_smem + (size_t)stg * stage_bytes;
+      const T* arow = reinterpret_cast<const T*>(base);
+      const T* alrow = reinterpret_cast<const T*>(base + off_alias);
+      const T* brow = reinterpret_cast<const T*>(base + off_b);
+      const T* crow = reinterpret_cast<const T*>(base + off_c);
+      const bool row_alias = reflect_alias(h, H, p) != NO_ALIAS;
+      for (int i = gt; i < Wseg * CV; i += GSZ) {
+        const int wl = i >> cv_sh;  // column within the segment
+        const int w = w_lo + wl;
+        float a[V], b[V], c[V];
+        load_vec<T, V>(arow + (size_t)(w - a0) * C + cv * V, a);
+        if (p) {
+          const int wa = reflect_alias(w, W, p);  // lies in the same slot (first / last segment)
           if (wa != NO_ALIAS) {
-            load_vec<T, V>(alrow + (size_t)(wa - a0) * C + cv * V, t);
+            float t[V];
+            load_vec<T, V>(arow + (size_t)(wa - a0) * C + cv * V, t);
 #pragma unroll
             for (int e = 0; e < V; ++e) a[e] += t[e];
           }
+          if (row_alias) {
+            float t[V];
+            load_vec<T, V>(alrow + (size_t)(w - a0) * C + cv * V, t);
+#pragma unroll
+            for (int e = 0; e < V; ++e) a[e] += t[e];
+            if (wa != NO_ALIAS) {
+              load_vec<T, V>(alrow + (size_t)(wa - a0) * C + cv * V, t);
+#pragma unroll
+              for (int e = 0; e < V; ++e) a[e] += t[e];
+            }
+          }
         }
-      }
-      if (has_b) {
-        load_vec<T, V>(brow + (size_t)wl * C + cv * V, b);
-      } else {
+        if (has_b) {
+          load_vec<T, V>(brow + (size_t)wl * C + cv * V, b);
+        } else {
 #pragma unroll
-        for (int e = 0; e < V; ++e) b[e] = 0.f;
-      }
-      if (has_c) {
-        load_vec<T, V>(crow + (size_t)wl * C + cv * V, c);
-      } else {
+          for (int e = 0; e < V; ++e) b[e] = 0.f;
+        }
+        if (has_c) {
+          load_vec<T, V>(crow + (size_t)wl * C + cv * V, c);
+        } else {
 #pragma unroll
-        for (int e = 0; e < V; ++e) c[e] = 0.f;
+          for (int e = 0; e < V; ++e) c[e] = 0.f;
+        }
+        op.run(n, h, w, cv * V, a, b, c, acc, st);
       }
-      op.run(n, h, w, cv * V, a, b, c, acc, st);
+      __syncwarp();
+      if (lane == 0) sb_mbar_arrive(sb_smem(&empty[stg]));
     }
-    __syncwarp();
-    if (lane == 0) sb_mbar_arrive(sb_smem(&empty[stg]));
+    flush(n);
   }
-  flush(cur_n);
 }
 
 // InstanceNorm / activation backward: A = g (fold), B = x, C = g2.  MODE 0 apply, 1 reductions.
@@ -1690,11 +1707,19 @@ static int row_stream_plan(const otm_tensor& A, int a_halo, const otm_tensor* B,
     const size_t stage =
         (arow * (a_halo ? 2 : 1) + ((B && B->ptr) ? xrow : 0) + ((Cc && Cc->ptr) ? xrow : 0) + 127) & ~(size_t)127;
     int stages = (int)((200 * 1024 - 256 - scratch) / stage);
-    if (stages < 3 && nseg < 8 && A.w % (2 * nseg) == 0 && A.w / (2 * nseg) >= 2 * a_halo + 2) continue;
+    // prefer a ring of RS_GROUPS or 2 * RS_GROUPS stages (grouped consumers): split further
+    const bool can_split = nseg < 8 && A.w % (2 * nseg) == 0 && A.w / (2 * nseg) >= 2 * a_halo + 2 &&
+                           (RS_THREADS / RS_GROUPS) % CV == 0 && (A.w / (2 * nseg)) * CV >= RS_THREADS / RS_GROUPS;
+    if (stages < (RS_GROUPS > 3 ? RS_GROUPS : 3) && can_split) continue;
     if (stages < 2) return 0;
     if (stages > 8) stages = 8;
+    int groups = 1;
+    if (RS_GROUPS > 1 && stages >= RS_GROUPS && (RS_THREADS / RS_GROUPS) % CV == 0) {
+      groups = RS_GROUPS;
+      stages -= stages % RS_GROUPS;
+    }
     *smem_bytes = stage * stages + 2 * 8 * stages + scratch + 64;
-    return stages | (nseg << 8);
+    return stages | (nseg << 8) | (groups << 16);
   }
   return 0;
 }
@@ -1704,7 +1729,7 @@ static int launch_row_stream(const OP& op, int N, int H, int W, int C, int stage
                              float* red_out, cudaStream_t st) {
   auto kern = row_stream_kernel<T, OP>;
   OTM_ENSURE_SMEM(kern, 200 * 1024);
-  int grid = num_sms();  // `stages` = stages | nseg << 8 as row_stream_plan returns it
+  int grid = num_sms();  // `stages` = stages | nseg << 8 | groups << 16 as row_stream_plan returns it
   if (grid > N * H) grid = N * H;
   kern<<<grid, RS_THREADS + 32, smem, st>>>(op, N, H, W, C, stages, red_out);
   OTM_LAUNCH_CHECK();

@@ -90,8 +90,10 @@ def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None,
     a.cs = L.ptr(cs)
     a.path = path
     ws = None
-    if use_ws and L.lib.otm_conv_wgrad_uses_tcgen05(_byref(a)):
-        ws = torch.empty(dw.numel(), dtype=torch.float32, device=dw.device)
+    if use_ws:
+        nbytes = L.lib.otm_conv_wgrad_workspace_bytes(_byref(a))
+        if nbytes:
+            ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dw.device)
     a.ws = L.ptr(ws)
     a.wfwd = L.ptr(wfwd)
     a.P = L.ptr(P)

@@ -8,6 +8,8 @@ straight into the all-reduce bucket and the update is a single 128-bit-vectorise
 
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -15,6 +17,13 @@ from . import kernels as K
 from . import ops
 
 _ALIGN = 64  # elements; keeps every tensor 256-byte aligned inside the arena
+
+
+# OTM_DDP_OVERLAP=0: every gradient all-reduce is waited for where it is issued, i.e. the NCCL
+# kernels never run beside compute kernels.  Overlap hides the transfer but NCCL's CTAs take SMs
+# from the persistent one-CTA-per-SM kernels running beside them (each of those then needs a
+# second wave); which side wins depends on the world size.
+OVERLAP = os.environ.get("OTM_DDP_OVERLAP", "1") != "0"
 
 
 class GradArena:
@@ -87,8 +96,12 @@ class GradArena:
             if start < hi and lo < end:
                 raise ValueError(f"all-reduce bucket [{start},{end}) overlaps [{lo},{hi})")
         self._issued.append((start, end))
-        self._pending.append(dist.all_reduce(self.grad_arena[start:end], op=dist.ReduceOp.SUM,
-                                             group=self.group, async_op=True))
+        work = dist.all_reduce(self.grad_arena[start:end], op=dist.ReduceOp.SUM, group=self.group,
+                               async_op=True)
+        if OVERLAP:
+            self._pending.append(work)
+        else:
+            work.wait()  # the compute stream waits here: the collective runs alone on the GPU
 
     def _missing(self):
         gaps, pos = [], 0

@@ -376,3 +376,51 @@ def test_stage_discriminator_layer_bf16(K, oracle128):
     scale = ref[2].abs().max().item()
     assert ref[3].abs().max().item() < 1e-3 * scale and torch.isfinite(got[3]).all()
     print("discriminator layer:", "; ".join(report))
+
+
+@pytest.mark.parametrize("case", [(32, 128, 128, 64, 64, 3, 1, 1), (8, 64, 128, 128, 128, 3, 1, 0),
+                                  (16, 128, 256, 31, 31, 4, 1, 0), (32, 64, 128, 63, 63, 4, 1, 0)])
+def test_conv_epilogue_instnorm_statistics(case):
+    """otm_conv_fwd_args.stat_sums: the transposed pair kernel accumulates sum / sum of squares of
+    its output per (n, channel) in its epilogue (even, odd and partial-tile sizes; with bias);
+    otm_instnorm_finalize turns them into (mean, rstd).  Against nn.InstanceNorm2d's statistics
+    of the stored bf16 output (reference blocks.py:23,27)."""
+    import math
+
+    from one_to_many_gan_b200 import kernels as K
+
+    n, cin, cout, h, w, k, pad, halo = case
+    dev = "cuda"
+    torch.manual_seed(0)
+    x = K.alloc(n, cin, h, w, torch.bfloat16, dev, halo, zero=True)
+    K.padded_view(x, halo).normal_()
+    wt = torch.randn(cout, cin, k, k, device=dev)
+    bias = torch.randn(cout, device=dev)
+    wp = K.weight_pack(wt, 1 / math.sqrt(cin * k * k), torch.bfloat16)
+    y, st = K.conv_fwd(x, wp, cout, k, k, pad, x_halo=halo, bias=bias, want_stats=True)
+    y_plain = K.conv_fwd(x, wp, cout, k, k, pad, x_halo=halo, bias=bias)
+    assert torch.equal(y, y_plain)  # the statistics do not disturb the output
+    yf = y.float()
+    mean = yf.mean(dim=(2, 3))
+    rstd = torch.rsqrt(yf.var(dim=(2, 3), unbiased=False) + 1e-5)
+    assert (st[..., 0] - mean).abs().max().item() < 2e-3
+    assert ((st[..., 1] - rstd).abs() / rstd).max().item() < 2e-3
+
+
+def test_wgrad_workspace_query():
+    """The caller allocates the tcgen05 wgrad's fp32 workspace from otm_conv_wgrad_workspace_bytes
+    (SURVEY 8(b) otm_query_workspace): taps * Cin * Cout floats on the tensor-core path, 0 on FFMA."""
+    from one_to_many_gan_b200 import _lib as L
+    from one_to_many_gan_b200 import kernels as K
+
+    def query(cin, cout, dtype):
+        x = K.alloc(2, cin, 16, 16, dtype, "cuda", 0, zero=True)
+        dy = K.alloc(2, cout, 16, 16, dtype, "cuda", 0, zero=True)
+        a = L.ConvWgradArgs()
+        a.x, a.dy = L.tdesc(x), L.tdesc(dy)
+        a.kh, a.kw, a.pad = 3, 3, 1
+        return L.lib.otm_conv_wgrad_workspace_bytes(K._byref(a))
+
+    assert query(128, 128, torch.bfloat16) == 4 * 9 * 128 * 128
+    assert query(128, 128, torch.float32) == 0
+    assert query(32, 32, torch.bfloat16) == 0
