@@ -24,6 +24,7 @@ import random
 import torch
 
 from . import ops, training
+from .optim import all_reduce_buckets
 
 
 class PoolIndexer:
@@ -210,8 +211,7 @@ class TrainIteration:
     def _decoder_grads_final(self):
         """Autograd is about to run the encoder backward: decoder, to_style and style-extractor
         gradients are complete (verified by test_engine_gpu.test_bucket_gradients_are_final)."""
-        self.oG.all_reduce_async(self.g_dec_start, self.oG.numel)
-        self.oS.all_reduce_async()
+        all_reduce_buckets([(self.oG, self.g_dec_start, None), (self.oS, 0, None)])
         if self.on_decoder_grads_final is not None:
             self.on_decoder_grads_final()
 
@@ -246,8 +246,12 @@ class TrainIteration:
         self.losses[3:].copy_(torch.cat([v.detach().reshape(1).float() for v in losses]))
 
     def _update_gms(self):
-        for o in (self.oG, self.oM, self.oS):
-            o.wait_all_reduce()  # issues the buckets not launched yet (G encoder slice, M)
+        # the buckets not launched yet (G encoder slice, M; everything without overlap) as one
+        # coalesced collective, then wait for all of them
+        opts = (self.oG, self.oM, self.oS)
+        all_reduce_buckets([(o, lo, hi) for o in opts for lo, hi in o._missing()])
+        for o in opts:
+            o.wait_all_reduce()
         self.oG.step(reduced=True)
         self.oM.step(reduced=True)
         self.oS.step(reduced=True)

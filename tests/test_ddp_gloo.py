@@ -50,6 +50,20 @@ def _worker(rank, world, port, out):
         out.put("ok")
     arena.zero_grad()
     assert float(arena.grad_arena.abs().sum()) == 0.0
+    # coalesced exchange over two arenas (engine: G decoder slice + S, then G encoder slice + M):
+    # one collective, bucket bookkeeping per arena, the second call fills exactly the gaps
+    from one_to_many_gan_b200.optim import all_reduce_buckets
+
+    other = GradArena(torch.nn.Linear(4, 4).parameters())
+    arena.grad_arena.fill_(float(rank + 1))
+    other.grad_arena.fill_(10.0 * (rank + 1))
+    cut = arena.offsets[2]
+    all_reduce_buckets([(arena, cut, None), (other, 0, None)])
+    all_reduce_buckets([(a, lo, hi) for a in (arena, other) for lo, hi in a._missing()])
+    for a in (arena, other):
+        a.wait_all_reduce()
+    assert torch.all(arena.grad_arena == 3.0) and torch.all(other.grad_arena == 30.0)
+    assert arena._issued == [] and other._pending == []
     dist.barrier()
     dist.destroy_process_group()
 
