@@ -156,3 +156,21 @@ def test_stream_up(K, shape):
     want = rp.up_sample(x, kern)
     out = K.up(to_nhwc(K, x))
     assert relerr(out.float(), want) < TOL[torch.bfloat16], shape
+
+
+@pytest.mark.parametrize("shape", [(16, 128, 64, 64), (4, 64, 128, 128), (8, 256, 32, 32), (16, 128, 63, 31),
+                                   (4, 128, 48, 80)])
+def test_stream_up_bwd(K, shape):
+    """UpSample backward at bench scale (2 x 2 block kernel: interior, border and odd-size blocks),
+    with and without the per-(n, c) style scale, against autograd of the oracle's UpSample."""
+    from oracle import reference_port as rp
+
+    kern = rp._smooth_kernel().cuda()
+    n, c, h, w = shape
+    x = rnd(n, c, h, w, seed=15).requires_grad_(True)
+    g = rnd(n, c, 2 * h, 2 * w, seed=16).bfloat16().float()
+    (want,) = torch.autograd.grad(rp.up_sample(x, kern), x, g)
+    gt = to_nhwc(K, g)
+    assert relerr(K.up_bwd(gt).float(), want) < TOL[torch.bfloat16], shape
+    s = torch.rand(n, c, device="cuda") + 0.5
+    assert relerr(K.up_bwd(gt, scale=s).float(), want * s[:, :, None, None]) < TOL[torch.bfloat16], shape
