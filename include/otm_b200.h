@@ -94,12 +94,52 @@ typedef struct {
                            * consumer (reference blocks.py:23,27; nn.InstanceNorm2d) without a
                            * separate read of y.  Zeroed by this call.  Only when
                            * otm_conv_fwd_fuses_stats() says so; finish with otm_instnorm_finalize. */
+  int32_t residual_mode;  /* 0: y = epi(v) + residual (above).
+                           * 1 ("gate"): `residual` is not added, it GATES the result and is
+                           *   reduced against the raw product:
+                           *     y[n,h,w,o]     = residual != 0 ? v * row_scale * post_scale : 0
+                           *     dot_sums[n,o]  = sum_hw v * residual         (v = alpha * conv)
+                           *   This is the input-side pass of a modulated conv's backward
+                           *   (otm_mod_in with relu_mask) done in the dgrad's epilogue: `residual`
+                           *   is the (style-scaled, so possibly negative) ReLU output the gradient
+                           *   is taken w.r.t.  bias must be NULL
+                           *   and act NONE.  Only when otm_conv_fwd_fuses_gate() says so.
+                           * 2 ("dot"): as 1 without the gate -- y = v * row_scale * post_scale,
+                           *   dot_sums = sum_hw v * residual: the style-gradient reduction of an
+                           *   up-sampling modulated conv (otm_mod_in with no gx) in its dgrad. */
+  float* dot_sums;        /* [n, Cout] fp32 (mode 1), zeroed by this call */
 } otm_conv_fwd_args;
 int otm_conv_fwd(const otm_conv_fwd_args* a, otm_stream stream);
 /* 1 if the tcgen05 path would be used for these arguments, 0 if SIMT */
 int otm_conv_fwd_uses_tcgen05(const otm_conv_fwd_args* a);
 /* 1 if this call would run on the kernel whose epilogue can accumulate stat_sums */
 int otm_conv_fwd_fuses_stats(const otm_conv_fwd_args* a);
+/* 1 if this call would run on the kernel whose epilogue implements residual_mode 1 */
+int otm_conv_fwd_fuses_gate(const otm_conv_fwd_args* a);
+
+/* Reflect-border correction of a 3x3 dgrad.  The gradient of conv3x3(ReflectionPad2d(1)(x))
+ * (reference blocks.py:21-27,49-56) w.r.t. x is the zero-padded "same" correlation of dy with
+ * the flipped pack -- one otm_conv_fwd call with pad = 1 on the H x W output, no padded
+ * (H+2) x (W+2) intermediate and no fold pass -- PLUS the contributions of the 2(H+W)+4 halo
+ * positions, which land on rows / columns 1 and H-2 / W-2.  This call computes those as four
+ * thin GEMMs (one per border line: positions x 3 taps x K) on warp-level tensor cores and adds
+ * them into y with the same per-channel epilogue as the main call:
+ *   y[n, refl(a), refl(b), o] += f(n,o) * gxp[a,b,o]   for (a,b) on the halo ring,
+ *   gxp[a,b,o] = sum_{r,s,i} dy[n, a+r-1, b+s-1, i] * wpack[nb][o][r][s][i],
+ *   f = row_scale * post_scale, and with `gate`: f *= (gate[n,refl(a),refl(b),o] != 0),
+ *   dot_sums[n,o] += gxp * gate  (accumulated, NOT zeroed: call it after the main otm_conv_fwd).
+ * bf16 only; K % 16 == 0, Cout % 64 == 0, H, W >= 3. */
+typedef struct {
+  otm_tensor dy;          /* [n, K, H, W]: the input of the dgrad call */
+  const void* wpack;      /* [wbatch][Cout][3][3][K] (the dgrad pack of otm_weight_pack) */
+  int64_t w_batch_stride; /* 0 = shared */
+  otm_tensor y;           /* [n, Cout, H, W], accumulated into */
+  const float* row_scale; /* [n, Cout] or NULL */
+  const float* post_scale;
+  otm_tensor gate;        /* ptr NULL = none */
+  float* dot_sums;        /* [n, Cout] or NULL */
+} otm_conv_reflect_border_args;
+int otm_conv_reflect_border(const otm_conv_reflect_border_args* a, otm_stream stream);
 
 /* wgrad:  dw[o][i][r][s] (fp32, torch parameter layout [Cout,Cin,kh,kw], ACCUMULATED into)
  *   += alpha * sum_{n,h,w} rs[n,o] * cs[n,i] * dy[n,h,w,o] * x[n, h+r-pad, w+s-pad, i]

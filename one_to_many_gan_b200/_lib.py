@@ -53,6 +53,21 @@ class ConvFwdArgs(C.Structure):
         ("path", C.c_int32),
         ("post_scale", C.c_void_p),
         ("stat_sums", C.c_void_p),
+        ("residual_mode", C.c_int32),
+        ("dot_sums", C.c_void_p),
+    ]
+
+
+class ConvReflectBorderArgs(C.Structure):
+    _fields_ = [
+        ("dy", Tensor),
+        ("wpack", C.c_void_p),
+        ("w_batch_stride", C.c_int64),
+        ("y", Tensor),
+        ("row_scale", C.c_void_p),
+        ("post_scale", C.c_void_p),
+        ("gate", Tensor),
+        ("dot_sums", C.c_void_p),
     ]
 
 
@@ -242,6 +257,8 @@ SYMBOLS = {
     "otm_conv_fwd": (C.c_int, [_P(ConvFwdArgs), C.c_void_p]),
     "otm_conv_fwd_uses_tcgen05": (C.c_int, [_P(ConvFwdArgs)]),
     "otm_conv_fwd_fuses_stats": (C.c_int, [_P(ConvFwdArgs)]),
+    "otm_conv_fwd_fuses_gate": (C.c_int, [_P(ConvFwdArgs)]),
+    "otm_conv_reflect_border": (C.c_int, [_P(ConvReflectBorderArgs), C.c_void_p]),
     "otm_conv_wgrad": (C.c_int, [_P(ConvWgradArgs), C.c_void_p]),
     "otm_conv_wgrad_uses_tcgen05": (C.c_int, [_P(ConvWgradArgs)]),
     "otm_conv_wgrad_fuses_P": (C.c_int, [_P(ConvWgradArgs)]),

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libotm_b200.so"
-SOURCES = ["pointwise.cu", "conv_simt.cu", "conv_tc.cu", "loss_optim.cu", "style.cu"]
+SOURCES = ["pointwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_border.cu", "loss_optim.cu", "style.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -186,6 +186,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+}
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.x4.trans.m8n8.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -229,6 +232,8 @@ struct TcFwdP {
   const float* row_scale;
   const float* post_scale;  // [n, cout] applied AFTER the activation (NULL = 1)
   float* stat_sums;         // [n, cout, 2] sum / sum of squares of the stored values, or NULL
+  float* dot_sums;          // [n, cout] sum_hw v * residual (gate mode of the transposed pair kernel)
+  int res_mode;             // 0: add the residual; 1: gate by it; 2: dot only (otm_conv_fwd_args.residual_mode)
   const float* bias;
   float alpha;
   int act, y_halo;
@@ -911,6 +916,8 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     //   2 + x   stage x is free again (finishing warps arrive, epilogue warps wait)
     //   4 + x   stage x holds a finished half-tile (epilogue warps arrive, finishing warps wait)
     const int wq = warp - 4;
+    const bool gate_mode = has_res && p.res_mode != 0;
+    const bool nomask = p.res_mode == 2;  // dot only
     int lt = 0, hc = 0;  // tiles / half-tiles done by this CTA
     for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x, ++lt) {
       int n, h0, w0, o0;
@@ -925,6 +932,8 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         bias[j] = p.bias ? p.bias[ch] : 0.f;
         post[j] = p.post_scale ? p.post_scale[(long long)n * p.cout + ch] : 1.f;
       }
+      const float gsc[4] = {scale[0] * post[0], scale[1] * post[1], scale[2] * post[2],
+                            scale[3] * post[3]};
       mbar_wait(smem_u32(&tmem_full[buf]), (lt >> 1) & 1);
       tc_fence_after();
       const int nhalf = (h0 + TH) < p.y.h ? 2 : 1;
@@ -959,6 +968,33 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (j2 < 3) {
             tmem_ld_16x256b_x4(tacc + (uint32_t)((j2 + 1) * 32), va[(j2 + 1) & 1]);
             tmem_ld_16x256b_x4(tacc + (uint32_t)((j2 + 1) * 32) + (16u << 16), vb[(j2 + 1) & 1]);
+          }
+          if (gate_mode) {
+            // residual_mode 1: the staged tile gates the result (ReLU backward through h~ = s * ReLU(u),
+            // s of either sign: the mask is h~ != 0, as in otm_mod_in) and
+            // is reduced against the raw accumulator; same fragment layout as the store below
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t sa = st_base + (uint32_t)((j2 * 32 + k * 8) * 128);
+              uint32_t rr[4];
+              ldmatrix_x4_trans(sa, rr);
+              const float2 g0 = bf16x2_to_float2(rr[0]), g1 = bf16x2_to_float2(rr[1]);
+              const float2 g2 = bf16x2_to_float2(rr[2]), g3 = bf16x2_to_float2(rr[3]);
+              ssum[0] = fmaf(xa[4 * k], g0.x, fmaf(xa[4 * k + 1], g0.y, ssum[0]));
+              ssum[1] = fmaf(xa[4 * k + 2], g1.x, fmaf(xa[4 * k + 3], g1.y, ssum[1]));
+              ssum[2] = fmaf(xb[4 * k], g2.x, fmaf(xb[4 * k + 1], g2.y, ssum[2]));
+              ssum[3] = fmaf(xb[4 * k + 2], g3.x, fmaf(xb[4 * k + 3], g3.y, ssum[3]));
+              const uint32_t o0 = pack_bf16x2((nomask || g0.x != 0.f) ? xa[4 * k] * gsc[0] : 0.f,
+                                              (nomask || g0.y != 0.f) ? xa[4 * k + 1] * gsc[0] : 0.f);
+              const uint32_t o1 = pack_bf16x2((nomask || g1.x != 0.f) ? xa[4 * k + 2] * gsc[1] : 0.f,
+                                              (nomask || g1.y != 0.f) ? xa[4 * k + 3] * gsc[1] : 0.f);
+              const uint32_t o2 = pack_bf16x2((nomask || g2.x != 0.f) ? xb[4 * k] * gsc[2] : 0.f,
+                                              (nomask || g2.y != 0.f) ? xb[4 * k + 1] * gsc[2] : 0.f);
+              const uint32_t o3 = pack_bf16x2((nomask || g3.x != 0.f) ? xb[4 * k + 2] * gsc[3] : 0.f,
+                                              (nomask || g3.y != 0.f) ? xb[4 * k + 3] * gsc[3] : 0.f);
+              stmatrix_x4_trans(sa, o0, o1, o2, o3);
+            }
+            continue;
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -1023,7 +1059,19 @@ conv_tc_fwd_rr2t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tc_fence_before();
         if (half == nhalf - 1) mbar_arrive(smem_u32(&tmem_empty[buf]));  // accumulator drained
       }
-      if (p.stat_sums) {
+      if (gate_mode && p.dot_sums) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 1);
+          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 2);
+        }
+        if ((lane & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            atomicAdd(p.dot_sums + (long long)n * p.cout + o0 + wq * 32 + 8 * j + (lane >> 2),
+                      ssum[j] * p.alpha);
+        }
+      } else if (p.stat_sums) {
         // the 4 lanes of a quad hold the same channels (different pixel columns)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1748,6 +1796,8 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
   p.res = a->residual.ptr ? make_view(a->residual) : null_view();
   p.row_scale = a->row_scale; p.post_scale = a->post_scale; p.bias = a->bias; p.alpha = a->alpha;
   p.stat_sums = nullptr;
+  p.dot_sums = nullptr;
+  p.res_mode = 0;
   p.act = a->act;
   p.y_halo = a->y_halo; p.cin = cin; p.cout = cout; p.kh = KS; p.kw = KS;
   p.coord_off = a->x_halo - a->pad;
@@ -1770,6 +1820,12 @@ int conv_fwd_tc(const otm_conv_fwd_args* a, cudaStream_t st) {
       if (a->stat_sums) {
         p.stat_sums = a->stat_sums;
         OTM_CHECK_CUDA(cudaMemsetAsync(a->stat_sums, 0, sizeof(float) * 2 * (size_t)a->y.n * cout, st));
+      }
+      if (a->residual_mode != 0 && a->residual.ptr) {
+        p.res_mode = a->residual_mode;
+        p.dot_sums = a->dot_sums;
+        if (a->dot_sums)
+          OTM_CHECK_CUDA(cudaMemsetAsync(a->dot_sums, 0, sizeof(float) * (size_t)a->y.n * cout, st));
       }
       CUtensorMap tmR = tmY;  // residual: same boxes as the output tile, its own strides
       if (a->residual.ptr) {
@@ -1968,6 +2024,8 @@ int otm_conv_fwd_fuses_stats(const otm_conv_fwd_args* a) {
   return conv_fwd_tc_uses_rr2t(a) ? 1 : 0;
 }
 
+int otm_conv_fwd_fuses_gate(const otm_conv_fwd_args* a) { return otm_conv_fwd_fuses_stats(a); }
+
 int otm_conv_fwd(const otm_conv_fwd_args* a, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int rc = validate_fwd(a);
@@ -1977,6 +2035,15 @@ int otm_conv_fwd(const otm_conv_fwd_args* a, otm_stream stream) {
     OTM_REQUIRE(tc && a->path != OTM_PATH_SIMT && conv_fwd_tc_uses_rr2t(a),
                 "conv_fwd: stat_sums given but this launch cannot accumulate them "
                 "(ask otm_conv_fwd_fuses_stats first)");
+  if (a->residual_mode != 0) {
+    OTM_REQUIRE(a->residual_mode == 1 || a->residual_mode == 2, "conv_fwd: unknown residual_mode %d",
+                a->residual_mode);
+    OTM_REQUIRE(a->residual.ptr && !a->bias && a->act == OTM_ACT_NONE && !a->stat_sums,
+                "conv_fwd: residual_mode 1 needs a gate tensor, no bias, no activation, no stat_sums");
+    OTM_REQUIRE(tc && a->path != OTM_PATH_SIMT && conv_fwd_tc_uses_rr2t(a),
+                "conv_fwd: residual_mode 1 is not available for this launch "
+                "(ask otm_conv_fwd_fuses_gate first)");
+  }
   if (a->path == OTM_PATH_TCGEN05 && !tc)
     return fail(OTM_ERR_UNSUPPORTED, "conv_fwd: tcgen05 path not available for this shape/dtype");
   if (tc && a->path != OTM_PATH_SIMT) return conv_fwd_tc(a, st);

@@ -74,6 +74,101 @@ def conv_fwd(x, wpack, cout, kh, kw, pad, *, x_halo=0, y_halo=0, alpha=1.0, row_
     return out, instnorm_stats(out, eps)
 
 
+def conv_fwd_dot(x, wpack, cout, pad, aux):
+    """3x3 conv_fwd (shared pack) that also returns dot[n, o] = sum_hw y * aux from its epilogue
+    (residual_mode 2), or None when this launch cannot fuse it."""
+    n, cin, h, w = x.shape
+    out = alloc(n, cout, h + 2 * pad - 2, w + 2 * pad - 2, x.dtype, x.device)
+    a = L.ConvFwdArgs()
+    a.x = L.tdesc(x)
+    a.wpack = L.ptr(wpack)
+    a.kh, a.kw, a.pad = 3, 3, pad
+    a.y = L.tdesc(out)
+    a.alpha = 1.0
+    a.act = ACT_NONE
+    a.path = PATH_AUTO
+    if x.dtype != torch.bfloat16 or not L.lib.otm_conv_fwd_fuses_gate(_byref(a)):
+        return None
+    dot = torch.empty((n, cout), dtype=torch.float32, device=x.device)
+    a.residual = L.tdesc(aux)
+    a.residual_mode = 2
+    a.dot_sums = L.ptr(dot)
+    L.check(L.lib.otm_conv_fwd(_byref(a), L.stream_ptr()), "otm_conv_fwd")
+    return out, dot
+
+
+def _dgrad_reflect_args(g, wpack_t, cin, per_sample, out):
+    a = L.ConvFwdArgs()
+    a.x = L.tdesc(g)
+    a.x_halo = 0
+    a.wpack = L.ptr(wpack_t)
+    a.w_batch_stride = cin * 9 * g.shape[1] if per_sample else 0
+    a.kh, a.kw, a.pad = 3, 3, 1
+    a.y = L.tdesc(out)
+    a.y_halo = 0
+    a.alpha = 1.0
+    a.act = ACT_NONE
+    a.path = PATH_AUTO
+    return a
+
+
+def dgrad_reflect_ok(g, cin) -> bool:
+    """Can conv_dgrad_reflect run for this upstream gradient?  (bf16 on the tcgen05 path, channel
+    counts the border kernel tiles, an image the reflect pad is defined on)"""
+    n, k, h, w = g.shape
+    return g.dtype == torch.bfloat16 and k % 64 == 0 and cin % 64 == 0 and h >= 3 and w >= 3
+
+
+def conv_dgrad_reflect(g, wpack_t, cin, *, per_sample=False, residual=None, gate=None,
+                       row_scale=None, post_scale=None, want_dot=False):
+    """Gradient of conv3x3(ReflectionPad2d(1)(x)) w.r.t. x, [n, cin, H, W], WITHOUT the padded
+    (H+2) x (W+2) intermediate: the zero-padded "same" dgrad on the tcgen05 path plus
+    otm_conv_reflect_border for the halo ring (reference blocks.py:21-27,49-56 backward).
+    wpack_t: the dgrad pack (weight_pack(..., transpose=True)).
+      residual: added to the result (the block's skip gradient);
+      gate: (style-scaled) ReLU output the gradient is taken w.r.t. -- result = (gate != 0) * row_scale *
+            post_scale * dgrad, and with want_dot also dot[n, c] = sum_hw dgrad * gate
+            (the otm_mod_in pass of a modulated conv, done in the dgrad epilogue).
+    Returns y or (y, dot).  The caller checks dgrad_reflect_ok / dgrad_reflect_fuses_gate."""
+    n, k, h, w = g.shape
+    out = alloc(n, cin, h, w, g.dtype, g.device)
+    a = _dgrad_reflect_args(g, wpack_t, cin, per_sample, out)
+    a.row_scale = L.ptr(row_scale)
+    a.post_scale = L.ptr(post_scale)
+    dot = None
+    if gate is not None:
+        a.residual = L.tdesc(gate)
+        a.residual_mode = 1
+        if want_dot:
+            dot = torch.empty((n, cin), dtype=torch.float32, device=g.device)
+            a.dot_sums = L.ptr(dot)
+    else:
+        a.residual = L.tdesc(residual)
+    L.check(L.lib.otm_conv_fwd(_byref(a), L.stream_ptr()), "otm_conv_fwd")
+    b = L.ConvReflectBorderArgs()
+    b.dy = L.tdesc(g)
+    b.wpack = L.ptr(wpack_t)
+    b.w_batch_stride = a.w_batch_stride
+    b.y = L.tdesc(out)
+    b.row_scale = L.ptr(row_scale)
+    b.post_scale = L.ptr(post_scale)
+    b.gate = L.tdesc(gate)
+    b.dot_sums = L.ptr(dot)
+    L.check(L.lib.otm_conv_reflect_border(_byref(b), L.stream_ptr()), "otm_conv_reflect_border")
+    return (out, dot) if want_dot else out
+
+
+def dgrad_reflect_fuses_gate(g, wpack_t, cin, per_sample=False) -> bool:
+    """Would the main launch of conv_dgrad_reflect run on the kernel that implements the gate?"""
+    if not dgrad_reflect_ok(g, cin):
+        return False
+    n, k, h, w = g.shape
+    a = _dgrad_reflect_args(g, wpack_t, cin, per_sample, g)
+    # only the geometry / dtype / alignment of y decide the kernel: describe a dense y from g
+    a.y.c, a.y.sw, a.y.sh, a.y.sn = cin, cin, cin * w, cin * w * h
+    return bool(L.lib.otm_conv_fwd_fuses_gate(_byref(a)))
+
+
 def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None, path=PATH_AUTO,
                use_ws=True, wfwd=None, P=None, wfwd_per_sample=True):
     """P (zeroed [n, Cout] fp32) + wfwd (forward pack: per-sample, or the shared one when x

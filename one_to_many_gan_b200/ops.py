@@ -302,15 +302,26 @@ class ResBlockFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             buf, gw2 = _wgrad_buffer(w2)
             K.conv_wgrad(t, g_raw2, buf, 3, 3, 1, x_halo=1, alpha=eq_scale(w2))
-        gt_p = K.conv_fwd(g_raw2, _pack(w2, g.dtype, True), f, 3, 3, 2)
-        g_raw1 = K.norm_act_bwd(gt_p[:, :, 1 : 1 + h, 1 : 1 + w], raw1, st1, ACT_RELU, g_halo=1)
+        # dgrad through ReflectionPad2d(1): "same" dgrad + halo-ring correction where the library
+        # has it (bf16), else the padded (h+2) x (w+2) dgrad folded by the next pass
+        direct = K.dgrad_reflect_ok(g_raw2, f)
+        if direct:
+            gt = K.conv_dgrad_reflect(g_raw2, _pack(w2, g.dtype, True), f)
+            g_raw1 = K.norm_act_bwd(gt, raw1, st1, ACT_RELU)
+        else:
+            gt_p = K.conv_fwd(g_raw2, _pack(w2, g.dtype, True), f, 3, 3, 2)
+            g_raw1 = K.norm_act_bwd(gt_p[:, :, 1 : 1 + h, 1 : 1 + w], raw1, st1, ACT_RELU, g_halo=1)
         if ctx.needs_input_grad[1]:
             buf, gw1 = _wgrad_buffer(w1)
             K.conv_wgrad(x, g_raw1, buf, 3, 3, 1, x_halo=1, alpha=eq_scale(w1))
         gx = None
         if ctx.needs_input_grad[0]:
-            gx_p = K.conv_fwd(g_raw1, _pack(w1, g.dtype, True), f, 3, 3, 2)
-            gx = K.norm_act_bwd(gx_p[:, :, 1 : 1 + h, 1 : 1 + w], None, None, ACT_NONE, g_halo=1, g2=g)
+            if direct:  # the skip gradient is the dgrad's residual: no fold + add pass
+                gx = K.conv_dgrad_reflect(g_raw1, _pack(w1, g.dtype, True), f, residual=g)
+            else:
+                gx_p = K.conv_fwd(g_raw1, _pack(w1, g.dtype, True), f, 3, 3, 2)
+                gx = K.norm_act_bwd(gx_p[:, :, 1 : 1 + h, 1 : 1 + w], None, None, ACT_NONE, g_halo=1,
+                                    g2=g)
         return gx, gw1, gw2, None
 
 
@@ -413,8 +424,13 @@ class UpModConvFn(torch.autograd.Function):
         gu, P = K.mod_out(g, y, act=ctx.act, gy_scale=sig)  # gu = sigma_inv * act'(y) * g
         dw, dw_ret = _wgrad_buffer(weight)
         K.conv_wgrad(xt, gu, dw, 3, 3, 1, alpha=c)
-        gxt = K.conv_fwd(gu, _pack(weight, gu.dtype, True), weight.shape[1], 3, 3, 1)
-        _, Qt = K.mod_in(gxt, xt, s, want_gx=False)         # sum_hw gxt * x~  (= s * Q)
+        # Qt = sum_hw gxt * x~ (= s * Q): from the dgrad's epilogue where the launch can
+        fused = K.conv_fwd_dot(gu, _pack(weight, gu.dtype, True), weight.shape[1], 1, xt)
+        if fused is not None:
+            gxt, Qt = fused
+        else:
+            gxt = K.conv_fwd(gu, _pack(weight, gu.dtype, True), weight.shape[1], 3, 3, 1)
+            _, Qt = K.mod_in(gxt, xt, s, want_gx=False)
         ds = K.mod_bwd(weight.detach(), c, s, sig, _sqsum(weight), P, Qt, dw, q_scaled=True)
         gz = K.up_bwd(gxt, scale=s) if ctx.needs_input_grad[0] else None
         return gz, ds, dw_ret, None, None
@@ -471,16 +487,30 @@ class ModResBlockFn(torch.autograd.Function):
             _, P2 = K.mod_out(g, out, res=x, materialise=False)
             K.conv_wgrad(ht, g, dw2, 3, 3, 1, x_halo=1, alpha=c2, rs=sig2)
         wpt2 = K.weight_pack(w2.detach(), c2, g.dtype, rs=sig2, nb=n, transpose=True)
-        ght_p = K.conv_fwd(g, wpt2, f, 3, 3, 2, per_sample=True)
-        gu1, Qt2 = K.mod_in(ght_p[:, :, 1 : 1 + h, 1 : 1 + w], ht, s2, g_halo=1, relu_mask=True,
-                            gx_scale=sig1)
+        direct = K.dgrad_reflect_ok(g, f)
+        if direct and K.dgrad_reflect_fuses_gate(g, wpt2, f, per_sample=True):
+            # the input-side pass runs in the dgrad's epilogue: gate by ReLU(h~), s2 * sigma1 as
+            # the row / post scale, Q~2 reduced against the raw accumulator
+            gu1, Qt2 = K.conv_dgrad_reflect(g, wpt2, f, per_sample=True, gate=ht, row_scale=s2,
+                                            post_scale=sig1, want_dot=True)
+        elif direct:
+            ght = K.conv_dgrad_reflect(g, wpt2, f, per_sample=True)
+            gu1, Qt2 = K.mod_in(ght, ht, s2, relu_mask=True, gx_scale=sig1)
+        else:
+            ght_p = K.conv_fwd(g, wpt2, f, 3, 3, 2, per_sample=True)
+            gu1, Qt2 = K.mod_in(ght_p[:, :, 1 : 1 + h, 1 : 1 + w], ht, s2, g_halo=1, relu_mask=True,
+                                gx_scale=sig1)
         ds2 = K.mod_bwd(w2.detach(), c2, s2, sig2, _sqsum(w2), P2, Qt2, dw2, q_scaled=True)
         # ---- conv1: dy = gu1 (w.r.t. its raw output), P1 == Qt2 --------------------------------
         dw1, dw1_ret = _wgrad_buffer(w1)
         K.conv_wgrad(x, gu1, dw1, 3, 3, 1, x_halo=1, alpha=c1, cs=s1)
-        gxt_p = K.conv_fwd(gu1, _pack(w1, g.dtype, True), f, 3, 3, 2)
-        gx, Q1 = K.mod_in(gxt_p[:, :, 1 : 1 + h, 1 : 1 + w], x, s1, g_halo=1, gadd=g,
-                          want_gx=ctx.needs_input_grad[0])
+        if direct:
+            gxt = K.conv_dgrad_reflect(gu1, _pack(w1, g.dtype, True), f)
+            gx, Q1 = K.mod_in(gxt, x, s1, gadd=g, want_gx=ctx.needs_input_grad[0])
+        else:
+            gxt_p = K.conv_fwd(gu1, _pack(w1, g.dtype, True), f, 3, 3, 2)
+            gx, Q1 = K.mod_in(gxt_p[:, :, 1 : 1 + h, 1 : 1 + w], x, s1, g_halo=1, gadd=g,
+                              want_gx=ctx.needs_input_grad[0])
         ds1 = K.mod_bwd(w1.detach(), c1, s1, sig1, _sqsum(w1), Qt2, Q1, dw1)
         return gx, ds1, ds2, dw1_ret, dw2_ret, None
 

@@ -424,3 +424,93 @@ def test_wgrad_workspace_query():
     assert query(128, 128, torch.bfloat16) == 4 * 9 * 128 * 128
     assert query(128, 128, torch.float32) == 0
     assert query(32, 32, torch.bfloat16) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# dgrad through ReflectionPad2d(1) without the padded intermediate: "same" tcgen05 dgrad +
+# otm_conv_reflect_border, vs autograd through F.pad(reflect) + F.conv2d (reference
+# blocks.py:21-27,49-56) on the same bf16-rounded operands.
+# ---------------------------------------------------------------------------------------------
+# (n, K = channels of dy, C = channels of x, H, W); the first two are the bench's launches
+REFLECT_CASES = [(96, 128, 128, 64, 64), (64, 128, 128, 64, 64), (3, 64, 128, 40, 24),
+                 (2, 256, 256, 128, 128), (5, 128, 64, 19, 83), (2, 64, 64, 3, 3)]
+
+
+def _reflect_ref(dy, w, x_shape):
+    x = torch.zeros(x_shape, device="cuda", requires_grad=True)
+    y = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w)
+    (gx,) = torch.autograd.grad(y, x, dy)
+    return gx
+
+
+@pytest.mark.parametrize("case", REFLECT_CASES)
+@pytest.mark.parametrize("residual", [False, True])
+def test_dgrad_reflect_vs_torch(K, case, residual):
+    n, kc, c, h, w_ = case
+    dy = q(rnd(n, kc, h, w_, seed=1))
+    wt = q(rnd(kc, c, 3, 3, seed=2) / math.sqrt(9 * kc))  # conv weight [Cout = K, Cin = C, 3, 3]
+    res = q(rnd(n, c, h, w_, seed=3)) if residual else None
+    ref = _reflect_ref(dy, wt, (n, c, h, w_))
+    if residual:
+        ref = ref + res
+    g = nhwc(dy, BF)
+    assert K.dgrad_reflect_ok(g, c)
+    wpt = K.weight_pack(wt.contiguous(), 1.0, BF, transpose=True)
+    got = K.conv_dgrad_reflect(g, wpt, c, residual=None if res is None else nhwc(res, BF))
+    # identical bf16 operands, fp32 accumulation; the border pixels are rounded to bf16 up to
+    # three more times (one packed-bf16 atomic per contributing ring position): 1e-2
+    assert relerr(got.float(), ref) < 1e-2
+    # the ring targets alone (rows / columns 1 and H-2 / W-2), where the correction lives
+    rows = sorted({1, h - 2})
+    cols = sorted({1, w_ - 2})
+    assert relerr(got.float()[:, :, rows, :], ref[:, :, rows, :]) < 1.5e-2
+    assert relerr(got.float()[:, :, :, cols], ref[:, :, :, cols]) < 1.5e-2
+
+
+@pytest.mark.parametrize("case", [(96, 128, 128, 64, 64), (40, 128, 128, 40, 56),
+                                  (24, 256, 256, 64, 64)])
+def test_dgrad_reflect_gate_per_sample_vs_torch(K, case):
+    """The fused input-side pass of ModulatedResnetBlock's conv2 backward: per-sample dgrad packs
+    (sigma2 folded in), gate = ReLU output h~, row / post scale, dot = sum_hw dgrad * h~."""
+    n, kc, c, h, w_ = case
+    dy = q(rnd(n, kc, h, w_, seed=1))
+    wt = q(rnd(kc, c, 3, 3, seed=2) / math.sqrt(9 * kc))
+    sig2 = (rnd(n, kc, seed=4).abs() + 0.5).contiguous()
+    s2 = (rnd(n, c, seed=5) + 1.0).contiguous()
+    sig1 = (rnd(n, c, seed=6).abs() + 0.5).contiguous()
+    # h~ = s2 * ReLU(u): the gate is negative where its channel's style scale is
+    ht = q(torch.relu(rnd(n, c, h, w_, seed=7)) * s2[:, :, None, None])
+    g = nhwc(dy, BF)
+    wpt = K.weight_pack(wt.contiguous(), 1.0, BF, rs=sig2, nb=n, transpose=True)
+    assert K.dgrad_reflect_fuses_gate(g, wpt, c, per_sample=True)
+    got, dot = K.conv_dgrad_reflect(g, wpt, c, per_sample=True, gate=nhwc(ht, BF, halo=1),
+                                    row_scale=s2, post_scale=sig1, want_dot=True)
+    # reference on the same rounded per-sample weights: w * sigma2[n, o] rounded to bf16
+    wn = q(wt[None] * sig2[:, :, None, None, None])  # [n, K, C, 3, 3]
+    ref_raw = torch.stack([_reflect_ref(dy[i : i + 1], wn[i], (1, c, h, w_))[0] for i in range(n)])
+    ref = ref_raw * (ht != 0) * (s2 * sig1)[:, :, None, None]
+    ref_dot = (ref_raw * ht).sum((2, 3))
+    assert relerr(got.float(), ref) < 1e-2
+    assert relerr(dot, ref_dot) < 2e-3  # fp32 accumulator x bf16 gate, no intermediate rounding
+    # the unfused route (direct dgrad, then otm_mod_in) agrees with the fused one
+    ght = K.conv_dgrad_reflect(g, wpt, c, per_sample=True)
+    gu, Q = K.mod_in(ght, nhwc(ht, BF, halo=1), s2, relu_mask=True, gx_scale=sig1)
+    assert relerr(gu.float(), ref) < 1.5e-2
+    assert relerr(Q, ref_dot) < 1e-2
+
+
+@pytest.mark.parametrize("case", [(64, 64, 128, 128, 128), (20, 128, 128, 64, 64)])
+def test_conv_fwd_dot_vs_torch(K, case):
+    """residual_mode 2: the up-sampling modulated conv's style-gradient reduction
+    sum_hw dgrad * x~ out of the dgrad epilogue (zero padding 1)."""
+    n, cin, cout, h, w_ = case
+    x = q(rnd(n, cin, h, w_, seed=1))
+    wt = q(rnd(cout, cin, 3, 3, seed=2) / math.sqrt(9 * cin))
+    aux = q(rnd(n, cout, h, w_, seed=3))
+    ref = F.conv2d(x, wt, padding=1)
+    wp = K.weight_pack(wt.contiguous(), 1.0, BF)
+    r = K.conv_fwd_dot(nhwc(x, BF), wp, cout, 1, nhwc(aux, BF))
+    assert r is not None
+    y, dot = r
+    assert relerr(y.float(), ref) < 5e-3
+    assert relerr(dot, (ref * aux).sum((2, 3))) < 2e-3
