@@ -169,10 +169,19 @@ typedef struct {
   const void* wfwd;
   float* P;
   int64_t wfwd_batch_stride;
+  /* Optional fused direct style-gradient term (the other reduction of the same accumulator):
+   *   Q[n,i] += sum_{o,r,s} G_n[o,i,r,s] * wfwd[n | 0][o][r][s][i]
+   * With x the un-modulated input of a modulated conv and wfwd the shared pack alpha*w this is
+   * sum_hw (dL/d(s*x)) * x, i.e. what otm_mod_in reduces from the dgrad's output: the dgrad then
+   * needs no input-side pass (its epilogue applies s and adds the skip gradient).  Filter-column
+   * tcgen05 kernel only, rs must be NULL (otm_conv_wgrad_fuses_Q tells); Q zeroed by the caller;
+   * needs the workspace `ws`. */
+  float* Q;
 } otm_conv_wgrad_args;
 int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream);
 int otm_conv_wgrad_uses_tcgen05(const otm_conv_wgrad_args* a);
 int otm_conv_wgrad_fuses_P(const otm_conv_wgrad_args* a);
+int otm_conv_wgrad_fuses_Q(const otm_conv_wgrad_args* a);
 /* bytes of the fp32 workspace `ws` this call wants (0: none, e.g. the FFMA path): the caller
  * allocates it -- the library never owns memory ("otm_query_workspace"). */
 int64_t otm_conv_wgrad_workspace_bytes(const otm_conv_wgrad_args* a);

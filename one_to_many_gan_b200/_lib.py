@@ -88,6 +88,7 @@ class ConvWgradArgs(C.Structure):
         ("wfwd", C.c_void_p),
         ("P", C.c_void_p),
         ("wfwd_batch_stride", C.c_int64),
+        ("Q", C.c_void_p),
     ]
 
 
@@ -262,6 +263,7 @@ SYMBOLS = {
     "otm_conv_wgrad": (C.c_int, [_P(ConvWgradArgs), C.c_void_p]),
     "otm_conv_wgrad_uses_tcgen05": (C.c_int, [_P(ConvWgradArgs)]),
     "otm_conv_wgrad_fuses_P": (C.c_int, [_P(ConvWgradArgs)]),
+    "otm_conv_wgrad_fuses_Q": (C.c_int, [_P(ConvWgradArgs)]),
     "otm_conv_wgrad_workspace_bytes": (C.c_int64, [_P(ConvWgradArgs)]),
     "otm_weight_pack": (C.c_int, [_P(WeightPackArgs), C.c_void_p]),
     "otm_weight_sqsum": (

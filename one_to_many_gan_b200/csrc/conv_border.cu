@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(128) conv_reflect_border_kernel(BorderP p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
 
+  const int mt_n = min(BD_MT, (L - p0 + 15) / 16);  // m16 tiles that hold ring positions
   const __nv_bfloat16* wsample = p.wp + (long long)n * p.w_batch_stride;
   const long long wrow = 9LL * p.K;  // elements per output channel in the pack
 #pragma unroll 1
@@ -147,10 +148,12 @@ __global__ void __launch_bounds__(128) conv_reflect_border_kernel(BorderP p) {
       }
 #pragma unroll
       for (int mt = 0; mt < BD_MT; ++mt) {
-        uint32_t a[4];
-        bd_ldmatrix_x4(a, arow + (size_t)(mt * 16) * pitch + kc * 32);
-        bd_mma(acc[mt][0], a, b[0]);
-        bd_mma(acc[mt][1], a, b[1]);
+        if (mt < mt_n) {  // (warp-uniform) a 64-position vertical line has no fifth tile
+          uint32_t a[4];
+          bd_ldmatrix_x4(a, arow + (size_t)(mt * 16) * pitch + kc * 32);
+          bd_mma(acc[mt][0], a, b[0]);
+          bd_mma(acc[mt][1], a, b[1]);
+        }
       }
     }
   }

@@ -1406,6 +1406,7 @@ struct TcWgRowP {
   float* ws;                  // [tap][cout][cin] fp32
   const __nv_bfloat16* wfwd;  // forward pack [n | 1][cout][taps][cin] (fused P term) or NULL
   float* P;                   // [n][cout]
+  float* Q;                   // [n][cin]: sum_{o,tap} rs * G_n[o,i,tap] * wfwd[o][tap][i], or NULL
   const float* rs;            // [n][cout] or NULL
   const float* cs;            // [n][cin] or NULL
   float alpha;
@@ -1563,8 +1564,10 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDy,
       // the previous segment's flush has read cs_s (barrier at its end)
       if (te < 128) cs_s[te] = p.cs ? p.cs[(long long)n * p.cin + nt * 128 + te] : 1.f;
       const __nv_bfloat16* wbase =
-          p.P ? p.wfwd + (long long)n * p.wfwd_n_stride + (long long)m * 9 * p.cin + nt * 128 + c * 64
+          (p.P || p.Q)
+              ? p.wfwd + (long long)n * p.wfwd_n_stride + (long long)m * 9 * p.cin + nt * 128 + c * 64
               : nullptr;
+      float qacc[2] = {0.f, 0.f};  // this lane's column (hf * 32 + lane) of the Q term
       uint4 wnext[8];
       if (wbase) {  // filter row 0: tap fs
 #pragma unroll
@@ -1593,7 +1596,7 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDy,
         for (int hf = 0; hf < 2; ++hf) {  // 32 columns = one 128-byte half row
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c * 192 + fr * 64 + hf * 32), v);
-          if (wbase) {
+          if (p.P) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const __nv_bfloat162* wp2 = reinterpret_cast<const __nv_bfloat162*>(&wcur[4 * hf + k]);
@@ -1603,6 +1606,33 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDy,
                 pacc = fmaf(v[8 * k + 2 * i], wf.x, fmaf(v[8 * k + 2 * i + 1], wf.y, pacc));
               }
             }
+          }
+          if (p.Q) {
+            // column sums over the 32 output channels of this warp: transpose-reduce, after
+            // step `off` a lane keeps the half of the columns its bit `off` selects, so lane l
+            // ends with column l (31 shuffles for 32 columns)
+            float pr[32];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __nv_bfloat162* wp2 = reinterpret_cast<const __nv_bfloat162*>(&wcur[4 * hf + k]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 wf = __bfloat1622float2(wp2[i]);
+                pr[8 * k + 2 * i] = v[8 * k + 2 * i] * wf.x;
+                pr[8 * k + 2 * i + 1] = v[8 * k + 2 * i + 1] * wf.y;
+              }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send = up ? pr[i] : pr[i + off];
+                const float keep = up ? pr[i + off] : pr[i];
+                pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            qacc[hf] += pr[0];
           }
           // the bulk reduce issued from this half row one filter row ago has read it
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -1626,6 +1656,11 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmDy,
       tc_fence_before();
       mbar_arrive(smem_u32(accum_empty));  // accumulator drained: the next segment may start
       if (p.P) atomicAdd(p.P + (long long)n * p.cout + m, pacc * rsv);
+      if (p.Q) {  // (offered only without rs: a row factor would have to scale the products)
+        float* qd = p.Q + (long long)n * p.cin + nt * 128 + c * 64 + lane;
+        atomicAdd(qd, qacc[0]);
+        atomicAdd(qd + 32, qacc[1]);
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // everybody has read cs_s
       u += t1 - t0;
       ++seg;
@@ -1894,7 +1929,7 @@ static bool wgrad_row_eligible(const otm_conv_wgrad_args* a) {
 static int conv_wgrad_tc_row(const otm_conv_wgrad_args* a, cudaStream_t st) {
   const int cin = a->x.c, cout = a->dy.c;
   TcWgRowP p;
-  p.ws = a->ws; p.wfwd = (const __nv_bfloat16*)a->wfwd; p.P = a->P; p.rs = a->rs; p.cs = a->cs;
+  p.ws = a->ws; p.wfwd = (const __nv_bfloat16*)a->wfwd; p.P = a->P; p.Q = a->Q; p.rs = a->rs; p.cs = a->cs;
   p.alpha = a->alpha; p.cin = cin; p.cout = cout;
   p.x_coord_off = a->x_halo - a->pad;
   p.tiles_w = (a->dy.w + 7) / 8;
@@ -1903,6 +1938,7 @@ static int conv_wgrad_tc_row(const otm_conv_wgrad_args* a, cudaStream_t st) {
   p.units_total = (long long)a->dy.n * p.m_tiles * p.n_tiles * 3 * p.tiles_total;
   p.wfwd_n_stride = a->wfwd_batch_stride;
   if (p.P) OTM_REQUIRE(p.wfwd, "conv_wgrad: fused P needs wfwd");
+  if (p.Q) OTM_REQUIRE(p.wfwd && !p.rs, "conv_wgrad: fused Q needs wfwd and no rs");
   CUtensorMap tmX, tmDy;
   int rc = make_act_map(&tmX, a->x, a->x_halo, 8, 10);
   if (rc) return rc;
@@ -1923,6 +1959,8 @@ static int conv_wgrad_tc_row(const otm_conv_wgrad_args* a, cudaStream_t st) {
 
 int conv_wgrad_tc(const otm_conv_wgrad_args* a, cudaStream_t st) {
   if (wgrad_row_eligible(a)) return conv_wgrad_tc_row(a, st);
+  OTM_REQUIRE(!a->Q, "conv_wgrad: the fused Q term is not available for this launch "
+                     "(ask otm_conv_wgrad_fuses_Q first)");
   const int cin = a->x.c, cout = a->dy.c;
   TcWgP p;
   p.dw = a->dw; p.rs = a->rs; p.cs = a->cs; p.alpha = a->alpha;
@@ -2065,6 +2103,11 @@ int otm_conv_wgrad_fuses_P(const otm_conv_wgrad_args* a) {
   return (a->dy.c % 128 == 0) ? 1 : 0;
 }
 
+int otm_conv_wgrad_fuses_Q(const otm_conv_wgrad_args* a) {
+  if (!a || a->path == OTM_PATH_SIMT || !conv_wgrad_tc_eligible(a)) return 0;
+  return (a->kh == 3 && a->kw == 3 && a->x.c % 128 == 0 && a->dy.c % 128 == 0 && !a->rs) ? 1 : 0;
+}
+
 int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   OTM_REQUIRE(a && a->x.ptr && a->dy.ptr && a->dw, "conv_wgrad: null argument");
@@ -2077,7 +2120,7 @@ int otm_conv_wgrad(const otm_conv_wgrad_args* a, otm_stream stream) {
   if (a->path == OTM_PATH_TCGEN05 && !tc)
     return fail(OTM_ERR_UNSUPPORTED, "conv_wgrad: tcgen05 path not available for this shape/dtype");
   if (tc && a->path != OTM_PATH_SIMT) return conv_wgrad_tc(a, st);
-  OTM_REQUIRE(!a->P, "conv_wgrad: the fused P term is only available on the tcgen05 path");
+  OTM_REQUIRE(!a->P && !a->Q, "conv_wgrad: the fused P / Q terms are only available on the tcgen05 path");
   return conv_wgrad_simt(a, st);
 }
 

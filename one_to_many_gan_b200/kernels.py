@@ -170,7 +170,7 @@ def dgrad_reflect_fuses_gate(g, wpack_t, cin, per_sample=False) -> bool:
 
 
 def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None, path=PATH_AUTO,
-               use_ws=True, wfwd=None, P=None, wfwd_per_sample=True):
+               use_ws=True, wfwd=None, P=None, wfwd_per_sample=True, Q=None):
     """P (zeroed [n, Cout] fp32) + wfwd (forward pack: per-sample, or the shared one when x
     already carries the modulation): also accumulate the demodulation term sum_hw dy*y in the
     epilogue (check wgrad_fuses_P first)."""
@@ -192,6 +192,7 @@ def conv_wgrad(x, dy, dw, kh, kw, pad, *, x_halo=0, alpha=1.0, rs=None, cs=None,
     a.ws = L.ptr(ws)
     a.wfwd = L.ptr(wfwd)
     a.P = L.ptr(P)
+    a.Q = L.ptr(Q)
     a.wfwd_batch_stride = dw.numel() if (wfwd is not None and wfwd_per_sample) else 0
     L.check(L.lib.otm_conv_wgrad(_byref(a), L.stream_ptr()), "otm_conv_wgrad")
     return dw
@@ -229,6 +230,17 @@ def wgrad_fuses_P(x, dy, kh, kw, pad, x_halo=0) -> bool:
     a.kh, a.kw, a.pad = kh, kw, pad
     a.path = PATH_AUTO
     return bool(L.lib.otm_conv_wgrad_fuses_P(_byref(a)))
+
+
+def wgrad_fuses_Q(x, dy, kh, kw, pad, x_halo=0) -> bool:
+    """Can conv_wgrad(..., Q=) reduce the direct style-gradient term in its epilogue (rs=None)?"""
+    a = L.ConvWgradArgs()
+    a.x = L.tdesc(x)
+    a.x_halo = x_halo
+    a.dy = L.tdesc(dy)
+    a.kh, a.kw, a.pad = kh, kw, pad
+    a.path = PATH_AUTO
+    return bool(L.lib.otm_conv_wgrad_fuses_Q(_byref(a)))
 
 
 def weight_pack(w, alpha, dtype, *, cs=None, rs=None, nb=1, transpose=False):

@@ -503,6 +503,17 @@ class ModResBlockFn(torch.autograd.Function):
         ds2 = K.mod_bwd(w2.detach(), c2, s2, sig2, _sqsum(w2), P2, Qt2, dw2, q_scaled=True)
         # ---- conv1: dy = gu1 (w.r.t. its raw output), P1 == Qt2 --------------------------------
         dw1, dw1_ret = _wgrad_buffer(w1)
+        if direct and K.wgrad_fuses_Q(x, gu1, 3, 3, 1, 1):
+            # Q1 = sum_hw (dL/d(s1 x)) * x is a column reduction of the per-sample accumulator the
+            # wgrad kernel already holds; the dgrad's epilogue applies s1 and adds the skip
+            # gradient: conv1 needs no input-side pass at all
+            Q1 = torch.zeros((n, f), dtype=torch.float32, device=x.device)
+            K.conv_wgrad(x, gu1, dw1, 3, 3, 1, x_halo=1, alpha=c1, cs=s1,
+                         wfwd=_pack(w1, x.dtype, False), Q=Q1, wfwd_per_sample=False)
+            gx = (K.conv_dgrad_reflect(gu1, _pack(w1, g.dtype, True), f, residual=g, row_scale=s1)
+                  if ctx.needs_input_grad[0] else None)
+            ds1 = K.mod_bwd(w1.detach(), c1, s1, sig1, _sqsum(w1), Qt2, Q1, dw1)
+            return gx, ds1, ds2, dw1_ret, dw2_ret, None
         K.conv_wgrad(x, gu1, dw1, 3, 3, 1, x_halo=1, alpha=c1, cs=s1)
         if direct:
             gxt = K.conv_dgrad_reflect(gu1, _pack(w1, g.dtype, True), f)

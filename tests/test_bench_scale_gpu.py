@@ -514,3 +514,31 @@ def test_conv_fwd_dot_vs_torch(K, case):
     y, dot = r
     assert relerr(y.float(), ref) < 5e-3
     assert relerr(dot, (ref * aux).sum((2, 3))) < 2e-3
+
+
+@pytest.mark.parametrize("case", [(96, 128, 128, 64, 64), (10, 256, 128, 40, 24)])
+def test_wgrad_fused_Q_vs_torch(K, case):
+    """The direct style-gradient term Q[n,i] = sum_hw (dL/d(s x)) * x of a modulated conv's
+    un-modulated input from the wgrad epilogue (column reduction of the per-sample accumulator
+    against the shared forward pack), vs autograd: conv1 of ModulatedResnetBlock's backward."""
+    n, cin, cout, H, W = case
+    alpha = 1 / math.sqrt(cin * 9)
+    x = q(rnd(n, cin, H, W, seed=3))
+    w = rnd(cout, cin, 3, 3, seed=4)
+    s = rnd(n, cin, seed=5) * 0.3 + 1
+    dy = q(rnd(n, cout, H, W, seed=6))
+    wp = K.weight_pack(w, alpha, BF)                       # shared pack [cout][3][3][cin] bf16
+    wq = wp[0].permute(0, 3, 1, 2).float()                 # the rounded alpha * w the kernel reads
+    # u = conv(reflpad(s * x), alpha w);  Q = d<dy, u>/ds
+    sv = s.clone().requires_grad_(True)
+    u = F.conv2d(F.pad(x * sv[:, :, None, None], (1,) * 4, mode="reflect"), wq)
+    (Q_ref,) = torch.autograd.grad(u, sv, dy)
+    ref = torch.nn.grad.conv2d_weight(F.pad(x, (1,) * 4, mode="reflect") * s[:, :, None, None],
+                                      (cout, cin, 3, 3), dy) * alpha
+    xt, dyt = nhwc(x, BF, 1), nhwc(dy, BF)
+    assert K.wgrad_fuses_Q(xt, dyt, 3, 3, 1, 1)
+    dw = torch.zeros_like(w)
+    Q = torch.zeros(n, cin, device="cuda")
+    K.conv_wgrad(xt, dyt, dw, 3, 3, 1, x_halo=1, alpha=alpha, cs=s, wfwd=wp, Q=Q, wfwd_per_sample=False)
+    assert relerr(dw, ref) < 5e-4
+    assert relerr(Q, Q_ref) < 2e-3
