@@ -203,6 +203,10 @@ typedef struct {
   int32_t out_dtype;
 } otm_weight_pack_args;
 int otm_weight_pack(const otm_weight_pack_args* a, otm_stream stream);
+/* njobs SHARED packs (nb == 1, cs == rs == NULL, one out_dtype, inner packed dimension a multiple
+ * of 8) in one launch: every staged pack of a network right after its optimiser step
+ * (reference train.py:94-116 -> EqualisedWeight.forward layers.py:23-24 of the next iteration). */
+int otm_weight_pack_multi(const otm_weight_pack_args* jobs, int32_t njobs, otm_stream stream);
 
 /* q[o,i] = sum_k (alpha*w[o,i,k])^2   (layers.py:156-158, dense form SURVEY App. B.2) */
 int otm_weight_sqsum(const float* w, int32_t cout, int32_t cin, int32_t taps, float alpha,

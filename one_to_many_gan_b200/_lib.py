@@ -266,6 +266,7 @@ SYMBOLS = {
     "otm_conv_wgrad_fuses_Q": (C.c_int, [_P(ConvWgradArgs)]),
     "otm_conv_wgrad_workspace_bytes": (C.c_int64, [_P(ConvWgradArgs)]),
     "otm_weight_pack": (C.c_int, [_P(WeightPackArgs), C.c_void_p]),
+    "otm_weight_pack_multi": (C.c_int, [_P(WeightPackArgs), C.c_int32, C.c_void_p]),
     "otm_weight_sqsum": (
         C.c_int,
         [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p],

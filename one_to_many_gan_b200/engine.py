@@ -121,6 +121,7 @@ class TrainIteration:
         self.on_decoder_grads_final = None  # test hook
         self.graph = None
         self._warm_left = warmup
+        self.packs = ops.PackRecorder()  # shared weight packs of a phase in one launch
         self.iterations = 0
 
     # ---------------------------------------------------------------- host part
@@ -186,6 +187,7 @@ class TrainIteration:
     def _d_step_and_zero(self):
         B = self.B
         ops.invalidate_packs()
+        self.packs.phase("iteration")  # every shared pack of G / D / S in one launch
         self.oD.zero_grad()
         with torch.no_grad():
             (w,) = self._style(0)
@@ -207,6 +209,7 @@ class TrainIteration:
         all-reduce hides behind the G step's encode / decode."""
         self.oD.wait_all_reduce()
         self.oD.step(reduced=True)
+        self.packs.phase("after_adam_d")  # D's packs went stale: rebuild them in one launch
 
     def _decoder_grads_final(self):
         """Autograd is about to run the encoder backward: decoder, to_style and style-extractor
@@ -256,6 +259,7 @@ class TrainIteration:
         self.oM.step(reduced=True)
         self.oS.step(reduced=True)
         ops.invalidate_packs()
+        self.packs.phase(None)
 
     def _iteration(self):
         self._d_step_and_zero()
@@ -270,6 +274,7 @@ class TrainIteration:
     def _segment_b(self):
         ops.invalidate_packs()
         self.oD.step(reduced=True)
+        self.packs.phase("segment_b")
         self._g_step(None, overlap=False)
 
     def _segment_c(self):
@@ -277,6 +282,7 @@ class TrainIteration:
         self.oM.step(reduced=True)
         self.oS.step(reduced=True)
         ops.invalidate_packs()
+        self.packs.phase(None)
 
     def _exchange(self, opts):
         for o in opts:

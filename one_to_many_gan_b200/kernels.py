@@ -261,6 +261,40 @@ def weight_pack(w, alpha, dtype, *, cs=None, rs=None, nb=1, transpose=False):
     return out
 
 
+def weight_pack_multi_ok(w, transpose: bool) -> bool:
+    cout, cin = w.shape[:2]
+    return (cout if transpose else cin) % 8 == 0
+
+
+def weight_pack_multi(jobs, dtype):
+    """jobs: [(w [Cout,Cin,kh,kw] fp32, alpha, transpose)] -> the shared packs (as weight_pack
+    returns them, [1, ...]) built by ONE launch into one buffer."""
+    es = 2 if dtype == torch.bfloat16 else 4
+    offs, total = [], 0
+    for w, _, _ in jobs:
+        offs.append(total)
+        total += (w.numel() * es + 255) // 256 * 256  # 256-byte aligned slices
+    dev = jobs[0][0].device
+    flat = torch.empty(total, dtype=torch.uint8, device=dev)
+    arr = (L.WeightPackArgs * len(jobs))()
+    outs = []
+    for k, (w, alpha, transpose) in enumerate(jobs):
+        cout, cin, kh, kw = w.shape
+        shape = (1, cin if transpose else cout, kh, kw, cout if transpose else cin)
+        out = flat[offs[k] : offs[k] + w.numel() * es].view(dtype).view(shape)
+        a = arr[k]
+        a.w = L.ptr(w)
+        a.cout, a.cin, a.kh, a.kw = cout, cin, kh, kw
+        a.alpha = alpha
+        a.nb = 1
+        a.transpose = int(transpose)
+        a.out = L.ptr(out)
+        a.out_dtype = L.dtype_code(out)
+        outs.append(out)
+    L.check(L.lib.otm_weight_pack_multi(arr, len(jobs), L.stream_ptr()), "otm_weight_pack_multi")
+    return outs
+
+
 def weight_sqsum(w, alpha):
     cout, cin, kh, kw = w.shape
     q = torch.empty((cout, cin), dtype=torch.float32, device=w.device)

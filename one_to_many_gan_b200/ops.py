@@ -62,8 +62,52 @@ def _cached(key, weight: torch.Tensor, make):
 
 def _pack(weight: torch.Tensor, dtype, transpose: bool):
     key = (weight.data_ptr(), weight._version, _EPOCH, dtype, transpose)
+    if _RECORDER is not None and key not in _PACKS and K.weight_pack_multi_ok(weight, transpose):
+        _RECORDER.note(weight, dtype, transpose)
     return _cached(key, weight, lambda: K.weight_pack(weight.detach(), eq_scale(weight), dtype,
                                                        transpose=transpose))
+
+
+class PackRecorder:
+    """Batches the shared weight packs of a repeating iteration.  The first time the iteration
+    runs, every pack that is built lazily is noted under the phase it was first needed in (a phase
+    starts where packs went stale: the start of the iteration, an optimiser step in the middle of
+    it); from then on `phase()` rebuilds all of a phase's packs with ONE launch
+    (otm_weight_pack_multi) and the lazy path only sees hits.  ~50 launches of 5 us per iteration
+    become 2.  Owned by the caller (engine.TrainIteration): nothing is shared between models."""
+
+    def __init__(self):
+        self.phases: dict = {}
+        self.current = None
+
+    def note(self, weight, dtype, transpose):
+        if self.current is None:
+            return
+        rec = self.phases.setdefault(self.current, {})
+        rec.setdefault((weight.data_ptr(), dtype, transpose), (weight, dtype, transpose))
+
+    def phase(self, name):
+        """Enter phase `name` (None: stop recording) and stage everything noted for it so far."""
+        global _RECORDER
+        _RECORDER = self if name is not None else None
+        self.current = name
+        rec = self.phases.get(name)
+        if not rec:
+            return
+        by_dtype: dict = {}
+        for weight, dtype, transpose in rec.values():
+            key = (weight.data_ptr(), weight._version, _EPOCH, dtype, transpose)
+            if key not in _PACKS:
+                by_dtype.setdefault(dtype, []).append((key, weight, transpose))
+        for dtype, jobs in by_dtype.items():
+            outs = K.weight_pack_multi([(w.detach(), eq_scale(w), t) for _, w, t in jobs], dtype)
+            for (key, w, _), out in zip(jobs, outs):
+                if len(_PACKS) > 512:
+                    _PACKS.clear()
+                _PACKS[key] = (out, w.detach(), getattr(w, "_otm_owner", None))
+
+
+_RECORDER: PackRecorder | None = None
 
 
 def _sqsum(weight: torch.Tensor):

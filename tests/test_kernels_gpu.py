@@ -475,3 +475,22 @@ def test_cast_add(K):
     assert torch.equal(b.float(), x.bfloat16().float())
     K.add_(a, nhwc(x, torch.float32))
     assert relerr(a, 2 * x) < 1e-6
+
+
+def test_weight_pack_multi_matches_single():
+    """otm_weight_pack_multi: many shared packs in one launch == otm_weight_pack one by one
+    (bit-exact: same arithmetic, same rounding)."""
+    from one_to_many_gan_b200 import kernels as K
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(128, 128, 3, 3), (64, 128, 3, 3), (128, 64, 4, 4), (256, 128, 4, 4), (64, 8, 7, 7)]
+    for dtype in (torch.bfloat16, torch.float32):
+        jobs = []
+        for i, sh in enumerate(shapes * 15):  # 75 jobs: more than one kernel-parameter table
+            w = torch.randn(*sh, generator=g, device="cuda")
+            jobs.append((w, 0.1 + 0.01 * i, bool(i % 2)))
+        outs = K.weight_pack_multi(jobs, dtype)
+        for (w, alpha, tr), out in zip(jobs, outs):
+            ref = K.weight_pack(w, alpha, dtype, transpose=tr)
+            assert out.shape == ref.shape
+            assert torch.equal(out, ref)
