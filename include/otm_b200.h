@@ -128,7 +128,7 @@ int otm_conv_fwd_fuses_gate(const otm_conv_fwd_args* a);
  *   gxp[a,b,o] = sum_{r,s,i} dy[n, a+r-1, b+s-1, i] * wpack[nb][o][r][s][i],
  *   f = row_scale * post_scale, and with `gate`: f *= (gate[n,refl(a),refl(b),o] != 0),
  *   dot_sums[n,o] += gxp * gate  (accumulated, NOT zeroed: call it after the main otm_conv_fwd).
- * bf16 only; K % 16 == 0, Cout % 64 == 0, H, W >= 3. */
+ * bf16 only; K % 64 == 0, Cout % 64 == 0, H, W >= 3. */
 typedef struct {
   otm_tensor dy;          /* [n, K, H, W]: the input of the dgrad call */
   const void* wpack;      /* [wbatch][Cout][3][3][K] (the dgrad pack of otm_weight_pack) */

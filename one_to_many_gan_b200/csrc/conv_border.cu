@@ -16,8 +16,8 @@
 //
 // CTA = (border line, 80-position chunk, 64 output channels, sample), 4 warps x 16 channels.
 // The dy line (K channels per position, zero-extended by 2) sits in shared memory once, filter tap
-// t is a row offset into it (ldmatrix A fragments); weight (B) fragments come straight from the
-// dgrad pack in global memory (each warp reads its own 16 rows, once).
+// t is a row offset into it (ldmatrix A fragments); the tap's 64 x K weight rows are staged next to
+// it (ldmatrix B fragments), both by cp.async into dense XOR-swizzled rows.
 #include "common.cuh"
 
 namespace otm {
@@ -33,11 +33,11 @@ struct BorderP {
   float* dot_sums;
   int K, C, H, W;
   int mchunks;
+  int line_rows;  // staged rows of the dy line (positions + taps + shift actually needed)
 };
 
 constexpr int BD_MT = 5;               // m16 tiles per CTA
 constexpr int BD_M = BD_MT * 16;       // positions per CTA
-constexpr int BD_ROWS = BD_M + 3;      // staged line rows: positions + 2 taps + 1 shift
 constexpr int BD_N = 64;               // output channels per CTA
 
 __device__ __forceinline__ void bd_ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
@@ -67,7 +67,7 @@ __device__ __forceinline__ void ring_target(int line, int pos, int H, int W, int
 }
 
 // line 0: top halo row (a = -1), 1: bottom (a = H), 2: left halo column (b = -1), 3: right (b = W)
-__global__ void __launch_bounds__(128) conv_reflect_border_kernel(BorderP p) {
+__global__ void __launch_bounds__(128, 6) conv_reflect_border_kernel(BorderP p) {
   extern __shared__ __align__(16) uint8_t bd_smem[];
   const int line = blockIdx.x / p.mchunks, mc = blockIdx.x % p.mchunks;
   const int n = blockIdx.z;
@@ -76,48 +76,69 @@ __global__ void __launch_bounds__(128) conv_reflect_border_kernel(BorderP p) {
   const int ext = horiz ? p.W : p.H;      // extent of the dy line
   const int p0 = mc * BD_M;
   if (p0 >= L) return;
-  const int pitch = p.K * 2 + 16;         // bytes per staged row (bank skew)
+  const int pitch = p.K * 2;              // bytes per staged row; 16-byte chunks XOR-swizzled by row & 7
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
-  // ---- stage the dy line: row j <-> line coordinate q = p0 + j - 2, zero outside [0, ext) ----
-  // cp.async: every 16-byte chunk of the line is in flight at once (a register-staged loop paid
-  // one global-load latency per chunk and thread: ~10 serialised round trips)
-  {
-    const int chunks = p.K / 8;  // 16-byte chunks per row
-    for (int idx = threadIdx.x; idx < BD_ROWS * chunks; idx += blockDim.x) {
-      const int j = idx / chunks, c8 = idx - j * chunks;
-      const int q = p0 + j - 2;
-      uint8_t* dst = bd_smem + (size_t)j * pitch + c8 * 16;
-      if (q >= 0 && q < ext) {
-        const int hh = line == 0 ? 0 : line == 1 ? p.H - 1 : q;
-        const int ww = line == 2 ? 0 : line == 3 ? p.W - 1 : q;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                         (uint32_t)__cvta_generic_to_shared(dst)),
-                     "l"(vptr<__nv_bfloat16>(p.x, n, hh, ww, c8 * 8))
-                     : "memory");
-      } else {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-      }
+  // Shared memory: the dy line, then ONE weight buffer [64 output channels][K] holding the current
+  // filter tap.  Everything arrives by 16-byte cp.async, rows are dense (pitch 2K bytes) with the
+  // 16-byte chunks XOR-swizzled by (row & 7) for conflict-free ldmatrix: 37 KB per CTA at K = 128,
+  // six CTAs per SM, so the 768 CTAs of an n = 96 launch are one wave.  (The first version read the
+  // weight fragments with 32-bit global loads -- 8 rows x 16 B per instruction -- and ncu showed
+  // half of all stall samples on the first MMA / ldmatrix after each batch of them; its 5 CTAs
+  // per SM also left a 28-CTA second wave.)
+  uint8_t* const bsm = bd_smem + (size_t)p.line_rows * pitch;
+  const __nv_bfloat16* wsample = p.wp + (long long)n * p.w_batch_stride;
+  const long long wrow = 9LL * p.K;  // elements per output channel in the pack
+  const int chunks = p.K / 8;        // 16-byte chunks per row
+  auto tap_of = [&](int t) {
+    // pack tap (r', s') a ring position sees: top r' = 2, bottom r' = 0, left s' = 2, right s' = 0
+    return line == 0 ? 6 + t : line == 1 ? t : line == 2 ? 3 * t + 2 : 3 * t;
+  };
+  auto stage_weights = [&](int t) {
+    const __nv_bfloat16* src = wsample + (long long)(blockIdx.y * BD_N) * wrow + (long long)tap_of(t) * p.K;
+    for (int idx = threadIdx.x; idx < BD_N * chunks; idx += blockDim.x) {
+      const int r = idx / chunks, c8 = idx - r * chunks;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(bsm + (size_t)r * pitch + ((c8 ^ (r & 7)) << 4))),
+                   "l"(src + (long long)r * wrow + c8 * 8)
+                   : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  // epilogue factors and the first weight fragments are fetched under the staging copies
-  const int shift = horiz ? 0 : 1;
-  const int o0 = blockIdx.y * BD_N + warp * 16;
-  float f[2][2], dot[2][2];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const long long ci = (long long)n * p.C + o0 + nt * 8 + (lane & 3) * 2 + e;
-      f[nt][e] = (p.row_scale ? p.row_scale[ci] : 1.f) * (p.post_scale ? p.post_scale[ci] : 1.f);
-      dot[nt][e] = 0.f;
+  };
+
+  // ---- stage the dy line: row j <-> line coordinate q = p0 + j - 2, zero outside [0, ext) ----
+  for (int idx = threadIdx.x; idx < p.line_rows * chunks; idx += blockDim.x) {
+    const int j = idx / chunks, c8 = idx - j * chunks;
+    const int q = p0 + j - 2;
+    uint8_t* dst = bd_smem + (size_t)j * pitch + ((c8 ^ (j & 7)) << 4);
+    if (q >= 0 && q < ext) {
+      const int hh = line == 0 ? 0 : line == 1 ? p.H - 1 : q;
+      const int ww = line == 2 ? 0 : line == 3 ? p.W - 1 : q;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(dst)),
+                   "l"(vptr<__nv_bfloat16>(p.x, n, hh, ww, c8 * 8))
+                   : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  }
+  stage_weights(0);  // one group: line + tap 0
+
+  // the gate pixels of the epilogue: towards L2 now, under the copies and the MMAs
+  if (p.gate.ptr) {
+    const int pos = p0 + (int)threadIdx.x;
+    if (threadIdx.x < BD_M && pos < L) {
+      int ta, tb;
+      ring_target(line, pos, p.H, p.W, ta, tb);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(
+          vptr<__nv_bfloat16>(p.gate, n, ta, tb, blockIdx.y * BD_N)));
+    }
+  }
 
   // ring position pos (line-local, pos = p0 + m) reads line coordinates pos + t - 2 + shift,
   // t = 0..2: horizontal lines have pos = b + 1 (b = -1 .. W), vertical ones pos = a (a = 0 .. H-1)
+  const int shift = horiz ? 0 : 1;
+  const int o0 = blockIdx.y * BD_N + warp * 16;
   float acc[BD_MT][2][4];
 #pragma unroll
   for (int a = 0; a < BD_MT; ++a)
@@ -127,38 +148,48 @@ __global__ void __launch_bounds__(128) conv_reflect_border_kernel(BorderP p) {
       for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
 
   const int mt_n = min(BD_MT, (L - p0 + 15) / 16);  // m16 tiles that hold ring positions
-  const __nv_bfloat16* wsample = p.wp + (long long)n * p.w_batch_stride;
-  const long long wrow = 9LL * p.K;  // elements per output channel in the pack
 #pragma unroll 1
   for (int t = 0; t < 3; ++t) {
-    // pack tap (r', s') a ring position sees: top r' = 2, bottom r' = 0, left s' = 2, right s' = 0
-    const int tap = line == 0 ? 6 + t : line == 1 ? t : line == 2 ? 3 * t + 2 : 3 * t;
-    const __nv_bfloat16* w0 = wsample + (long long)(o0 + (lane >> 2)) * wrow + (long long)tap * p.K +
-                              (lane & 3) * 2;
-    const uint8_t* arow = bd_smem + (size_t)(t + shift + (lane & 7) + ((lane >> 3) & 1) * 8) * pitch +
-                          (lane >> 4) * 16;
-#pragma unroll 4
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tap t's weights (and, for t = 0, the line) have landed
+    // A fragment rows: t + shift + mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1); row & 7 below
+    const int a_sw = (t + shift + (lane & 7)) & 7;
+    const uint8_t* arow = bd_smem + (size_t)(t + shift + (lane & 7) + ((lane >> 3) & 1) * 8) * pitch;
+    // B fragments of this warp's two n8 tiles: matrices (rows +0..7, k 0..7), (+0..7, k 8..15),
+    // (+8..15, k 0..7), (+8..15, k 8..15) = b0[0], b0[1], b1[0], b1[1]; row & 7 == lane & 7
+    const uint8_t* brow = bsm + (size_t)(warp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * pitch;
+#pragma unroll 2
     for (int kc = 0; kc < p.K / 16; ++kc) {
-      uint32_t b[2][2];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const __nv_bfloat16* wq = w0 + (long long)nt * 8 * wrow + kc * 16;
-        b[nt][0] = __ldg(reinterpret_cast<const unsigned int*>(wq));
-        b[nt][1] = __ldg(reinterpret_cast<const unsigned int*>(wq + 8));
-      }
+      uint32_t bq[4];
+      bd_ldmatrix_x4(bq, brow + (((kc * 2 + ((lane >> 3) & 1)) ^ (lane & 7)) << 4));
+      const uint32_t b0[2] = {bq[0], bq[1]}, b1[2] = {bq[2], bq[3]};
+      const int a_off = ((kc * 2 + (lane >> 4)) ^ a_sw) << 4;
 #pragma unroll
       for (int mt = 0; mt < BD_MT; ++mt) {
         if (mt < mt_n) {  // (warp-uniform) a 64-position vertical line has no fifth tile
           uint32_t a[4];
-          bd_ldmatrix_x4(a, arow + (size_t)(mt * 16) * pitch + kc * 32);
-          bd_mma(acc[mt][0], a, b[0]);
-          bd_mma(acc[mt][1], a, b[1]);
+          bd_ldmatrix_x4(a, arow + (size_t)(mt * 16) * pitch + a_off);
+          bd_mma(acc[mt][0], a, b0);
+          bd_mma(acc[mt][1], a, b1);
         }
       }
+    }
+    if (t < 2) {
+      __syncthreads();  // every warp is done with tap t's weights
+      stage_weights(t + 1);
     }
   }
 
   // ---- epilogue: scale / gate / dot, packed-bf16 atomic add onto the reflected target ----
+  float f[2][2], dot[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const long long ci = (long long)n * p.C + o0 + nt * 8 + (lane & 3) * 2 + e;
+      f[nt][e] = (p.row_scale ? p.row_scale[ci] : 1.f) * (p.post_scale ? p.post_scale[ci] : 1.f);
+      dot[nt][e] = 0.f;
+    }
   // all gate values first (independent loads in flight together), then the math and the reds
   uint32_t gv[BD_MT][2][2];
   if (p.gate.ptr) {
@@ -238,8 +269,8 @@ extern "C" int otm_conv_reflect_border(const otm_conv_reflect_border_args* a, ot
   OTM_REQUIRE(a->y.h >= 3 && a->y.w >= 3, "conv_reflect_border: image smaller than 3x3");
   OTM_REQUIRE(bd_tensor_ok(a->dy) && bd_tensor_ok(a->y), "conv_reflect_border: bf16 NHWC tensors with "
               "16-byte aligned pixels required");
-  OTM_REQUIRE(a->dy.c % 16 == 0 && a->y.c % BD_N == 0,
-              "conv_reflect_border: K (%d) must be a multiple of 16 and Cout (%d) of %d", a->dy.c,
+  OTM_REQUIRE(a->dy.c % 64 == 0 && a->y.c % BD_N == 0,
+              "conv_reflect_border: K (%d) must be a multiple of 64 and Cout (%d) of %d", a->dy.c,
               a->y.c, BD_N);
   OTM_REQUIRE((uintptr_t)a->wpack % 4 == 0, "conv_reflect_border: unaligned pack");
   OTM_REQUIRE(a->w_batch_stride == 0 || a->w_batch_stride == 9LL * a->dy.c * a->y.c,
@@ -261,10 +292,27 @@ extern "C" int otm_conv_reflect_border(const otm_conv_reflect_border_args* a, ot
   p.K = a->dy.c; p.C = a->y.c; p.H = a->y.h; p.W = a->y.w;
   const int lmax = (p.W + 2 > p.H) ? p.W + 2 : p.H;
   p.mchunks = (lmax + BD_M - 1) / BD_M;
-  const int smem = BD_ROWS * (p.K * 2 + 16);
-  OTM_REQUIRE(smem <= 200 * 1024, "conv_reflect_border: K = %d too large", p.K);
+  // staged line rows: positions of the fullest chunk + 2 tap rows (+ 1 for vertical lines)
+  auto rows_for = [](int L, int extra) { int m = ((L < BD_M ? L : BD_M) + 15) / 16 * 16; return m + 2 + extra; };
+  const int rh = rows_for(p.W + 2, 0), rv = rows_for(p.H, 1);
+  p.line_rows = rh > rv ? rh : rv;
+  const int smem = (p.line_rows + BD_N) * (p.K * 2);  // dy line + one weight tap
+  OTM_REQUIRE(smem <= 224 * 1024, "conv_reflect_border: K = %d too large", p.K);
   auto kern = conv_reflect_border_kernel;
-  if (smem > 48 * 1024) OTM_ENSURE_SMEM(kern, 200 * 1024);  // one ceiling: the attribute is not additive
+  if (smem > 48 * 1024) OTM_ENSURE_SMEM(kern, 224 * 1024);  // one ceiling: the attribute is not additive
+  {
+    // 768 CTAs (n = 96) must be ONE wave: 6 CTAs per SM need the large shared-memory carve-out
+    // (ncu showed 5 per SM by shared memory AND by registers: a 28-CTA second wave doubled the time)
+    static std::atomic<unsigned long long> carve_done{0};
+    int dev = 0;
+    OTM_CHECK_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(carve_done.load(std::memory_order_acquire) & bit)) {
+      OTM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+      carve_done.fetch_or(bit, std::memory_order_release);
+    }
+  }
   dim3 grid(4 * p.mchunks, p.C / BD_N, p.y.n);
   kern<<<grid, 128, smem, st>>>(p);
   OTM_LAUNCH_CHECK();

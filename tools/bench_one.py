@@ -24,6 +24,8 @@ sig = torch.rand(n, c, device=dev) + 0.5
 alpha = 1 / math.sqrt(c * 9)
 wp = K.weight_pack(w, alpha, torch.bfloat16, cs=s, nb=n)
 wp1 = K.weight_pack(w, alpha, torch.bfloat16)
+wpt = K.weight_pack(w, alpha, torch.bfloat16, rs=sig, nb=n, transpose=True)
+wpt1 = K.weight_pack(w, alpha, torch.bfloat16, transpose=True)
 y = K.alloc(n, c, hw, hw, torch.bfloat16, dev, 1)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 flops = 2.0 * n * hw * hw * c * c * 9
@@ -32,6 +34,14 @@ forms = {
     "per_sample": lambda: K.conv_fwd(x, wp, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, act=K.ACT_RELU,
                                      post_scale=s, per_sample=True, out=y),
     "plain": lambda: K.conv_fwd(x, wp1, c, 3, 3, 1, x_halo=1, out=y),
+    # backward of a ModulatedResnetBlock (reflect-pad dgrad = same-size launch + halo-ring launch):
+    # conv2's dgrad with the fused input-side pass (per-sample packs, gate, dot) ...
+    "dgrad_gate": lambda: K.conv_dgrad_reflect(x, wpt, c, per_sample=True, gate=res, row_scale=s,
+                                               post_scale=sig, want_dot=True),
+    # ... conv1's dgrad (shared pack, s1 as row scale, skip gradient as residual)
+    "dgrad_residual": lambda: K.conv_dgrad_reflect(x, wpt1, c, residual=res, row_scale=s),
+    # the round-2 form of the same gradient: padded 66x66 dgrad (folded by the next pass)
+    "dgrad_padded": lambda: K.conv_fwd(x, wpt1, c, 3, 3, 2),
 }
 if only:
     forms[only]()
