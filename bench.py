@@ -45,7 +45,7 @@ WORKLOAD = "G+D train iteration, default arch, 128x128, batch 32/GPU, bf16 act /
 # dense-conv algorithmic GFLOP per image per iteration for the extra configs
 GFLOP_256 = 1441.2
 # dram bytes (read + write) of the roofline launch: profiles/r2_ncu_conv_tc_fwd_rr2t_residual.md
-NCU_TRAFFIC_RESIDUAL = 285.7e6
+NCU_TRAFFIC_RESIDUAL = 282.1e6
 
 
 def base_config(world):
