@@ -233,8 +233,18 @@ def dominant_kernel_roofline(device):
         K.conv_fwd(x, wp_sample, c, 3, 3, 1, x_halo=1, y_halo=1, row_scale=sig, act=K.ACT_RELU,
                    post_scale=s, per_sample=True, out=y)
 
-    def plain():  # dgrad: shared flipped pack, no epilogue work
+    def plain():  # shared pack, no epilogue work (encoder ResnetBlock convs, plain dgrads)
         K.conv_fwd(x, wp_shared, c, 3, 3, 1, x_halo=1, out=y)
+
+    wpt_sample = K.weight_pack(w, alpha, torch.bfloat16, rs=sig, nb=n, transpose=True)
+    wpt_shared = K.weight_pack(w, alpha, torch.bfloat16, transpose=True)
+
+    def dgrad_gate():  # conv2's dgrad through ReflectionPad2d(1): gate + dot epilogue, + ring launch
+        K.conv_dgrad_reflect(x, wpt_sample, c, per_sample=True, gate=res, row_scale=s, post_scale=sig,
+                             want_dot=True)
+
+    def dgrad_residual():  # conv1's dgrad: s1 row scale, skip gradient as residual, + ring launch
+        K.conv_dgrad_reflect(x, wpt_shared, c, residual=res, row_scale=s)
 
     def timed(fn):
         fn()
@@ -255,8 +265,10 @@ def dominant_kernel_roofline(device):
     ms = timed(residual)
     ach = flops / ms / 1e9
     forms = {}
-    for name, fn, cnt in (("per_sample_weights_relu_poststyle_halo", per_sample, 20),
-                          ("shared_weights_bare", plain, 30)):
+    for name, fn, cnt in (("per_sample_weights_relu_poststyle_halo", per_sample, 12),
+                          ("shared_weights_bare", plain, 18),
+                          ("reflect_dgrad_gate_dot_per_sample_plus_ring_launch", dgrad_gate, 8),
+                          ("reflect_dgrad_rowscale_residual_plus_ring_launch", dgrad_residual, 12)):
         t = timed(fn)
         forms[name] = {"achieved": round(flops / t / 1e9, 1), "frac": round(flops / t / 1e9 / peak, 4),
                        "launch_ms": round(t, 4), "launches_per_iteration": cnt}
