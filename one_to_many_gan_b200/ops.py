@@ -322,6 +322,65 @@ def up(x):
     return UpFn.apply(x)
 
 
+class StackHaloFn(torch.autograd.Function):
+    """Batch ranges of a halo-carrying tensor stacked along the batch, halo included:
+    out = cat([src[a : a + k] for (a, k) in blocks]) as straight copies of the padded NHWC
+    buffers.  The step batches its three decodes and its two path-length extractions this way
+    (training.generator_losses); `torch.cat` on the interior views wrote an NCHW tensor that
+    then needed a transposing copy and a halo pass (and the three matching passes in backward)."""
+
+    @staticmethod
+    def forward(ctx, src, blocks, halo):
+        n = sum(k for _, k in blocks)
+        _, c, h, w = src.shape
+        out = K.alloc(n, c, h, w, src.dtype, src.device, halo)
+        dst, sp = K.padded_view(out, halo), K.padded_view(src, halo)
+        off = 0
+        for a, k in blocks:
+            dst[off : off + k].copy_(sp[a : a + k])
+            off += k
+        ctx.blocks, ctx.n_src = blocks, src.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = nhwc(g)
+        _, c, h, w = g.shape
+        gs = K.alloc(ctx.n_src, c, h, w, g.dtype, g.device)
+        covered = [False] * ctx.n_src
+        off = 0
+        for a, k in ctx.blocks:
+            if not any(covered[a : a + k]):
+                gs[a : a + k].copy_(g[off : off + k])
+            elif all(covered[a : a + k]):
+                gs[a : a + k].add_(g[off : off + k])
+            else:
+                raise ValueError("stack_halo: partially overlapping blocks")
+            covered[a : a + k] = [True] * k
+            off += k
+        if not all(covered):  # batch entries no block reads get a zero gradient
+            i = 0
+            while i < ctx.n_src:
+                if covered[i]:
+                    i += 1
+                    continue
+                j = i
+                while j < ctx.n_src and not covered[j]:
+                    j += 1
+                gs[i:j].zero_()
+                i = j
+        return gs, None, None
+
+
+def stack_halo(src, blocks):
+    """src: tensor whose producer materialised a reflect halo (halo_of(src) > 0); blocks:
+    [(start, length)] batch ranges.  Returns the stacked tensor with the same halo."""
+    halo = halo_of(src)
+    if halo <= 0:
+        raise ValueError("stack_halo needs a tensor with a materialised halo")
+    return with_halo(StackHaloFn.apply(src, tuple(blocks), halo), halo)
+
+
 class ResBlockFn(torch.autograd.Function):
     """ResnetBlock (reference blocks.py:9-33): x + IN(conv(refl(ReLU(IN(conv(refl(x))))))).
     x carries a reflect halo of 1."""

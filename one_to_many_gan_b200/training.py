@@ -198,9 +198,15 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
     identity_w = real_shoemark_w.expand(nb, *real_shoemark_w.shape)
 
     # reconstruction / identity / translation as one 3B decode
+    # (K = 1 and a halo-carrying latent: the batches are stacked as copies of the padded NHWC
+    # buffer, ops.stack_halo; otherwise plain torch.cat, which decode() re-lays out)
+    stacked = n_sty == 1 and ops.halo_of(combined_latents) > 0
     shoeprint_latent_k = (shoeprint_latent if n_sty == 1
                           else shoeprint_latent.repeat_interleave(n_sty, dim=0))
-    dec_latents = torch.cat([shoeprint_latent, shoemark_latent, shoeprint_latent_k], dim=0)
+    if stacked:
+        dec_latents = ops.stack_halo(combined_latents, [(0, 2 * batch), (0, batch)])
+    else:
+        dec_latents = torch.cat([shoeprint_latent, shoemark_latent, shoeprint_latent_k], dim=0)
     dec_w = torch.cat([reconstruct_w, identity_w, translation_w], dim=1)
     images = generator.decode(dec_latents, dec_w)
     reconstruction_loss, rec_raw = ops.l1(images[:batch], prints, opt["reconstruction_loss_lambda"])
@@ -226,8 +232,9 @@ def generator_losses(config, generator, discriminator, style_extractor, prints, 
                                             opt["style_cycle_loss_lambda"])
 
     # path length: two extractions of the same latent as one 2B batch
-    feats = generator.extract(torch.cat([shoeprint_latent_k, shoeprint_latent_k], dim=0),
-                              torch.cat([w1, w2], dim=1))
+    ext_latents = (ops.stack_halo(combined_latents, [(0, batch), (0, batch)]) if stacked
+                   else torch.cat([shoeprint_latent_k, shoeprint_latent_k], dim=0))
+    feats = generator.extract(ext_latents, torch.cat([w1, w2], dim=1))
     path_loss, path_raw = ops.path(feats, cent_fin_diff_h, opt["path_loss_lambda"])
 
     total = gan_loss + identity_loss + reconstruction_loss + kl_loss + path_loss + style_loss
