@@ -61,3 +61,28 @@ def test_same_dgrad_plus_ring_equals_reflect_pad_backward(H, W):
     same = F.conv2d(dy, wp.permute(0, 3, 1, 2), padding=1)
     got = same[0] + ring_correction(dy[0], wp)
     assert torch.allclose(got, gx_ref[0], atol=1e-12)
+
+
+def test_style_gradient_terms_are_reductions_of_the_per_sample_weight_gradient():
+    """The identities behind otm_conv_wgrad_args.P / .Q, in fp64 against
+    autograd on the reference's formulation of a modulated conv (layers.py:145-182):
+        u[n,o] = sigma[n,o] * conv(reflpad(s[n,i] * x[n,i]), cW)[o]
+        G_n[o,i,t] = sum_hw dy[n,o,hw] * xpad[n,i,hw+t]        (what the wgrad kernel accumulates)
+        Q[n,i] = sum_{o,t} sigma[n,o] * G_n[o,i,t] * cW[o,i,t]  == dL/ds[n,i] at fixed sigma
+        P[n,o] = sigma[n,o] * sum_{i,t} G_n[o,i,t] * cW[o,i,t] * s[n,i]  == sum_hw dy * u
+    so neither needs a pass over the activations once G_n sits in the accumulator."""
+    torch.manual_seed(1)
+    n, cin, cout, H, W = 3, 4, 5, 6, 7
+    x = torch.randn(n, cin, H, W, dtype=torch.float64)
+    w = torch.randn(cout, cin, 3, 3, dtype=torch.float64)
+    s = torch.randn(n, cin, dtype=torch.float64, requires_grad=True)
+    sigma = torch.rand(n, cout, dtype=torch.float64) + 0.5
+    dy = torch.randn(n, cout, H, W, dtype=torch.float64)
+    xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    u = F.conv2d(xp * s[:, :, None, None], w) * sigma[:, :, None, None]
+    (ds,) = torch.autograd.grad(u, s, dy)
+    G = torch.stack([torch.nn.grad.conv2d_weight(xp[b : b + 1], w.shape, dy[b : b + 1]) for b in range(n)])
+    Q = torch.einsum("no,noikl,oikl->ni", sigma, G, w)
+    P = sigma * torch.einsum("noikl,oikl,ni->no", G, w, s.detach())
+    assert torch.allclose(Q, ds, atol=1e-10)
+    assert torch.allclose(P, (dy * u.detach()).sum((2, 3)), atol=1e-10)
